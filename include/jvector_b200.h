@@ -1,0 +1,198 @@
+/*
+ * jvector_b200.h — C ABI of libjvector_b200.so, the B200 (sm_100a) replacement for JVector's libjvector.so.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) The 24 symbols of the reference's native library, with identical C signatures, so the library can be
+ *      installed as `libjvector.so` under jvector-native unchanged. They replace
+ *      /root/reference/jvector-native/src/main/native/src/jvector_simd_kernel_list.h:35-61 and
+ *      src/jvector_simd.h:47,53. The reference binds them with Linker.Option.critical(true) on on-heap segments
+ *      (jvector-native/src/main/java/.../cnative/NativeSimdOps.java:1164,1226,...), i.e. they must be short,
+ *      synchronous, host-memory functions; they are the n = 1 case and stay on the host by contract.
+ *
+ *  (2) The batched GPU entry points (prefix jv_) that the GPU-backed VectorizationProvider / ScoreFunction
+ *      implementations bind with ordinary (non-critical) downcall handles: data sets are registered once and
+ *      live in HBM; each hop / rerank list / multi-query step / whole search batch is ONE call.
+ *      They replace the per-candidate call sites
+ *        base:graph/OnHeapGraphIndex.java:475-483, base:graph/disk/OnDiskGraphIndex.java:639-661 (neighbour loop),
+ *        base:graph/NodeQueue.java:168-188 (rerank loop), base:quantization/PQDecoder.java:48-53 (LUT build),
+ *        base:graph/GraphIndexBuilder.java:830-835, base:graph/diversity/VamanaDiversityProvider.java:56-95,
+ *        base:graph/GraphSearcher.java:263-282,406-457 (whole traversal, device resident).
+ *      (`base:` = jvector-base/src/main/java/io/github/jbellis/jvector/)
+ *
+ * Conventions for group (2): every function returns an int status (0 = JV_OK, negative = error) and never throws
+ * or aborts across the ABI; jv_last_error() returns a thread-local message. All pointer arguments are HOST
+ * pointers borrowed for the duration of the call unless the name ends in _device. Scores are the reference's
+ * similarity scores (base:vector/VectorSimilarityFunction.java:37-69), higher = closer. Top-k keys are the
+ * reference's 64-bit ordering key (base:graph/NodeQueue.java:125-137). No CPU fallback exists: without an
+ * sm_100 device jv_gpu_init() fails and every other jv_ call returns JV_ERR_NO_DEVICE.
+ */
+#ifndef JVECTOR_B200_H
+#define JVECTOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JV_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) legacy libjvector.so ABI — jvector_simd_kernel_list.h:35-61
+ * ---------------------------------------------------------------------------------------------- */
+JV_API float cosine_f32(const float *a, size_t aoffset, const float *b, size_t boffset, size_t length);
+JV_API float dot_product_f32(const float *a, size_t aoffset, const float *b, size_t boffset, size_t length);
+JV_API float euclidean_f32(const float *a, size_t aoffset, const float *b, size_t boffset, size_t length);
+JV_API void add_in_place_f32(float *v1, const float *v2, size_t length);
+JV_API void add_scalar_in_place_f32(float *v1, float value, size_t length);
+JV_API void sub_in_place_f32(float *v1, const float *v2, size_t length);
+JV_API void sub_scalar_in_place_f32(float *v1, float value, size_t length);
+JV_API float max_f32(const float *v, size_t length);
+JV_API void min_in_place_f32(float *v1, const float *v2, size_t length);
+JV_API float assemble_and_sum_f32(const float *data, int dataBase, const unsigned char *baseOffsets, int baseOffsetsOffset, size_t baseOffsetsLength);
+JV_API float assemble_and_sum_pq_f32(const float *data, size_t subspaceCount, const unsigned char *baseOffsets1, int baseOffsetsOffset1, const unsigned char *baseOffsets2, int baseOffsetsOffset2, int clusterCount);
+JV_API float pq_decoded_cosine_similarity_f32(const unsigned char *baseOffsets, int baseOffsetsOffset, size_t baseOffsetsLength, int clusterCount, const float *partialSums, const float *aMagnitude, float bMagnitude);
+JV_API void calculate_partial_sums_dot_f32(const float *codebook, int codebookIndex, size_t size, int clusterCount, const float *query, int queryOffset, float *partialSums);
+JV_API void calculate_partial_sums_euclidean_f32(const float *codebook, int codebookIndex, size_t size, int clusterCount, const float *query, int queryOffset, float *partialSums);
+JV_API void calculate_partial_sums_self_magnitude_f32(const float *codebook, int codebookIndex, size_t size, int clusterCount, float *partialSums);
+JV_API void nvq_quantize_8bit(const float *vector, size_t length, float alpha, float x0, float minValue, float maxValue, unsigned char *destination);
+JV_API float nvq_loss(const float *vector, size_t length, float alpha, float x0, float minValue, float maxValue, int nBits);
+JV_API float nvq_uniform_loss(const float *vector, size_t length, float minValue, float maxValue, int nBits);
+JV_API float nvq_square_l2_distance_8bit(const float *vector, const unsigned char *quantized, size_t length, float alpha, float x0, float minValue, float maxValue);
+JV_API float nvq_dot_product_8bit(const float *vector, const unsigned char *quantized, size_t length, float alpha, float x0, float minValue, float maxValue);
+JV_API int64_t nvq_cosine_8bit_packed(const float *vector, const unsigned char *quantized, size_t length, float alpha, float x0, float minValue, float maxValue, const float *centroid);
+/* no-op here: this library reads NVQ bytes in natural order (as base:vector/DefaultVectorUtilSupport.java:454) */
+JV_API void nvq_shuffle_query_in_place_8bit(float *vector, size_t length);
+/* jvector_simd.h:47,53 — reflected on by base:vector/VectorizationProvider.java:132-136 */
+JV_API const char *jvector_simd_get_active_isa(void);
+JV_API const char *jvector_simd_get_max_isa_env(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) batched GPU ABI
+ * ---------------------------------------------------------------------------------------------- */
+enum { JV_EUCLIDEAN = 0, JV_DOT_PRODUCT = 1, JV_COSINE = 2 }; /* VectorSimilarityFunction ordinal order */
+
+enum {
+    JV_OK = 0,
+    JV_ERR_NO_DEVICE = -1,   /* no CUDA device / not sm_100 / jv_gpu_init not called */
+    JV_ERR_INVALID = -2,     /* bad argument */
+    JV_ERR_CUDA = -3,        /* CUDA runtime error, see jv_last_error() */
+    JV_ERR_OOM = -4,
+    JV_ERR_UNSUPPORTED = -5, /* combination not implemented (e.g. metric for BQ other than Hamming score) */
+    JV_ERR_OVERFLOW = -6     /* device scratch (visited table, candidate list) too small even after retry */
+};
+
+typedef struct jv_dataset_s *jv_dataset; /* vectors / codes resident in HBM */
+typedef struct jv_query_s *jv_query;     /* one query prepared against one data set (LUT / bits / shifted copy) */
+typedef struct jv_graph_s *jv_graph;     /* adjacency resident in HBM */
+
+JV_API int jv_gpu_init(int device);      /* bind the calling process to CUDA device `device`; idempotent */
+JV_API int jv_gpu_device_count(void);
+JV_API const char *jv_last_error(void);
+JV_API const char *jv_version(void);
+JV_API int jv_gpu_sm_count(void);
+
+/* ---- data sets (the RandomAccessVectorValues / CompressedVectors a ScoreFunction reads) ---- */
+/* rows: [n][dim] fp32 row-major (base:graph/RandomAccessVectorValues.java) */
+JV_API int jv_dataset_register_f32(const float *rows, int64_t n, int dim, jv_dataset *out);
+/* PQVectors: codes [n][M] u8 (base:quantization/PQVectors.java:377-395), codebooks concatenated in sub-space order,
+ * codebook m = k * size_m floats [k][size_m] (ProductQuantization.java:66), sub-vector sizes per
+ * ProductQuantization.java:535-550, centroid = globalCentroid or NULL */
+JV_API int jv_dataset_register_pq(const uint8_t *codes, int64_t n, int dim, int M, int k, const float *codebooks,
+                                  const float *centroid, jv_dataset *out);
+/* BQVectors: words [n][ceil(dim/64)] u64, bit j of word i = (v[64 i + j] > 0) (BinaryQuantization.java:96-109) */
+JV_API int jv_dataset_register_bq(const uint64_t *words, int64_t n, int dim, jv_dataset *out);
+/* NVQVectors, 8 bit: bytes [n][dim] u8 (sub-vectors concatenated), params [n][nsub][4] = {min,max,growthRate,midpoint}
+ * (NVQuantization.java:489-498), mean = globalMean */
+JV_API int jv_dataset_register_nvq(const uint8_t *bytes, const float *params, int64_t n, int dim, int nsub,
+                                   const float *mean, jv_dataset *out);
+JV_API int jv_dataset_free(jv_dataset ds);
+JV_API int64_t jv_dataset_size(jv_dataset ds);
+JV_API int jv_dataset_dim(jv_dataset ds);
+JV_API int64_t jv_dataset_device_bytes(jv_dataset ds);
+
+/* ---- ScoreFunction for one query: CompressedVectors.precomputedScoreFunctionFor / DefaultSearchScoreProvider.exact ---- */
+JV_API int jv_query_begin(jv_dataset ds, const float *q, int metric, jv_query *out);
+/* the neighbour loop of one processNeighbors call / one rerank list: ids[n] -> scores[n], ONE kernel launch */
+JV_API int jv_score_batch(jv_query q, const int32_t *ids, int n, float *scores_out);
+JV_API int jv_query_end(jv_query q);
+/* PQ only: copy the query's partial-sums table (PQDecoder.java:41-54) back, lut_out[M*k] */
+JV_API int jv_query_get_lut(jv_query q, float *lut_out);
+
+/* one step of many searches: query qi scores ids[offsets[qi] .. offsets[qi+1]) ; one launch for the whole step */
+JV_API int jv_score_multi(jv_dataset ds, int metric, const float *queries, int nq, const int32_t *ids,
+                          const int32_t *offsets, float *scores_out);
+/* diversity scoring (BuildScoreProvider.diversityProviderFor): score(a[i], b[i]) for n pairs, one launch.
+ * f32: exact; PQ: codebook-vs-codebook (PQVectors.java:284-350); BQ: BQVectors.java:98-105 */
+JV_API int jv_score_pairs(jv_dataset ds, int metric, const int32_t *a, const int32_t *b, int n, float *scores_out);
+/* exhaustive scoring of every row for nq queries with a fused device-side top-k; keys_out[nq][k] best first,
+ * padded with INT64_MIN */
+JV_API int jv_topk_bruteforce(jv_dataset ds, int metric, const float *queries, int nq, int k, int64_t *keys_out);
+
+/* ---- bulk encoders (next to the scoring path: ProductQuantization.encodeAll, BinaryQuantization.encodeAll,
+ *      NVQuantization.encodeAll) ---- */
+JV_API int jv_bq_encode_batch(const float *rows, int64_t n, int dim, uint64_t *words_out);
+JV_API int jv_pq_encode_batch(const float *rows, int64_t n, int dim, int M, int k, const float *codebooks,
+                              const float *centroid, uint8_t *codes_out);
+JV_API int jv_nvq_encode_batch(const float *rows, int64_t n, int dim, int nsub, const float *mean, int learn,
+                               float *params_out, uint8_t *bytes_out);
+
+/* ---- graph: ImmutableGraphIndex adjacency in HBM + GraphSearcher traversal on the device ---- */
+/* adj0: [n][degree] int32, -1 padded (level 0). */
+JV_API int jv_graph_create(int32_t n, int degree, const int32_t *adj0, int32_t entry_node, jv_graph *out);
+/* add level 1, 2, ... in order; node_ids[count] are the members, adj [count][degree] their lists at that level.
+ * The entry node must be a member of the last level added. */
+JV_API int jv_graph_add_level(jv_graph g, int32_t count, const int32_t *node_ids, const int32_t *adj);
+JV_API int jv_graph_free(jv_graph g);
+JV_API int jv_graph_info(jv_graph g, int32_t *n, int *degree, int *levels, int32_t *entry_node);
+JV_API int jv_graph_download(jv_graph g, int level, int32_t *node_ids_out, int32_t *adj_out, int32_t *count_out);
+
+typedef struct {
+    int64_t visited;       /* sum over queries of SearchResult.visitedCount (GraphSearcher.java:445-449) */
+    int64_t expanded;      /* expandedCount */
+    int64_t expanded_base; /* expandedCountBaseLayer */
+    int64_t reranked;      /* reranked */
+    int64_t retried;       /* queries re-run with a larger visited table */
+    double device_ms;      /* CUDA-event time of the device work of this call */
+} jv_search_stats;
+
+/* GraphSearcher.search for nq queries at once: traversal scored by `approx`, optional exact rerank by `reranker`
+ * (NULL = none, then rerankK survivors are cut to topK by approximate score as GraphSearcher.java:478-486).
+ * nodes_out/scores_out [nq][topK], best first, padded with -1 / 0. */
+JV_API int jv_graph_search_batch(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric,
+                                 const float *queries, int nq, int topK, int rerankK,
+                                 int32_t *nodes_out, float *scores_out, jv_search_stats *stats);
+/* same with queries / outputs already in HBM (no host copies in the call) */
+JV_API int jv_graph_search_batch_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric,
+                                        const float *queries_device, int nq, int topK, int rerankK,
+                                        int32_t *nodes_out_device, float *scores_out_device, jv_search_stats *stats);
+
+/* GraphIndexBuilder.build over an f32 data set with exact scoring (BuildScoreProvider.randomAccessScoreProvider):
+ * batched inserts, device-side beam search + Vamana robust prune + back-links. */
+typedef struct {
+    int degree;        /* M */
+    int beam_width;    /* efConstruction */
+    float overflow;    /* neighborOverflow, e.g. 1.2 */
+    float alpha;       /* 1.2 */
+    int add_hierarchy; /* HNSW-style upper levels (GraphIndexBuilder.java:562-575) */
+    uint64_t seed;
+    int max_batch;     /* 0 = default */
+} jv_build_params;
+JV_API int jv_graph_build(jv_dataset f32, int metric, const jv_build_params *params, jv_graph *out, double *device_ms);
+
+/* device-memory helpers for callers that keep queries/results in HBM (bench `value` leg) */
+JV_API int jv_device_malloc(void **out, size_t bytes);
+JV_API int jv_device_free(void *p);
+JV_API int jv_memcpy_h2d(void *dst_device, const void *src_host, size_t bytes);
+JV_API int jv_memcpy_d2h(void *dst_host, const void *src_device, size_t bytes);
+JV_API int jv_host_register(void *p, size_t bytes); /* pin a host buffer for faster copies */
+JV_API int jv_host_unregister(void *p);
+JV_API int jv_device_synchronize(void);
+JV_API int64_t jv_kernel_launch_count(void); /* kernels this library has launched since load */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JVECTOR_B200_H */

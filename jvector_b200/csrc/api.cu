@@ -1,0 +1,850 @@
+// api.cu — the C ABI of include/jvector_b200.h, batched GPU group: handle management, host<->HBM staging, launches.
+// No CPU fallback lives here: without an sm_100 device every entry point returns JV_ERR_NO_DEVICE.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/jvector_b200.h"
+#include "kernels.h"
+
+using namespace jv;
+
+namespace {
+
+thread_local std::string t_err;
+std::mutex g_mu;
+int g_device = -1;
+int g_sm_count = 0;
+
+int fail(int code, const std::string &msg)
+{
+    t_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what)
+{
+    t_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? JV_ERR_OOM : JV_ERR_CUDA;
+}
+#define CK(x, what)                                      \
+    do {                                                 \
+        cudaError_t e_ = (x);                            \
+        if (e_ != cudaSuccess) return cuda_fail(e_, what); \
+    } while (0)
+#define NEED_INIT()                                                                            \
+    do {                                                                                       \
+        if (g_device < 0) return fail(JV_ERR_NO_DEVICE, "jv_gpu_init() has not succeeded");    \
+        cudaError_t e0_ = cudaSetDevice(g_device);                                             \
+        if (e0_ != cudaSuccess) return cuda_fail(e0_, "cudaSetDevice");                        \
+    } while (0)
+
+// per-thread stream + growable staging buffers (callers are ForkJoinPool workers: no global locks on the score path)
+struct ThreadCtx {
+    cudaStream_t stream = nullptr;
+    void *dbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t dcap[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int init()
+    {
+        if (stream) return JV_OK;
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        CK(cudaEventCreate(&ev0), "cudaEventCreate");
+        CK(cudaEventCreate(&ev1), "cudaEventCreate");
+        return JV_OK;
+    }
+    int ensure(int slot, size_t bytes)
+    {
+        if (bytes <= dcap[slot]) return JV_OK;
+        if (dbuf[slot]) cudaFree(dbuf[slot]);
+        dbuf[slot] = nullptr;
+        dcap[slot] = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CK(cudaMalloc(&dbuf[slot], want), "cudaMalloc(staging)");
+        dcap[slot] = want;
+        return JV_OK;
+    }
+};
+thread_local ThreadCtx t_ctx;
+
+int round4(int v) { return (v + 3) & ~3; }
+
+void pq_layout(int dim, int M, std::vector<int> &sizes, std::vector<int> &offsets)
+{
+    // base:quantization/ProductQuantization.java:535-550
+    sizes.resize(M);
+    offsets.resize(M);
+    int base = dim / M, rem = dim % M, off = 0;
+    for (int m = 0; m < M; m++) {
+        sizes[m] = base + (m < rem ? 1 : 0);
+        offsets[m] = off;
+        off += sizes[m];
+    }
+}
+
+}  // namespace
+
+struct jv_dataset_s {
+    DataDesc d;
+    std::vector<void *> allocs;
+    size_t bytes = 0;
+    int alloc(void **p, size_t n)
+    {
+        CK(cudaMalloc(p, n ? n : 16), "cudaMalloc(dataset)");
+        allocs.push_back(*p);
+        bytes += n;
+        return JV_OK;
+    }
+    ~jv_dataset_s()
+    {
+        for (void *p : allocs) cudaFree(p);
+    }
+};
+
+struct jv_query_s {
+    jv_dataset ds;
+    int metric;
+    float *blob = nullptr;
+};
+
+struct jv_graph_s {
+    GraphDesc g;
+    int32_t *adj0 = nullptr;
+    int32_t *upper_row = nullptr;
+    int32_t *upper_adj = nullptr;
+    long long *upper_off = nullptr;
+    std::vector<std::vector<int32_t>> level_ids;  // host copies, level >= 1
+    std::vector<std::vector<int32_t>> level_adj;
+    ~jv_graph_s()
+    {
+        cudaFree(adj0); cudaFree(upper_row); cudaFree(upper_adj); cudaFree(upper_off);
+    }
+};
+
+extern "C" {
+
+int jv_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int jv_gpu_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(JV_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(JV_ERR_INVALID, "device index out of range");
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device), "cudaGetDeviceProperties");
+    if (p.major != 10) return fail(JV_ERR_NO_DEVICE, "device is not sm_100 (this library carries sm_100a code only)");
+    CK(cudaSetDevice(device), "cudaSetDevice");
+    g_device = device;
+    g_sm_count = p.multiProcessorCount;
+    return JV_OK;
+}
+
+const char *jv_last_error(void) { return t_err.c_str(); }
+const char *jv_version(void) { return "jvector-b200 0.1 (sm_100a)"; }
+int jv_gpu_sm_count(void) { return g_sm_count; }
+int64_t jv_kernel_launch_count(void) { return (int64_t)g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------ data sets
+int jv_dataset_register_f32(const float *rows, int64_t n, int dim, jv_dataset *out)
+{
+    NEED_INIT();
+    if (!rows || !out || n <= 0 || dim <= 0 || n > 0x7fffffffLL) return fail(JV_ERR_INVALID, "register_f32: bad arguments");
+    jv_dataset ds = new jv_dataset_s();
+    memset(&ds->d, 0, sizeof(DataDesc));
+    ds->d.kind = KIND_F32;
+    ds->d.dim = dim;
+    ds->d.n = n;
+    ds->d.stride = round4(dim);
+    float *dev = nullptr;
+    int rc = ds->alloc((void **)&dev, (size_t)n * ds->d.stride * sizeof(float));
+    if (rc) { delete ds; return rc; }
+    cudaError_t e;
+    if (ds->d.stride == dim) e = cudaMemcpy(dev, rows, (size_t)n * dim * sizeof(float), cudaMemcpyHostToDevice);
+    else {
+        e = cudaMemset(dev, 0, (size_t)n * ds->d.stride * sizeof(float));
+        if (e == cudaSuccess)
+            e = cudaMemcpy2D(dev, (size_t)ds->d.stride * 4, rows, (size_t)dim * 4, (size_t)dim * 4, (size_t)n, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) { delete ds; return cuda_fail(e, "upload rows"); }
+    ds->d.rows = dev;
+    *out = ds;
+    return JV_OK;
+}
+
+int jv_dataset_register_pq(const uint8_t *codes, int64_t n, int dim, int M, int k, const float *codebooks, const float *centroid, jv_dataset *out)
+{
+    NEED_INIT();
+    if (!codes || !codebooks || !out || n <= 0 || dim <= 0 || M <= 0 || M > dim || k <= 0 || k > 256 || n > 0x7fffffffLL)
+        return fail(JV_ERR_INVALID, "register_pq: bad arguments");
+    jv_dataset ds = new jv_dataset_s();
+    memset(&ds->d, 0, sizeof(DataDesc));
+    DataDesc &d = ds->d;
+    d.kind = KIND_PQ; d.dim = dim; d.n = n; d.M = M; d.k = k; d.code_stride = round4(M);
+    std::vector<int> sizes, offsets;
+    pq_layout(dim, M, sizes, offsets);
+    uint8_t *dcodes = nullptr;
+    float *dcb = nullptr, *dcen = nullptr, *dmag = nullptr;
+    int *dsz = nullptr, *doff = nullptr;
+    int rc;
+    if ((rc = ds->alloc((void **)&dcodes, (size_t)n * d.code_stride)) || (rc = ds->alloc((void **)&dcb, (size_t)k * dim * 4)) ||
+        (rc = ds->alloc((void **)&dsz, (size_t)M * 4)) || (rc = ds->alloc((void **)&doff, (size_t)M * 4)) ||
+        (rc = ds->alloc((void **)&dmag, (size_t)M * k * 4)) || (centroid && (rc = ds->alloc((void **)&dcen, (size_t)dim * 4)))) {
+        delete ds;
+        return rc;
+    }
+    cudaError_t e;
+    if (d.code_stride == M) e = cudaMemcpy(dcodes, codes, (size_t)n * M, cudaMemcpyHostToDevice);
+    else {
+        e = cudaMemset(dcodes, 0, (size_t)n * d.code_stride);
+        if (e == cudaSuccess) e = cudaMemcpy2D(dcodes, d.code_stride, codes, M, M, (size_t)n, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(dcb, codebooks, (size_t)k * dim * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dsz, sizes.data(), (size_t)M * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(doff, offsets.data(), (size_t)M * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && centroid) e = cudaMemcpy(dcen, centroid, (size_t)dim * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete ds; return cuda_fail(e, "upload pq"); }
+    d.codes = dcodes; d.codebooks = dcb; d.sub_sizes = dsz; d.sub_offsets = doff; d.centroid = dcen; d.mag = dmag;
+    e = launch_pq_self_magnitudes(d, dmag, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { delete ds; return cuda_fail(e, "pq self magnitudes"); }
+    *out = ds;
+    return JV_OK;
+}
+
+int jv_dataset_register_bq(const uint64_t *words, int64_t n, int dim, jv_dataset *out)
+{
+    NEED_INIT();
+    if (!words || !out || n <= 0 || dim <= 0 || n > 0x7fffffffLL) return fail(JV_ERR_INVALID, "register_bq: bad arguments");
+    jv_dataset ds = new jv_dataset_s();
+    memset(&ds->d, 0, sizeof(DataDesc));
+    ds->d.kind = KIND_BQ; ds->d.dim = dim; ds->d.n = n; ds->d.W = (dim + 63) / 64;
+    unsigned long long *dw = nullptr;
+    int rc = ds->alloc((void **)&dw, (size_t)n * ds->d.W * 8);
+    if (rc) { delete ds; return rc; }
+    cudaError_t e = cudaMemcpy(dw, words, (size_t)n * ds->d.W * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete ds; return cuda_fail(e, "upload bq"); }
+    ds->d.words = dw;
+    *out = ds;
+    return JV_OK;
+}
+
+int jv_dataset_register_nvq(const uint8_t *bytes, const float *params, int64_t n, int dim, int nsub, const float *mean, jv_dataset *out)
+{
+    NEED_INIT();
+    if (!bytes || !params || !mean || !out || n <= 0 || dim <= 0 || nsub <= 0 || nsub > dim || n > 0x7fffffffLL)
+        return fail(JV_ERR_INVALID, "register_nvq: bad arguments");
+    jv_dataset ds = new jv_dataset_s();
+    memset(&ds->d, 0, sizeof(DataDesc));
+    DataDesc &d = ds->d;
+    d.kind = KIND_NVQ; d.dim = dim; d.n = n; d.nsub = nsub; d.stride = round4(dim); d.byte_stride = round4(dim);
+    std::vector<int> sizes, offsets;
+    pq_layout(dim, nsub, sizes, offsets);  // base:quantization/NVQuantization.java:236-251 uses the same split
+    uint8_t *db = nullptr;
+    float *dp = nullptr, *dm = nullptr;
+    int *dsz = nullptr, *doff = nullptr;
+    int rc;
+    if ((rc = ds->alloc((void **)&db, (size_t)n * d.byte_stride)) || (rc = ds->alloc((void **)&dp, (size_t)n * nsub * 16)) ||
+        (rc = ds->alloc((void **)&dm, (size_t)d.stride * 4)) || (rc = ds->alloc((void **)&dsz, (size_t)nsub * 4)) ||
+        (rc = ds->alloc((void **)&doff, (size_t)nsub * 4))) {
+        delete ds;
+        return rc;
+    }
+    cudaError_t e;
+    if (d.byte_stride == dim) e = cudaMemcpy(db, bytes, (size_t)n * dim, cudaMemcpyHostToDevice);
+    else {
+        e = cudaMemset(db, 0, (size_t)n * d.byte_stride);
+        if (e == cudaSuccess) e = cudaMemcpy2D(db, d.byte_stride, bytes, dim, dim, (size_t)n, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(dp, params, (size_t)n * nsub * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(dm, 0, (size_t)d.stride * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(dm, mean, (size_t)dim * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dsz, sizes.data(), (size_t)nsub * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(doff, offsets.data(), (size_t)nsub * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete ds; return cuda_fail(e, "upload nvq"); }
+    d.bytes = db; d.params = dp; d.mean = dm; d.sub_sizes = dsz; d.sub_offsets = doff;
+    *out = ds;
+    return JV_OK;
+}
+
+int jv_dataset_free(jv_dataset ds)
+{
+    if (!ds) return JV_OK;
+    if (g_device >= 0) cudaSetDevice(g_device);
+    cudaDeviceSynchronize();
+    delete ds;
+    return JV_OK;
+}
+int64_t jv_dataset_size(jv_dataset ds) { return ds ? ds->d.n : 0; }
+int jv_dataset_dim(jv_dataset ds) { return ds ? ds->d.dim : 0; }
+int64_t jv_dataset_device_bytes(jv_dataset ds) { return ds ? (int64_t)ds->bytes : 0; }
+
+// ------------------------------------------------------------------------------------------------ one query
+static int check_metric(const DataDesc &d, int metric)
+{
+    if (metric < 0 || metric > 2) return fail(JV_ERR_INVALID, "unknown similarity function");
+    (void)d;
+    return JV_OK;
+}
+
+int jv_query_begin(jv_dataset ds, const float *q, int metric, jv_query *out)
+{
+    NEED_INIT();
+    if (!ds || !q || !out) return fail(JV_ERR_INVALID, "query_begin: null argument");
+    int rc = check_metric(ds->d, metric);
+    if (rc) return rc;
+    if ((rc = t_ctx.init())) return rc;
+    jv_query h = new jv_query_s();
+    h->ds = ds;
+    h->metric = metric;
+    cudaError_t e = cudaMalloc((void **)&h->blob, (size_t)blob_floats(ds->d) * 4);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(query)"); }
+    if ((rc = t_ctx.ensure(0, (size_t)ds->d.dim * 4))) { cudaFree(h->blob); delete h; return rc; }
+    cudaStream_t s = t_ctx.stream;
+    e = cudaMemcpyAsync(t_ctx.dbuf[0], q, (size_t)ds->d.dim * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = launch_prepare(ds->d, metric, (const float *)t_ctx.dbuf[0], 1, h->blob, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { cudaFree(h->blob); delete h; return cuda_fail(e, "prepare query"); }
+    *out = h;
+    return JV_OK;
+}
+
+int jv_score_batch(jv_query q, const int32_t *ids, int n, float *scores_out)
+{
+    NEED_INIT();
+    if (!q || (n > 0 && (!ids || !scores_out)) || n < 0) return fail(JV_ERR_INVALID, "score_batch: bad arguments");
+    if (n == 0) return JV_OK;
+    int rc;
+    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(1, (size_t)n * 4)) || (rc = t_ctx.ensure(2, (size_t)n * 4))) return rc;
+    cudaStream_t s = t_ctx.stream;
+    CK(cudaMemcpyAsync(t_ctx.dbuf[1], ids, (size_t)n * 4, cudaMemcpyHostToDevice, s), "H2D ids");
+    CK(launch_score_ragged(q->ds->d, q->metric, q->blob, 1, (const int32_t *)t_ctx.dbuf[1], nullptr, n, n, (float *)t_ctx.dbuf[2], s), "score_ragged");
+    CK(cudaMemcpyAsync(scores_out, t_ctx.dbuf[2], (size_t)n * 4, cudaMemcpyDeviceToHost, s), "D2H scores");
+    CK(cudaStreamSynchronize(s), "sync");
+    return JV_OK;
+}
+
+int jv_query_get_lut(jv_query q, float *lut_out)
+{
+    NEED_INIT();
+    if (!q || !lut_out || q->ds->d.kind != KIND_PQ) return fail(JV_ERR_INVALID, "get_lut: not a PQ query");
+    CK(cudaMemcpy(lut_out, q->blob, (size_t)q->ds->d.M * q->ds->d.k * 4, cudaMemcpyDeviceToHost), "D2H lut");
+    return JV_OK;
+}
+
+int jv_query_end(jv_query q)
+{
+    if (!q) return JV_OK;
+    if (g_device >= 0) cudaSetDevice(g_device);
+    cudaFree(q->blob);
+    delete q;
+    return JV_OK;
+}
+
+int jv_score_multi(jv_dataset ds, int metric, const float *queries, int nq, const int32_t *ids, const int32_t *offsets, float *scores_out)
+{
+    NEED_INIT();
+    if (!ds || !queries || !ids || !offsets || !scores_out || nq <= 0) return fail(JV_ERR_INVALID, "score_multi: bad arguments");
+    if (nq > 65535) return fail(JV_ERR_INVALID, "score_multi: at most 65535 queries per call");
+    int rc = check_metric(ds->d, metric);
+    if (rc) return rc;
+    const int total = offsets[nq];
+    int maxc = 0;
+    for (int i = 0; i < nq; i++) {
+        if (offsets[i + 1] < offsets[i]) return fail(JV_ERR_INVALID, "score_multi: offsets not monotone");
+        maxc = std::max(maxc, offsets[i + 1] - offsets[i]);
+    }
+    if (total == 0) return JV_OK;
+    const size_t bf = (size_t)blob_floats(ds->d);
+    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(0, (size_t)nq * ds->d.dim * 4)) || (rc = t_ctx.ensure(1, (size_t)total * 4)) ||
+        (rc = t_ctx.ensure(2, (size_t)total * 4)) || (rc = t_ctx.ensure(3, (size_t)(nq + 1) * 4)) || (rc = t_ctx.ensure(4, (size_t)nq * bf * 4)))
+        return rc;
+    cudaStream_t s = t_ctx.stream;
+    CK(cudaMemcpyAsync(t_ctx.dbuf[0], queries, (size_t)nq * ds->d.dim * 4, cudaMemcpyHostToDevice, s), "H2D queries");
+    CK(cudaMemcpyAsync(t_ctx.dbuf[1], ids, (size_t)total * 4, cudaMemcpyHostToDevice, s), "H2D ids");
+    CK(cudaMemcpyAsync(t_ctx.dbuf[3], offsets, (size_t)(nq + 1) * 4, cudaMemcpyHostToDevice, s), "H2D offsets");
+    CK(launch_prepare(ds->d, metric, (const float *)t_ctx.dbuf[0], nq, (float *)t_ctx.dbuf[4], s), "prepare");
+    CK(launch_score_ragged(ds->d, metric, (const float *)t_ctx.dbuf[4], nq, (const int32_t *)t_ctx.dbuf[1], (const int32_t *)t_ctx.dbuf[3], 0, maxc,
+                           (float *)t_ctx.dbuf[2], s),
+       "score_ragged");
+    CK(cudaMemcpyAsync(scores_out, t_ctx.dbuf[2], (size_t)total * 4, cudaMemcpyDeviceToHost, s), "D2H scores");
+    CK(cudaStreamSynchronize(s), "sync");
+    return JV_OK;
+}
+
+int jv_score_pairs(jv_dataset ds, int metric, const int32_t *a, const int32_t *b, int n, float *scores_out)
+{
+    NEED_INIT();
+    if (!ds || n < 0 || (n > 0 && (!a || !b || !scores_out))) return fail(JV_ERR_INVALID, "score_pairs: bad arguments");
+    if (ds->d.kind == KIND_NVQ) return fail(JV_ERR_UNSUPPORTED, "score_pairs: NVQ has no node-vs-node scorer in the reference");
+    if (n == 0) return JV_OK;
+    int rc = check_metric(ds->d, metric);
+    if (rc) return rc;
+    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(1, (size_t)n * 8)) || (rc = t_ctx.ensure(2, (size_t)n * 4))) return rc;
+    cudaStream_t s = t_ctx.stream;
+    int32_t *da = (int32_t *)t_ctx.dbuf[1], *db = da + n;
+    CK(cudaMemcpyAsync(da, a, (size_t)n * 4, cudaMemcpyHostToDevice, s), "H2D a");
+    CK(cudaMemcpyAsync(db, b, (size_t)n * 4, cudaMemcpyHostToDevice, s), "H2D b");
+    CK(launch_score_pairs(ds->d, metric, da, db, n, (float *)t_ctx.dbuf[2], s), "score_pairs");
+    CK(cudaMemcpyAsync(scores_out, t_ctx.dbuf[2], (size_t)n * 4, cudaMemcpyDeviceToHost, s), "D2H scores");
+    CK(cudaStreamSynchronize(s), "sync");
+    return JV_OK;
+}
+
+int jv_topk_bruteforce(jv_dataset ds, int metric, const float *queries, int nq, int k, int64_t *keys_out)
+{
+    NEED_INIT();
+    if (!ds || !queries || !keys_out || nq <= 0 || k <= 0) return fail(JV_ERR_INVALID, "topk_bruteforce: bad arguments");
+    if (k > 2048) return fail(JV_ERR_INVALID, "topk_bruteforce: k <= 2048");
+    int rc = check_metric(ds->d, metric);
+    if (rc) return rc;
+    if ((rc = t_ctx.init())) return rc;
+    cudaStream_t s = t_ctx.stream;
+    const size_t bf = (size_t)blob_floats(ds->d);
+    const int chunk_max = (int)std::max<size_t>(1, std::min<size_t>(4096, ((size_t)512 << 20) / (bf * 4)));
+    TopkScratch ts;
+    ts.S = (int)std::min<long long>(ds->d.n, 4096);
+    long long expect = ds->d.n <= ts.S ? ds->d.n : ((long long)k * ds->d.n) / ts.S;
+    ts.cap = expect * 2 > 4096 ? 16384 : 4096;
+    if (ds->d.n <= ts.S) ts.cap = 4096;
+    for (int q0 = 0; q0 < nq; q0 += chunk_max) {
+        const int cq = std::min(chunk_max, nq - q0);
+        if ((rc = t_ctx.ensure(0, (size_t)cq * ds->d.dim * 4)) || (rc = t_ctx.ensure(4, (size_t)cq * bf * 4)) ||
+            (rc = t_ctx.ensure(1, (size_t)ts.S * 4 + (size_t)cq * ts.S * 4 + 64)) ||
+            (rc = t_ctx.ensure(2, (size_t)cq * 8 + (size_t)cq * 4 + 64 + (size_t)cq * ts.cap * 8)) || (rc = t_ctx.ensure(3, (size_t)cq * k * 8 + 16)))
+            return rc;
+        ts.sample_ids = (int32_t *)t_ctx.dbuf[1];
+        ts.sample_scores = (float *)((char *)t_ctx.dbuf[1] + (((size_t)ts.S * 4 + 15) & ~(size_t)15));
+        ts.buf = (long long *)t_ctx.dbuf[2];
+        ts.thr = ts.buf + (size_t)cq * ts.cap;
+        ts.cnt = (int *)(ts.thr + cq);
+        long long *dkeys = (long long *)t_ctx.dbuf[3];
+        int *dflag = (int *)(dkeys + (size_t)cq * k);
+        CK(cudaMemcpyAsync(t_ctx.dbuf[0], queries + (size_t)q0 * ds->d.dim, (size_t)cq * ds->d.dim * 4, cudaMemcpyHostToDevice, s), "H2D queries");
+        CK(cudaMemsetAsync(dflag, 0, sizeof(int), s), "memset flag");
+        CK(launch_prepare(ds->d, metric, (const float *)t_ctx.dbuf[0], cq, (float *)t_ctx.dbuf[4], s), "prepare");
+        CK(launch_topk_bruteforce(ds->d, metric, (const float *)t_ctx.dbuf[4], cq, k, ts, dkeys, dflag, s), "topk");
+        int flag = 0;
+        CK(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, s), "D2H flag");
+        CK(cudaMemcpyAsync(keys_out + (size_t)q0 * k, dkeys, (size_t)cq * k * 8, cudaMemcpyDeviceToHost, s), "D2H keys");
+        CK(cudaStreamSynchronize(s), "sync");
+        if (flag) return fail(JV_ERR_OVERFLOW, "topk_bruteforce: candidate buffer overflow (adversarial score distribution)");
+    }
+    return JV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ encoders
+int jv_bq_encode_batch(const float *rows, int64_t n, int dim, uint64_t *words_out)
+{
+    NEED_INIT();
+    if (!rows || !words_out || n <= 0 || dim <= 0) return fail(JV_ERR_INVALID, "bq_encode: bad arguments");
+    int rc;
+    const int W = (dim + 63) / 64;
+    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(0, (size_t)n * dim * 4)) || (rc = t_ctx.ensure(1, (size_t)n * W * 8))) return rc;
+    cudaStream_t s = t_ctx.stream;
+    CK(cudaMemcpyAsync(t_ctx.dbuf[0], rows, (size_t)n * dim * 4, cudaMemcpyHostToDevice, s), "H2D rows");
+    CK(launch_bq_encode((const float *)t_ctx.dbuf[0], n, dim, (unsigned long long *)t_ctx.dbuf[1], s), "bq_encode");
+    CK(cudaMemcpyAsync(words_out, t_ctx.dbuf[1], (size_t)n * W * 8, cudaMemcpyDeviceToHost, s), "D2H words");
+    CK(cudaStreamSynchronize(s), "sync");
+    return JV_OK;
+}
+
+int jv_pq_encode_batch(const float *rows, int64_t n, int dim, int M, int k, const float *codebooks, const float *centroid, uint8_t *codes_out)
+{
+    NEED_INIT();
+    if (!rows || !codebooks || !codes_out || n <= 0 || dim <= 0 || M <= 0 || M > dim || k <= 0 || k > 256) return fail(JV_ERR_INVALID, "pq_encode: bad arguments");
+    int rc;
+    std::vector<int> sizes, offsets;
+    pq_layout(dim, M, sizes, offsets);
+    const size_t cb_bytes = (size_t)k * dim * 4;
+    const size_t aux = cb_bytes + (size_t)dim * 4 + (size_t)M * 8 + 64;
+    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(0, (size_t)n * dim * 4)) || (rc = t_ctx.ensure(1, (size_t)n * M)) || (rc = t_ctx.ensure(2, aux))) return rc;
+    cudaStream_t s = t_ctx.stream;
+    char *a = (char *)t_ctx.dbuf[2];
+    float *dcb = (float *)a, *dcen = (float *)(a + cb_bytes);
+    int *dsz = (int *)(a + cb_bytes + (size_t)dim * 4), *doff = dsz + M;
+    CK(cudaMemcpyAsync(t_ctx.dbuf[0], rows, (size_t)n * dim * 4, cudaMemcpyHostToDevice, s), "H2D rows");
+    CK(cudaMemcpyAsync(dcb, codebooks, cb_bytes, cudaMemcpyHostToDevice, s), "H2D codebooks");
+    if (centroid) CK(cudaMemcpyAsync(dcen, centroid, (size_t)dim * 4, cudaMemcpyHostToDevice, s), "H2D centroid");
+    CK(cudaMemcpyAsync(dsz, sizes.data(), (size_t)M * 4, cudaMemcpyHostToDevice, s), "H2D sizes");
+    CK(cudaMemcpyAsync(doff, offsets.data(), (size_t)M * 4, cudaMemcpyHostToDevice, s), "H2D offsets");
+    DataDesc d;
+    memset(&d, 0, sizeof(d));
+    d.kind = KIND_PQ; d.dim = dim; d.n = n; d.M = M; d.k = k; d.codebooks = dcb; d.sub_sizes = dsz; d.sub_offsets = doff; d.centroid = centroid ? dcen : nullptr;
+    CK(launch_pq_encode(d, (const float *)t_ctx.dbuf[0], n, (uint8_t *)t_ctx.dbuf[1], s), "pq_encode");
+    CK(cudaMemcpyAsync(codes_out, t_ctx.dbuf[1], (size_t)n * M, cudaMemcpyDeviceToHost, s), "D2H codes");
+    CK(cudaStreamSynchronize(s), "sync");
+    return JV_OK;
+}
+
+int jv_nvq_encode_batch(const float *rows, int64_t n, int dim, int nsub, const float *mean, int learn, float *params_out, uint8_t *bytes_out)
+{
+    NEED_INIT();
+    if (!rows || !mean || !params_out || !bytes_out || n <= 0 || dim <= 0 || nsub <= 0 || nsub > dim) return fail(JV_ERR_INVALID, "nvq_encode: bad arguments");
+    int rc;
+    std::vector<int> sizes, offsets;
+    pq_layout(dim, nsub, sizes, offsets);
+    const size_t aux = (size_t)dim * 4 + (size_t)nsub * 8 + 64;
+    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(0, (size_t)n * dim * 4)) || (rc = t_ctx.ensure(1, (size_t)n * dim)) ||
+        (rc = t_ctx.ensure(2, aux)) || (rc = t_ctx.ensure(3, (size_t)n * nsub * 16)))
+        return rc;
+    cudaStream_t s = t_ctx.stream;
+    char *a = (char *)t_ctx.dbuf[2];
+    float *dmean = (float *)a;
+    int *dsz = (int *)(a + (size_t)dim * 4), *doff = dsz + nsub;
+    CK(cudaMemcpyAsync(t_ctx.dbuf[0], rows, (size_t)n * dim * 4, cudaMemcpyHostToDevice, s), "H2D rows");
+    CK(cudaMemcpyAsync(dmean, mean, (size_t)dim * 4, cudaMemcpyHostToDevice, s), "H2D mean");
+    CK(cudaMemcpyAsync(dsz, sizes.data(), (size_t)nsub * 4, cudaMemcpyHostToDevice, s), "H2D sizes");
+    CK(cudaMemcpyAsync(doff, offsets.data(), (size_t)nsub * 4, cudaMemcpyHostToDevice, s), "H2D offsets");
+    CK(launch_nvq_encode((const float *)t_ctx.dbuf[0], n, dim, nsub, dsz, doff, dmean, learn, (float *)t_ctx.dbuf[3], (uint8_t *)t_ctx.dbuf[1], dim, s), "nvq_encode");
+    CK(cudaMemcpyAsync(params_out, t_ctx.dbuf[3], (size_t)n * nsub * 16, cudaMemcpyDeviceToHost, s), "D2H params");
+    CK(cudaMemcpyAsync(bytes_out, t_ctx.dbuf[1], (size_t)n * dim, cudaMemcpyDeviceToHost, s), "D2H bytes");
+    CK(cudaStreamSynchronize(s), "sync");
+    return JV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ graph
+int jv_graph_create(int32_t n, int degree, const int32_t *adj0, int32_t entry_node, jv_graph *out)
+{
+    NEED_INIT();
+    if (!adj0 || !out || n <= 0 || degree <= 0 || degree > MAX_DEGREE || entry_node < 0 || entry_node >= n)
+        return fail(JV_ERR_INVALID, "graph_create: bad arguments");
+    jv_graph g = new jv_graph_s();
+    memset(&g->g, 0, sizeof(GraphDesc));
+    cudaError_t e = cudaMalloc((void **)&g->adj0, (size_t)n * degree * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(g->adj0, adj0, (size_t)n * degree * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete g; return cuda_fail(e, "upload adjacency"); }
+    g->g.n = n; g->g.degree = degree; g->g.levels = 1; g->g.entry_node = entry_node; g->g.entry_level = 0; g->g.adj0 = g->adj0;
+    *out = g;
+    return JV_OK;
+}
+
+static int graph_rebuild_upper(jv_graph g)
+{
+    const int L = (int)g->level_ids.size();
+    cudaFree(g->upper_row); cudaFree(g->upper_adj); cudaFree(g->upper_off);
+    g->upper_row = nullptr; g->upper_adj = nullptr; g->upper_off = nullptr;
+    if (L == 0) return JV_OK;
+    const int n = g->g.n, degree = g->g.degree;
+    std::vector<int32_t> rows((size_t)L * n, -1);
+    std::vector<long long> offs(L);
+    std::vector<int32_t> adj;
+    long long o = 0;
+    for (int l = 0; l < L; l++) {
+        offs[l] = o;
+        for (size_t i = 0; i < g->level_ids[l].size(); i++) rows[(size_t)l * n + g->level_ids[l][i]] = (int32_t)i;
+        adj.insert(adj.end(), g->level_adj[l].begin(), g->level_adj[l].end());
+        o += (long long)g->level_ids[l].size();
+    }
+    CK(cudaMalloc((void **)&g->upper_row, rows.size() * 4), "cudaMalloc(upper_row)");
+    CK(cudaMalloc((void **)&g->upper_adj, std::max<size_t>(adj.size(), 1) * 4), "cudaMalloc(upper_adj)");
+    CK(cudaMalloc((void **)&g->upper_off, (size_t)L * 8), "cudaMalloc(upper_off)");
+    CK(cudaMemcpy(g->upper_row, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice), "H2D upper_row");
+    CK(cudaMemcpy(g->upper_adj, adj.data(), adj.size() * 4, cudaMemcpyHostToDevice), "H2D upper_adj");
+    CK(cudaMemcpy(g->upper_off, offs.data(), (size_t)L * 8, cudaMemcpyHostToDevice), "H2D upper_off");
+    g->g.upper_row = g->upper_row; g->g.upper_adj = g->upper_adj; g->g.upper_off = g->upper_off;
+    g->g.levels = L + 1;
+    g->g.entry_level = L;
+    (void)degree;
+    return JV_OK;
+}
+
+int jv_graph_add_level(jv_graph g, int32_t count, const int32_t *node_ids, const int32_t *adj)
+{
+    NEED_INIT();
+    if (!g || count <= 0 || !node_ids || !adj) return fail(JV_ERR_INVALID, "graph_add_level: bad arguments");
+    bool has_entry = false;
+    for (int i = 0; i < count; i++) {
+        if (node_ids[i] < 0 || node_ids[i] >= g->g.n) return fail(JV_ERR_INVALID, "graph_add_level: node id out of range");
+        if (node_ids[i] == g->g.entry_node) has_entry = true;
+    }
+    if (!has_entry) return fail(JV_ERR_INVALID, "graph_add_level: the entry node must belong to every level");
+    g->level_ids.emplace_back(node_ids, node_ids + count);
+    g->level_adj.emplace_back(adj, adj + (size_t)count * g->g.degree);
+    return graph_rebuild_upper(g);
+}
+
+int jv_graph_free(jv_graph g)
+{
+    if (!g) return JV_OK;
+    if (g_device >= 0) cudaSetDevice(g_device);
+    cudaDeviceSynchronize();
+    delete g;
+    return JV_OK;
+}
+
+int jv_graph_info(jv_graph g, int32_t *n, int *degree, int *levels, int32_t *entry_node)
+{
+    if (!g) return fail(JV_ERR_INVALID, "graph_info: null graph");
+    if (n) *n = g->g.n;
+    if (degree) *degree = g->g.degree;
+    if (levels) *levels = g->g.levels;
+    if (entry_node) *entry_node = g->g.entry_node;
+    return JV_OK;
+}
+
+int jv_graph_download(jv_graph g, int level, int32_t *node_ids_out, int32_t *adj_out, int32_t *count_out)
+{
+    NEED_INIT();
+    if (!g || level < 0 || level >= g->g.levels) return fail(JV_ERR_INVALID, "graph_download: bad level");
+    if (level == 0) {
+        if (count_out) *count_out = g->g.n;
+        if (node_ids_out)
+            for (int i = 0; i < g->g.n; i++) node_ids_out[i] = i;
+        if (adj_out) CK(cudaMemcpy(adj_out, g->adj0, (size_t)g->g.n * g->g.degree * 4, cudaMemcpyDeviceToHost), "D2H adjacency");
+        return JV_OK;
+    }
+    const auto &ids = g->level_ids[level - 1];
+    if (count_out) *count_out = (int32_t)ids.size();
+    if (node_ids_out) memcpy(node_ids_out, ids.data(), ids.size() * 4);
+    if (adj_out) memcpy(adj_out, g->level_adj[level - 1].data(), g->level_adj[level - 1].size() * 4);
+    return JV_OK;
+}
+
+static int search_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric, const float *queries_dev, int nq, int topK, int rerankK,
+                         int32_t *nodes_dev, float *scores_dev, jv_search_stats *stats)
+{
+    if (!g || !approx || !queries_dev || !nodes_dev || !scores_dev || nq <= 0) return fail(JV_ERR_INVALID, "graph_search: bad arguments");
+    if (topK < 1 || rerankK < topK) return fail(JV_ERR_INVALID, "graph_search: need 1 <= topK <= rerankK");
+    if (rerankK > 4096) return fail(JV_ERR_INVALID, "graph_search: rerankK <= 4096");
+    if (approx->d.n != g->g.n) return fail(JV_ERR_INVALID, "graph_search: data set and graph sizes differ");
+    if (reranker && (reranker->d.n != g->g.n || reranker->d.dim != approx->d.dim)) return fail(JV_ERR_INVALID, "graph_search: reranker shape mismatch");
+    if (reranker && reranker->d.kind != KIND_F32 && reranker->d.kind != KIND_NVQ)
+        return fail(JV_ERR_UNSUPPORTED, "graph_search: the reranker must be fp32 or NVQ (OnDiskGraphIndex.java:705-713)");
+    int rc = check_metric(approx->d, metric);
+    if (rc) return rc;
+    if ((rc = t_ctx.init())) return rc;
+    cudaStream_t s = t_ctx.stream;
+    const DataDesc *rr = reranker ? &reranker->d : nullptr;
+    SearchPlan plan;
+    CK(plan_search(approx->d, rr, g->g, topK, rerankK, nq, 0, g_sm_count, &plan), "plan_search");
+    const size_t aux = sizeof(SearchCounters) + 64 + (size_t)nq + (size_t)nq * 4 + 64;
+    if ((rc = t_ctx.ensure(5, search_scratch_bytes(plan))) || (rc = t_ctx.ensure(3, aux))) return rc;
+    char *a = (char *)t_ctx.dbuf[3];
+    SearchCounters *dcnt = (SearchCounters *)a;
+    int *dwork = (int *)(a + sizeof(SearchCounters));
+    uint8_t *dover = (uint8_t *)(a + sizeof(SearchCounters) + 64);
+    int32_t *dindex = (int32_t *)(a + sizeof(SearchCounters) + 64 + (((size_t)nq + 63) & ~(size_t)63));
+    CK(cudaMemsetAsync(dcnt, 0, sizeof(SearchCounters), s), "memset counters");
+    CK(cudaEventRecord(t_ctx.ev0, s), "event");
+    CK(launch_search(g->g, approx->d, rr, metric, queries_dev, nq, topK, rerankK, plan, t_ctx.dbuf[5], dwork, nodes_dev, scores_dev, dcnt, dover, nullptr, 0, s),
+       "launch_search");
+    CK(cudaEventRecord(t_ctx.ev1, s), "event");
+    SearchCounters hc;
+    CK(cudaMemcpyAsync(&hc, dcnt, sizeof(hc), cudaMemcpyDeviceToHost, s), "D2H counters");
+    CK(cudaStreamSynchronize(s), "search kernel");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t_ctx.ev0, t_ctx.ev1);
+    long long retried = 0;
+    int cap = plan.visited_cap;
+    // queries whose visited table filled up are re-run with a 4x larger table (the result does not depend on the table size)
+    for (int attempt = 0; hc.overflowed > 0 && attempt < 4; attempt++) {
+        std::vector<uint8_t> hover(nq);
+        CK(cudaMemcpy(hover.data(), dover, (size_t)nq, cudaMemcpyDeviceToHost), "D2H overflow flags");
+        std::vector<int32_t> idx;
+        for (int i = 0; i < nq; i++)
+            if (hover[i]) idx.push_back(i);
+        if (idx.empty()) break;
+        retried += (long long)idx.size();
+        cap *= 4;
+        SearchPlan p2;
+        CK(plan_search(approx->d, rr, g->g, topK, rerankK, (int)idx.size(), cap, g_sm_count, &p2), "plan_search(retry)");
+        if ((rc = t_ctx.ensure(5, search_scratch_bytes(p2)))) return rc;
+        CK(cudaMemcpyAsync(dindex, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, s), "H2D retry index");
+        unsigned long long zero = 0;
+        CK(cudaMemcpyAsync(&dcnt->overflowed, &zero, sizeof(zero), cudaMemcpyHostToDevice, s), "reset overflow");
+        CK(cudaEventRecord(t_ctx.ev0, s), "event");
+        CK(launch_search(g->g, approx->d, rr, metric, queries_dev, (int)idx.size(), topK, rerankK, p2, t_ctx.dbuf[5], dwork, nodes_dev, scores_dev, dcnt, dover,
+                         dindex, 0, s),
+           "launch_search(retry)");
+        CK(cudaEventRecord(t_ctx.ev1, s), "event");
+        CK(cudaMemcpyAsync(&hc, dcnt, sizeof(hc), cudaMemcpyDeviceToHost, s), "D2H counters");
+        CK(cudaStreamSynchronize(s), "search kernel (retry)");
+        float ms2 = 0.f;
+        cudaEventElapsedTime(&ms2, t_ctx.ev0, t_ctx.ev1);
+        ms += ms2;
+    }
+    if (hc.overflowed > 0) return fail(JV_ERR_OVERFLOW, "graph_search: visited table overflow after retries");
+    if (stats) {
+        stats->visited = (int64_t)hc.visited;
+        stats->expanded = (int64_t)hc.expanded;
+        stats->expanded_base = (int64_t)hc.expanded_base;
+        stats->reranked = (int64_t)hc.reranked;
+        stats->retried = retried;
+        stats->device_ms = ms;
+    }
+    return JV_OK;
+}
+
+int jv_graph_search_batch_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric, const float *queries_device, int nq, int topK,
+                                 int rerankK, int32_t *nodes_out_device, float *scores_out_device, jv_search_stats *stats)
+{
+    NEED_INIT();
+    return search_device(g, approx, reranker, metric, queries_device, nq, topK, rerankK, nodes_out_device, scores_out_device, stats);
+}
+
+int jv_graph_search_batch(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric, const float *queries, int nq, int topK, int rerankK,
+                          int32_t *nodes_out, float *scores_out, jv_search_stats *stats)
+{
+    NEED_INIT();
+    if (!approx || !queries || !nodes_out || !scores_out || nq <= 0 || topK < 1) return fail(JV_ERR_INVALID, "graph_search: bad arguments");
+    int rc;
+    const size_t qb = (size_t)nq * approx->d.dim * 4, ob = (size_t)nq * topK * 4;
+    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(0, qb)) || (rc = t_ctx.ensure(1, ob)) || (rc = t_ctx.ensure(2, ob))) return rc;
+    cudaStream_t s = t_ctx.stream;
+    CK(cudaMemcpyAsync(t_ctx.dbuf[0], queries, qb, cudaMemcpyHostToDevice, s), "H2D queries");
+    rc = search_device(g, approx, reranker, metric, (const float *)t_ctx.dbuf[0], nq, topK, rerankK, (int32_t *)t_ctx.dbuf[1], (float *)t_ctx.dbuf[2], stats);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(nodes_out, t_ctx.dbuf[1], ob, cudaMemcpyDeviceToHost, s), "D2H nodes");
+    CK(cudaMemcpyAsync(scores_out, t_ctx.dbuf[2], ob, cudaMemcpyDeviceToHost, s), "D2H scores");
+    CK(cudaStreamSynchronize(s), "sync");
+    return JV_OK;
+}
+
+int jv_graph_build(jv_dataset f32, int metric, const jv_build_params *params, jv_graph *out, double *device_ms)
+{
+    NEED_INIT();
+    if (!f32 || !params || !out || f32->d.kind != KIND_F32) return fail(JV_ERR_INVALID, "graph_build: needs an fp32 data set");
+    int rc = check_metric(f32->d, metric);
+    if (rc) return rc;
+    if ((rc = t_ctx.init())) return rc;
+    cudaStream_t s = t_ctx.stream;
+    const int n = (int)f32->d.n, degree = params->degree;
+    if (degree < 1 || degree > 64 || params->beam_width < 1 || params->beam_width > 256 || params->overflow < 1.0f || params->alpha < 1.0f)
+        return fail(JV_ERR_INVALID, "graph_build: need 1 <= degree <= 64, 1 <= beam <= 256, overflow >= 1, alpha >= 1");
+    BuildParams bp;
+    bp.degree = degree; bp.beam = params->beam_width; bp.overflow = params->overflow; bp.alpha = params->alpha; bp.max_batch = params->max_batch;
+    jv_graph g = new jv_graph_s();
+    memset(&g->g, 0, sizeof(GraphDesc));
+    cudaError_t e = cudaMalloc((void **)&g->adj0, (size_t)n * degree * 4);
+    if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaMalloc(adjacency)"); }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, s);
+    BuildStats bs;
+    e = build_graph_flat(f32->d, metric, bp, g->adj0, g_sm_count, &bs, s);
+    cudaEventRecord(e1, s);
+    cudaStreamSynchronize(s);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) { delete g; return cuda_fail(e, "build_graph_flat"); }
+    g->g.n = n; g->g.degree = degree; g->g.levels = 1; g->g.entry_node = 0; g->g.entry_level = 0; g->g.adj0 = g->adj0;
+    if (params->add_hierarchy && n > 1) {
+        // HNSW-style levels (GraphIndexBuilder.java:562-575): level(node) = floor(-ln(U) / ln(M)); every upper level is a
+        // Vamana graph over its members, built with the same device builder on the gathered rows.
+        uint64_t st = params->seed ? params->seed : 0x9E3779B97F4A7C15ull;
+        auto next_u = [&st]() {
+            st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+            return ((st >> 11) + 1) * (1.0 / 9007199254740993.0);
+        };
+        const double ml = degree == 1 ? 1.0 : 1.0 / log((double)degree);
+        std::vector<int> level(n);
+        int maxl = 0;
+        for (int i = 0; i < n; i++) {
+            level[i] = (int)(-log(next_u()) * ml);
+            maxl = std::max(maxl, level[i]);
+        }
+        // the entry point is a node of the top level
+        int entry = 0;
+        for (int i = 0; i < n; i++)
+            if (level[i] == maxl) { entry = i; break; }
+        g->g.entry_node = entry;
+        std::vector<float> host_rows;
+        for (int l = 1; l <= maxl; l++) {
+            std::vector<int32_t> ids;
+            for (int i = 0; i < n; i++)
+                if (level[i] >= l) ids.push_back(i);
+            const int cnt = (int)ids.size();
+            std::vector<int32_t> ladj((size_t)cnt * degree, -1);
+            if (cnt > 1) {
+                // gather the members' rows into a temporary data set on the device
+                jv_dataset_s sub;
+                memset(&sub.d, 0, sizeof(DataDesc));
+                sub.d.kind = KIND_F32; sub.d.dim = f32->d.dim; sub.d.stride = f32->d.stride; sub.d.n = cnt;
+                float *drows = nullptr;
+                int32_t *dadj = nullptr;
+                if ((rc = sub.alloc((void **)&drows, (size_t)cnt * sub.d.stride * 4)) || (rc = sub.alloc((void **)&dadj, (size_t)cnt * degree * 4))) { delete g; return rc; }
+                for (int i = 0; i < cnt; i++) {
+                    e = cudaMemcpyAsync(drows + (size_t)i * sub.d.stride, f32->d.rows + (size_t)ids[i] * f32->d.stride, (size_t)sub.d.stride * 4,
+                                        cudaMemcpyDeviceToDevice, s);
+                    if (e != cudaSuccess) { delete g; return cuda_fail(e, "gather level rows"); }
+                }
+                sub.d.rows = drows;
+                BuildStats bs2;
+                e = build_graph_flat(sub.d, metric, bp, dadj, g_sm_count, &bs2, s);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(ladj.data(), dadj, ladj.size() * 4, cudaMemcpyDeviceToHost, s);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+                if (e != cudaSuccess) { delete g; return cuda_fail(e, "build upper level"); }
+                for (auto &x : ladj)
+                    if (x >= 0) x = ids[x];
+            }
+            g->level_ids.push_back(ids);
+            g->level_adj.push_back(ladj);
+        }
+        if ((rc = graph_rebuild_upper(g))) { delete g; return rc; }
+    }
+    if (device_ms) *device_ms = ms;
+    *out = g;
+    return JV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ memory helpers
+int jv_device_malloc(void **out, size_t bytes)
+{
+    NEED_INIT();
+    if (!out) return fail(JV_ERR_INVALID, "device_malloc: null");
+    CK(cudaMalloc(out, bytes ? bytes : 16), "cudaMalloc");
+    return JV_OK;
+}
+int jv_device_free(void *p)
+{
+    NEED_INIT();
+    CK(cudaFree(p), "cudaFree");
+    return JV_OK;
+}
+int jv_memcpy_h2d(void *dst, const void *src, size_t bytes)
+{
+    NEED_INIT();
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice), "cudaMemcpy H2D");
+    return JV_OK;
+}
+int jv_memcpy_d2h(void *dst, const void *src, size_t bytes)
+{
+    NEED_INIT();
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost), "cudaMemcpy D2H");
+    return JV_OK;
+}
+int jv_host_register(void *p, size_t bytes)
+{
+    NEED_INIT();
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterDefault), "cudaHostRegister");
+    return JV_OK;
+}
+int jv_host_unregister(void *p)
+{
+    NEED_INIT();
+    CK(cudaHostUnregister(p), "cudaHostUnregister");
+    return JV_OK;
+}
+int jv_device_synchronize(void)
+{
+    NEED_INIT();
+    CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    return JV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (internal; the public surface is include/jvector_b200.h)
+#pragma once
+#include <atomic>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "scorers.cuh"
+
+namespace jv {
+
+extern std::atomic<long long> g_launches;
+constexpr int MAX_DEGREE = 128;  // widest adjacency row the search kernel accepts  // kernels launched by this library (jv_kernel_launch_count)
+
+struct GraphDesc {
+    int32_t n;
+    int degree;
+    int levels;  // >= 1
+    int32_t entry_node;
+    int entry_level;
+    const int32_t *adj0;       // [n][degree]
+    const int32_t *upper_row;  // [(levels-1)][n] row index or -1 (nullptr when levels == 1)
+    const int32_t *upper_adj;  // rows of all upper levels, concatenated
+    const long long *upper_off;  // [(levels-1)] first row of each level in upper_adj (device)
+};
+
+struct SearchCounters {  // device-side totals
+    unsigned long long visited, expanded, expanded_base, reranked, overflowed;
+};
+
+// ---- kernels_batch.cu ----
+cudaError_t launch_prepare(const DataDesc &d, int metric, const float *queries_dev, int nq, float *blobs_dev, cudaStream_t s);
+// ragged: query qi scores ids[offsets[qi]..offsets[qi+1]); offsets == nullptr: every query scores ids[0..n) -> scores[qi*n + i]
+cudaError_t launch_score_ragged(const DataDesc &d, int metric, const float *blobs_dev, int nq, const int32_t *ids_dev,
+                                const int32_t *offsets_dev, int n_shared, int max_per_query, float *scores_dev, cudaStream_t s);
+cudaError_t launch_score_pairs(const DataDesc &d, int metric, const int32_t *a_dev, const int32_t *b_dev, int n, float *out_dev, cudaStream_t s);
+
+struct TopkScratch {
+    int32_t *sample_ids;   // [S]
+    float *sample_scores;  // [nq][S]
+    long long *thr;        // [nq]
+    long long *buf;        // [nq][cap]
+    int *cnt;              // [nq]
+    int S, cap;
+};
+cudaError_t launch_topk_bruteforce(const DataDesc &d, int metric, const float *blobs_dev, int nq, int k, const TopkScratch &ts,
+                                   long long *keys_out_dev, int *overflow_flag_dev, cudaStream_t s);
+
+cudaError_t launch_bq_encode(const float *rows_dev, long long n, int dim, unsigned long long *words_dev, cudaStream_t s);
+cudaError_t launch_pq_encode(const DataDesc &pq, const float *rows_dev, long long n, uint8_t *codes_dev, cudaStream_t s);
+cudaError_t launch_pq_self_magnitudes(const DataDesc &pq, float *mag_dev, cudaStream_t s);
+cudaError_t launch_nvq_encode(const float *rows_dev, long long n, int dim, int nsub, const int *sizes_dev, const int *offsets_dev,
+                              const float *mean_dev, int learn, float *params_dev, uint8_t *bytes_dev, int byte_stride, cudaStream_t s);
+
+// ---- search.cu ----
+struct SearchPlan {
+    int threads;
+    size_t smem_bytes;
+    int ctas;
+    int list_cap;     // rerankK rounded
+    int visited_cap;  // power of two
+};
+cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const GraphDesc &g, int topK, int rerankK, int nq,
+                        int visited_cap_hint, int sm_count, SearchPlan *plan);
+size_t search_scratch_bytes(const SearchPlan &p);
+cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const DataDesc *rerank, int metric, const float *queries_dev,
+                          int nq, int topK, int rerankK, const SearchPlan &plan, void *scratch_dev, int *work_counter_dev,
+                          int32_t *nodes_out_dev, float *scores_out_dev, SearchCounters *counters_dev, uint8_t *overflow_flags_dev,
+                          const int32_t *query_index_dev, int query_stride, cudaStream_t s);
+
+// ---- build.cu ----
+struct BuildParams {
+    int degree, beam;
+    float overflow, alpha;
+    int max_batch;
+};
+struct BuildStats {
+    long long searched, pruned, dropped_backlinks, batches;
+};
+// flat Vamana graph over rows [0, n) of an f32 data set; adj_out_dev [n][degree] (-1 padded); entry node is 0
+cudaError_t build_graph_flat(const DataDesc &f32, int metric, const BuildParams &bp, int32_t *adj_out_dev, int sm_count,
+                             BuildStats *stats, cudaStream_t s);
+
+}  // namespace jv

@@ -1,0 +1,443 @@
+// kernels_batch.cu — batched scoring kernels: one launch per hop / rerank list / multi-query step / brute-force pass.
+// HBM-bound reductions and gathers: CUDA cores, 128-bit loads, shuffle reductions; no tensor cores.
+#include "kernels.h"
+
+namespace jv {
+
+std::atomic<long long> g_launches{0};
+
+#define JV_DISPATCH_KIND_METRIC(kind, metric, CALL)                                            \
+    do {                                                                                        \
+        if ((kind) == KIND_F32) {                                                               \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN); }       \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT); }              \
+            else { CALL(KIND_F32, JV_METRIC_COSINE); }                                          \
+        } else if ((kind) == KIND_PQ) {                                                         \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_PQ, JV_METRIC_EUCLIDEAN); }        \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_PQ, JV_METRIC_DOT); }               \
+            else { CALL(KIND_PQ, JV_METRIC_COSINE); }                                           \
+        } else if ((kind) == KIND_BQ) {                                                         \
+            CALL(KIND_BQ, JV_METRIC_COSINE);                                                    \
+        } else {                                                                                \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_NVQ, JV_METRIC_EUCLIDEAN); }       \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_NVQ, JV_METRIC_DOT); }              \
+            else { CALL(KIND_NVQ, JV_METRIC_COSINE); }                                          \
+        }                                                                                       \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// query preparation: one CTA per query (LUT build = the M calculatePartialSums calls of PQDecoder.java:48-53)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prepare_kernel(DataDesc d, int metric, const float *__restrict__ queries, float *__restrict__ blobs, int blob_stride)
+{
+    __shared__ float red[36];
+    prepare_blob(d, metric, queries + (size_t)blockIdx.x * d.dim, blobs + (size_t)blockIdx.x * blob_stride, red);
+}
+
+cudaError_t launch_prepare(const DataDesc &d, int metric, const float *queries_dev, int nq, float *blobs_dev, cudaStream_t s)
+{
+    if (nq <= 0) return cudaSuccess;
+    prepare_kernel<<<nq, 256, 0, s>>>(d, metric, queries_dev, blobs_dev, blob_floats(d));
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// ragged scoring: grid = (chunks, nq); each CTA scores up to CHUNK ids of one query, one lane-group per id
+// ------------------------------------------------------------------------------------------------
+constexpr int RAGGED_THREADS = 128;
+constexpr int RAGGED_CHUNK = 128;
+
+template <int KIND, int METRIC>
+__global__ void __launch_bounds__(RAGGED_THREADS) score_ragged_kernel(DataDesc d, const float *__restrict__ blobs, int blob_stride,
+                                                                      const int32_t *__restrict__ ids, const int32_t *__restrict__ offsets,
+                                                                      int n_shared, float *__restrict__ scores)
+{
+    constexpr int G = GroupOf<KIND>::value;
+    const int q = blockIdx.y;
+    int begin, count;
+    size_t out_base;
+    if (offsets) {
+        begin = offsets[q];
+        count = offsets[q + 1] - begin;
+        out_base = (size_t)begin;
+    } else {
+        begin = 0;
+        count = n_shared;
+        out_base = (size_t)q * n_shared;
+    }
+    const int c0 = blockIdx.x * RAGGED_CHUNK;
+    if (c0 >= count) return;
+    const int c1 = min(count, c0 + RAGGED_CHUNK);
+    const float *blob = blobs + (size_t)q * blob_stride;
+    const int group = threadIdx.x / G, lane = threadIdx.x % G;
+    constexpr int NG = RAGGED_THREADS / G;
+    for (int i = c0 + group; i < c1; i += NG) {
+        const int node = ids[begin + i];
+        float sc = 0.f;
+        if (node >= 0 && node < d.n) sc = score_row<KIND, METRIC>(d, blob, node, lane);
+        if (lane == 0) scores[out_base + i] = sc;
+    }
+}
+
+cudaError_t launch_score_ragged(const DataDesc &d, int metric, const float *blobs_dev, int nq, const int32_t *ids_dev,
+                                const int32_t *offsets_dev, int n_shared, int max_per_query, float *scores_dev, cudaStream_t s)
+{
+    if (nq <= 0 || max_per_query <= 0) return cudaSuccess;
+    dim3 grid((max_per_query + RAGGED_CHUNK - 1) / RAGGED_CHUNK, nq);
+    if (grid.y > 65535u) return cudaErrorInvalidValue;
+#define CALL(K, M) score_ragged_kernel<K, M><<<grid, RAGGED_THREADS, 0, s>>>(d, blobs_dev, blob_floats(d), ids_dev, offsets_dev, n_shared, scores_dev)
+    JV_DISPATCH_KIND_METRIC(d.kind, metric, CALL);
+#undef CALL
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// pairs: one warp per (a, b) pair — the candidate x selected scores of VamanaDiversityProvider.retainDiverse
+// ------------------------------------------------------------------------------------------------
+template <int KIND, int METRIC>
+__global__ void __launch_bounds__(128) score_pairs_kernel(DataDesc d, const int32_t *__restrict__ a, const int32_t *__restrict__ b, int n, float *__restrict__ out)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const int x = a[warp], y = b[warp];
+    float sc;
+    if (KIND == KIND_F32) sc = pair_f32<METRIC>(d, x, y, lane);
+    else if (KIND == KIND_PQ) sc = pair_pq<METRIC>(d, x, y, lane);
+    else sc = pair_bq(d, x, y, lane);
+    if (lane == 0) out[warp] = sc;
+}
+
+cudaError_t launch_score_pairs(const DataDesc &d, int metric, const int32_t *a_dev, const int32_t *b_dev, int n, float *out_dev, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    if (d.kind == KIND_NVQ) return cudaErrorNotSupported;
+    const int blocks = (n * 32 + 127) / 128;
+#define CALL(K, M) score_pairs_kernel<K, M><<<blocks, 128, 0, s>>>(d, a_dev, b_dev, n, out_dev)
+    if (d.kind == KIND_F32) {
+        if (metric == JV_METRIC_EUCLIDEAN) CALL(KIND_F32, JV_METRIC_EUCLIDEAN);
+        else if (metric == JV_METRIC_DOT) CALL(KIND_F32, JV_METRIC_DOT);
+        else CALL(KIND_F32, JV_METRIC_COSINE);
+    } else if (d.kind == KIND_PQ) {
+        if (metric == JV_METRIC_EUCLIDEAN) CALL(KIND_PQ, JV_METRIC_EUCLIDEAN);
+        else if (metric == JV_METRIC_DOT) CALL(KIND_PQ, JV_METRIC_DOT);
+        else CALL(KIND_PQ, JV_METRIC_COSINE);
+    } else CALL(KIND_BQ, JV_METRIC_COSINE);
+#undef CALL
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// brute-force top-k: sample -> per-query threshold -> filtered full pass -> per-query sort.
+// Keys are the reference's 64-bit ordering key (NodeQueue.java:125-137), so ties go to the smaller node id.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort_desc(long long *keys, int n_pow2)
+{
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const long long a = keys[i], b = keys[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) topk_sample_ids_kernel(int32_t *ids, int S, long long n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S) ids[i] = (int32_t)(((long long)i * n) / S);
+}
+
+// thr[q] = k-th best key of the sample (a lower bound of the final k-th best); KEY_MIN when the sample is too small
+__global__ void __launch_bounds__(256) topk_threshold_kernel(const float *__restrict__ sample_scores, const int32_t *__restrict__ sample_ids, int S, int S_pow2,
+                                                             int k, long long *__restrict__ thr, int *__restrict__ cnt)
+{
+    extern __shared__ long long skeys[];
+    const int q = blockIdx.x;
+    for (int i = threadIdx.x; i < S_pow2; i += blockDim.x)
+        skeys[i] = i < S ? topk_key(sample_scores[(size_t)q * S + i], sample_ids[i]) : KEY_MIN;
+    __syncthreads();
+    bitonic_sort_desc(skeys, S_pow2);
+    if (threadIdx.x == 0) {
+        thr[q] = (k <= S) ? skeys[k - 1] : KEY_MIN;
+        cnt[q] = 0;
+    }
+}
+
+constexpr int BF_THREADS = 256;
+constexpr int BF_TILE = 2048;  // rows per CTA
+
+template <int KIND, int METRIC>
+__global__ void __launch_bounds__(BF_THREADS) topk_filter_kernel(DataDesc d, const float *__restrict__ blobs, int blob_stride, const long long *__restrict__ thr,
+                                                                 long long *__restrict__ buf, int *__restrict__ cnt, int cap)
+{
+    constexpr int G = GroupOf<KIND>::value;
+    constexpr int NG = BF_THREADS / G;
+    const int q = blockIdx.x;
+    const long long r0 = (long long)blockIdx.y * BF_TILE;
+    const long long r1 = min(d.n, r0 + BF_TILE);
+    const float *blob = blobs + (size_t)q * blob_stride;
+    const long long t = thr[q];
+    const int group = threadIdx.x / G, lane = threadIdx.x % G;
+    for (long long r = r0 + group; r < r1; r += NG) {
+        const float sc = score_row<KIND, METRIC>(d, blob, (int)r, lane);
+        if (lane == 0) {
+            const long long key = topk_key(sc, (int32_t)r);
+            if (key >= t) {
+                const int pos = atomicAdd(&cnt[q], 1);
+                if (pos < cap) buf[(size_t)q * cap + pos] = key;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) topk_select_kernel(const long long *__restrict__ buf, const int *__restrict__ cnt, int cap, int cap_pow2, int k,
+                                                          long long *__restrict__ keys_out, int *__restrict__ overflow)
+{
+    extern __shared__ long long skeys[];
+    const int q = blockIdx.x;
+    const int c = cnt[q];
+    if (c > cap && threadIdx.x == 0) atomicExch(overflow, 1);
+    const int m = min(c, cap);
+    for (int i = threadIdx.x; i < cap_pow2; i += blockDim.x) skeys[i] = i < m ? buf[(size_t)q * cap + i] : KEY_MIN;
+    __syncthreads();
+    bitonic_sort_desc(skeys, cap_pow2);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) keys_out[(size_t)q * k + i] = i < m ? skeys[i] : KEY_MIN;
+}
+
+static int next_pow2(int v)
+{
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+cudaError_t launch_topk_bruteforce(const DataDesc &d, int metric, const float *blobs_dev, int nq, int k, const TopkScratch &ts,
+                                   long long *keys_out_dev, int *overflow_flag_dev, cudaStream_t s)
+{
+    if (nq <= 0) return cudaSuccess;
+    cudaError_t e;
+    const int S = ts.S;
+    topk_sample_ids_kernel<<<(S + 255) / 256, 256, 0, s>>>(ts.sample_ids, S, d.n);
+    g_launches++;
+    if ((e = launch_score_ragged(d, metric, blobs_dev, nq, ts.sample_ids, nullptr, S, S, ts.sample_scores, s)) != cudaSuccess) return e;
+    const int S2 = next_pow2(S);
+    // k-th best of the sample; when the sample IS the data set (n <= S) ask for everything
+    topk_threshold_kernel<<<nq, 256, (size_t)S2 * sizeof(long long), s>>>(ts.sample_scores, ts.sample_ids, S, S2, (d.n <= S) ? S + 1 : k, ts.thr, ts.cnt);
+    g_launches++;
+    dim3 grid(nq, (unsigned)((d.n + BF_TILE - 1) / BF_TILE));
+    if (grid.y > 65535u) return cudaErrorInvalidValue;
+#define CALL(K, M) topk_filter_kernel<K, M><<<grid, BF_THREADS, 0, s>>>(d, blobs_dev, blob_floats(d), ts.thr, ts.buf, ts.cnt, ts.cap)
+    JV_DISPATCH_KIND_METRIC(d.kind, metric, CALL);
+#undef CALL
+    g_launches++;
+    const int cap2 = next_pow2(ts.cap);
+    topk_select_kernel<<<nq, 256, (size_t)cap2 * sizeof(long long), s>>>(ts.buf, ts.cnt, ts.cap, cap2, k, keys_out_dev, overflow_flag_dev);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// bulk encoders
+// ------------------------------------------------------------------------------------------------
+// BinaryQuantization.encodeTo (BinaryQuantization.java:96-109): one warp per 32 dimensions via ballot
+__global__ void __launch_bounds__(256) bq_encode_kernel(const float *__restrict__ rows, long long n, int dim, unsigned *__restrict__ halves, int halves_per_row)
+{
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long total = n * halves_per_row;
+    if (warp >= total) return;
+    const long long r = warp / halves_per_row;
+    const int h = (int)(warp - r * halves_per_row);
+    const int idx = h * 32 + lane;
+    const bool bit = idx < dim && rows[r * dim + idx] > 0.f;
+    const unsigned b = __ballot_sync(FULL, bit);
+    if (lane == 0) halves[warp] = b;
+}
+
+cudaError_t launch_bq_encode(const float *rows_dev, long long n, int dim, unsigned long long *words_dev, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    const int hp = 2 * ((dim + 63) / 64);
+    const long long warps = n * hp;
+    const long long blocks = (warps * 32 + 255) / 256;
+    bq_encode_kernel<<<(unsigned)blocks, 256, 0, s>>>(rows_dev, n, dim, reinterpret_cast<unsigned *>(words_dev), hp);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ProductQuantization.encode (ProductQuantization.java:507-520): code[m] = argmin_c ||v[off_m..] - centroid_{m,c}||^2, first
+// minimum wins. One warp per (row, subspace); lanes stride over the k centroids, then an arg-min shuffle that prefers
+// the smaller index on ties.
+__global__ void __launch_bounds__(256) pq_encode_kernel(DataDesc pq, const float *__restrict__ rows, long long n, uint8_t *__restrict__ codes)
+{
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n * pq.M) return;
+    const long long r = warp / pq.M;
+    const int m = (int)(warp - r * pq.M);
+    const int sz = pq.sub_sizes[m], off = pq.sub_offsets[m];
+    const float *v = rows + r * pq.dim + off;
+    const float *cb = pq.codebooks + (size_t)pq.k * off;
+    float best = __int_as_float(0x7f800000);
+    int bi = 0x7fffffff;
+    for (int c = lane; c < pq.k; c += 32) {
+        const float *cen = cb + (size_t)c * sz;
+        float s = 0.f;
+        for (int j = 0; j < sz; j++) {
+            float x = v[j];
+            if (pq.centroid) x = __fsub_rn(x, pq.centroid[off + j]);
+            // squareDistance(codebook, c*size, vector, off, size): (a - b)^2 accumulated in order
+            const float df = __fsub_rn(cen[j], x);
+            s = __fadd_rn(s, __fmul_rn(df, df));
+        }
+        if (s < best) { best = s; bi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) codes[r * pq.M + m] = (uint8_t)(bi == 0x7fffffff ? 0 : bi);
+}
+
+cudaError_t launch_pq_encode(const DataDesc &pq, const float *rows_dev, long long n, uint8_t *codes_dev, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    const long long warps = n * pq.M;
+    const long long blocks = (warps * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    pq_encode_kernel<<<(unsigned)blocks, 256, 0, s>>>(pq, rows_dev, n, codes_dev);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// calculatePartialSelfMagnitudes (PQDecoder.java:93-105): mag[m*k + c] = ||centroid_{m,c}||^2, query independent
+__global__ void __launch_bounds__(256) pq_self_mag_kernel(DataDesc pq, float *__restrict__ mag)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= pq.M * pq.k) return;
+    const int m = e / pq.k, c = e - m * pq.k;
+    const int sz = pq.sub_sizes[m];
+    const float *cen = pq.codebooks + (size_t)pq.k * pq.sub_offsets[m] + (size_t)c * sz;
+    float s = 0.f;
+    for (int j = 0; j < sz; j++) s = fmaf(cen[j], cen[j], s);
+    mag[e] = s;
+}
+
+cudaError_t launch_pq_self_magnitudes(const DataDesc &pq, float *mag_dev, cudaStream_t s)
+{
+    const int total = pq.M * pq.k;
+    pq_self_mag_kernel<<<(total + 255) / 256, 256, 0, s>>>(pq, mag_dev);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// NVQuantization.encodeTo + QuantizedSubVector.quantizeTo (NVQuantization.java:211-214,524-578): one warp per
+// (row, sub-vector): min/max, optional growth-rate grid search (20 coarse + 20 fine nvqLoss evaluations against the
+// uniform-loss baseline), then nvqQuantize8bit. Follows the native kernels' arithmetic (native-c:...:1149-1303).
+__device__ __forceinline__ float nvq_loss_warp(const float *v, const float *mean, int n, float alpha, float minv, float maxv, int lane)
+{
+    const NvqConsts c = nvq_setup(minv, maxv, alpha, 0.f, 255.0f);
+    const float inv = __fdiv_rn(1.0f, c.scale);
+    float s = 0.f;
+    for (int i = lane; i < n; i += 32) {
+        const float x = __fsub_rn(v[i], mean[i]);
+        const float r = __fmul_rn(__fsub_rn(nvq_logistic(x, c.sa, c.sx0), c.bias), inv);
+        const float rq = (float)__float2int_rz(__fadd_rn(r, 0.5f));
+        const float df = __fsub_rn(x, nvq_dequant(c, rq));
+        s = __fmaf_rn(df, df, s);
+    }
+    return group_sum<32>(s);
+}
+
+__global__ void __launch_bounds__(256) nvq_encode_kernel(const float *__restrict__ rows, long long n, int dim, int nsub, const int *__restrict__ sizes,
+                                                         const int *__restrict__ offsets, const float *__restrict__ mean, int learn,
+                                                         float *__restrict__ params, uint8_t *__restrict__ bytes, int byte_stride)
+{
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n * nsub) return;
+    const long long r = warp / nsub;
+    const int sv = (int)(warp - r * nsub);
+    const int sz = sizes[sv], off = offsets[sv];
+    const float *v = rows + r * dim + off;
+    const float *mu = mean + off;
+    float minv = 3.402823466e+38f, maxv = -3.402823466e+38f;
+    for (int i = lane; i < sz; i += 32) {
+        const float x = __fsub_rn(v[i], mu[i]);
+        minv = fminf(minv, x);
+        maxv = fmaxf(maxv, x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        minv = fminf(minv, __shfl_xor_sync(FULL, minv, o));
+        maxv = fmaxf(maxv, __shfl_xor_sync(FULL, maxv, o));
+    }
+    float growth = 1e-2f;
+    if (learn) {
+        // baseline = nvqUniformLoss (native-c:...:1258-1303)
+        const float constant = 255.0f, delta = __fsub_rn(maxv, minv);
+        float us = 0.f;
+        for (int i = lane; i < sz; i += 32) {
+            const float x = __fsub_rn(v[i], mu[i]);
+            const float rr = __fmul_rn(__fsub_rn(x, minv), __fdiv_rn(constant, delta));
+            const float rq = (float)__float2int_rz(__fadd_rn(rr, 0.5f));
+            const float rec = __fmaf_rn(rq, __fdiv_rn(delta, constant), minv);
+            const float df = __fsub_rn(x, rec);
+            us = __fmaf_rn(df, df, us);
+        }
+        const float baseline = group_sum<32>(us);
+        float coarse = 1e-2f, best = 1.40129846e-45f;
+        for (float gr = 1e-6f; gr < 20.f; gr = __fadd_rn(gr, 1.f)) {
+            const float lv = __fdiv_rn(baseline, nvq_loss_warp(v, mu, sz, gr, minv, maxv, lane));
+            if (lv > best) { best = lv; coarse = gr; }
+        }
+        float fine = coarse;
+        for (float gr = __fsub_rn(coarse, 1.f); gr < __fadd_rn(coarse, 1.f); gr = __fadd_rn(gr, 0.1f)) {
+            const float lv = __fdiv_rn(baseline, nvq_loss_warp(v, mu, sz, gr, minv, maxv, lane));
+            if (lv > best) { best = lv; fine = gr; }
+        }
+        growth = fine;
+    }
+    // nvq_quantize_8bit (native-c:...:1149-1197); the reference build fuses (L - bias) * inv + 0.5 into one fma
+    {
+        const float delta = __fsub_rn(maxv, minv), sa = __fdiv_rn(growth, delta), sx0 = __fmul_rn(0.f, delta);
+        const float bias = nvq_logistic(minv, sa, sx0);
+        const float inv = __fdiv_rn(255.0f, __fsub_rn(nvq_logistic(maxv, sa, sx0), bias));
+        uint8_t *dst = bytes + r * byte_stride + off;
+        for (int i = lane; i < sz; i += 32) {
+            const float x = __fsub_rn(v[i], mu[i]);
+            const float a = __fmaf_rn(__fsub_rn(nvq_logistic(x, sa, sx0), bias), inv, 0.5f);
+            const int qv = __float2int_rz(a);
+            dst[i] = (uint8_t)(qv < 0 ? 0 : qv > 255 ? 255 : qv);
+        }
+    }
+    if (lane == 0) {
+        float4 p = make_float4(minv, maxv, growth, 0.f);
+        reinterpret_cast<float4 *>(params)[warp] = p;
+    }
+}
+
+cudaError_t launch_nvq_encode(const float *rows_dev, long long n, int dim, int nsub, const int *sizes_dev, const int *offsets_dev,
+                              const float *mean_dev, int learn, float *params_dev, uint8_t *bytes_dev, int byte_stride, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    const long long warps = n * nsub;
+    const long long blocks = (warps * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    nvq_encode_kernel<<<(unsigned)blocks, 256, 0, s>>>(rows_dev, n, dim, nsub, sizes_dev, offsets_dev, mean_dev, learn, params_dev, bytes_dev, byte_stride);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace jv

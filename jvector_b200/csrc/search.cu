@@ -1,0 +1,372 @@
+// search.cu — GraphSearcher.search, device resident: one CTA walks one query through the whole traversal
+// (base:graph/GraphSearcher.java:263-282 internalSearch, :334-353 initializeInternal, :355-370 stopSearch,
+//  :406-457 searchOneLayer, :471-507 reranking; neighbour loop base:graph/OnHeapGraphIndex.java:475-483).
+//
+// State per query, all in shared memory except the visited set:
+//   * ONE list sorted by the reference's 64-bit key holding the best `rerankK` nodes SEEN so far, each with an
+//     "expanded" flag. The reference keeps a max-heap of unexpanded candidates plus a bounded min-heap of the best
+//     rerankK expanded ones and stops when |results| >= rerankK and best candidate < worst result; that is exactly
+//     "the first unexpanded entry of the merged sorted list lies at position >= rerankK" (a node outside the best
+//     rerankK seen can never be expanded before the stop condition fires, and the list only tightens). Exact up to
+//     score ties at the list boundary (the reference expands an equal-score candidate once more).
+//   * upper levels run with window K = 1 over the same list; moving down a level clears the expanded flags, which is
+//     setEntryPointsFromPreviousLayer (results + evicted + remaining candidates all become candidates again).
+//   * visited = open-addressing hash set in a per-CTA slice of global scratch (L2 resident), never cleared between
+//     levels (GraphSearcher keeps `visited` across levels).
+// Every hop is: read one adjacency row -> filter through visited -> score the survivors with the row scorers of
+// scorers.cuh (one lane group per candidate) -> parallel rank-merge into the list.
+#include <limits.h>
+
+#include "kernels.h"
+
+namespace jv {
+
+struct SearchParams {
+    GraphDesc g;
+    DataDesc approx;
+    DataDesc rerank;
+    int has_rerank;
+    int metric;
+    const float *queries;
+    int query_stride;
+    int nq, topK, rerankK;
+    int list_pow2;  // list buffers hold this many keys (>= rerankK, power of two)
+    int visited_cap;
+    int visited_shift;
+    int32_t *visited_tables;
+    int *work_counter;
+    int32_t *nodes_out;
+    float *scores_out;
+    SearchCounters *counters;
+    uint8_t *overflow;
+    const int32_t *query_index;
+    int blobA_floats, blobR_floats;
+};
+
+__device__ __forceinline__ bool visited_insert(int32_t *t, unsigned mask, int shift, int32_t v)
+{
+    unsigned h = ((unsigned)v * 2654435761u) >> shift;
+    for (unsigned probes = 0; probes <= mask; ++probes) {
+        const int old = atomicCAS(&t[h], -1, v);
+        if (old == -1) return true;
+        if (old == v) return false;
+        h = (h + 1) & mask;
+    }
+    return false;
+}
+
+// number of keys in the descending-sorted array a[0..n) that are greater than k
+__device__ __forceinline__ int count_greater_desc(const long long *a, int n, long long k)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] > k) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void bitonic_sort_desc_block(long long *keys, int n_pow2)
+{
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const long long a = keys[i], b = keys[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+constexpr int SEARCH_THREADS = 256;
+
+template <int KIND, int METRIC>
+__global__ void __launch_bounds__(SEARCH_THREADS) graph_search_kernel(SearchParams P)
+{
+    constexpr int G = GroupOf<KIND>::value;
+    constexpr int NG = SEARCH_THREADS / G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *blobA = reinterpret_cast<float *>(smem_raw);
+    float *blobR = blobA + P.blobA_floats;
+    long long *keys0 = reinterpret_cast<long long *>(blobR + P.blobR_floats);
+    long long *keys1 = keys0 + P.list_pow2;
+    long long *cand_keys = keys1 + P.list_pow2;
+    int32_t *cand_ids = reinterpret_cast<int32_t *>(cand_keys + MAX_DEGREE);
+    uint8_t *flags0 = reinterpret_cast<uint8_t *>(cand_ids + MAX_DEGREE);
+    uint8_t *flags1 = flags0 + P.list_pow2;
+    __shared__ float red[36];
+    __shared__ int s_q, s_pos, s_n;
+
+    const int tid = threadIdx.x;
+    const int group = tid / G, lane = tid % G;
+    const int L = P.rerankK;
+    const unsigned vmask = (unsigned)P.visited_cap - 1u;
+    int32_t *table = P.visited_tables + (size_t)blockIdx.x * P.visited_cap;
+    const int degree = P.g.degree;
+
+    for (;;) {
+        if (tid == 0) s_q = atomicAdd(P.work_counter, 1);
+        __syncthreads();
+        const int wq = s_q;
+        if (wq >= P.nq) break;
+        const int qi = P.query_index ? P.query_index[wq] : wq;
+        const float *q = P.queries + (size_t)qi * P.query_stride;
+
+        prepare_blob(P.approx, P.metric, q, blobA, red);
+        if (P.has_rerank) prepare_blob(P.rerank, P.metric, q, blobR, red);
+        {
+            int4 *t4 = reinterpret_cast<int4 *>(table);
+            const int4 m1 = make_int4(-1, -1, -1, -1);
+            for (int i = tid; i < (P.visited_cap >> 2); i += SEARCH_THREADS) t4[i] = m1;
+        }
+        __syncthreads();
+
+        long long *cur = keys0, *nxt = keys1;
+        uint8_t *fcur = flags0, *fnxt = flags1;
+        // initializeInternal: score the entry node, mark it visited (GraphSearcher.java:346-348)
+        if (group == 0) {
+            const float sc = score_row<KIND, METRIC>(P.approx, blobA, P.g.entry_node, lane);
+            if (lane == 0) {
+                cur[0] = topk_key(sc, P.g.entry_node);
+                visited_insert(table, vmask, P.visited_shift, P.g.entry_node);
+            }
+        }
+        int size = 1;
+        int table_cnt = 1;
+        unsigned visited = 0, expanded = 0, expanded_base = 0;
+        bool failed = false;
+        __syncthreads();
+
+        for (int lvl = P.g.entry_level; lvl >= 0 && !failed; --lvl) {
+            const int K = lvl > 0 ? 1 : L;
+            for (int i = tid; i < size; i += SEARCH_THREADS) fcur[i] = 0;
+            for (;;) {
+                if (tid == 0) { s_pos = INT_MAX; s_n = 0; }
+                __syncthreads();
+                const int lim = min(size, K);
+                for (int i = tid; i < lim; i += SEARCH_THREADS)
+                    if (!fcur[i]) { atomicMin(&s_pos, i); break; }
+                __syncthreads();
+                const int p = s_pos;
+                if (p == INT_MAX) break;  // stopSearch: every node of the best-K window is expanded
+                const int node = key_node(cur[p]);
+                if (tid == 0) fcur[p] = 1;
+                expanded++;
+                if (lvl == 0) expanded_base++;
+                const int32_t *nb;
+                if (lvl == 0) nb = P.g.adj0 + (size_t)node * degree;
+                else {
+                    const int32_t row = P.g.upper_row[(size_t)(lvl - 1) * P.g.n + node];
+                    nb = row >= 0 ? P.g.upper_adj + ((size_t)P.g.upper_off[lvl - 1] + row) * degree : nullptr;
+                }
+                // processNeighbors: score a neighbour only if visited.add() says it is new (OnHeapGraphIndex.java:478)
+                if (nb)
+                    for (int t = tid; t < degree; t += SEARCH_THREADS) {
+                        const int32_t f = __ldg(nb + t);
+                        if (f >= 0 && visited_insert(table, vmask, P.visited_shift, f)) cand_ids[atomicAdd(&s_n, 1)] = f;
+                    }
+                __syncthreads();
+                const int n = s_n;
+                table_cnt += n;
+                if (table_cnt * 2 > P.visited_cap) { failed = true; break; }
+                for (int i = group; i < n; i += NG) {
+                    const int32_t f = cand_ids[i];
+                    const float sc = score_row<KIND, METRIC>(P.approx, blobA, f, lane);
+                    if (lane == 0) cand_keys[i] = topk_key(sc, f);
+                }
+                __syncthreads();
+                visited += n;
+                // rank-merge (old list is sorted; candidates are few): every element computes its slot directly
+                for (int i = tid; i < size; i += SEARCH_THREADS) {
+                    const long long k = cur[i];
+                    int c = 0;
+                    for (int j = 0; j < n; j++) c += (cand_keys[j] > k);
+                    const int np = i + c;
+                    if (np < L) { nxt[np] = k; fnxt[np] = fcur[i]; }
+                }
+                for (int j = tid; j < n; j += SEARCH_THREADS) {
+                    const long long k = cand_keys[j];
+                    int c = count_greater_desc(cur, size, k);
+                    for (int jj = 0; jj < n; jj++) c += (cand_keys[jj] > k);
+                    if (c < L) { nxt[c] = k; fnxt[c] = 0; }
+                }
+                __syncthreads();
+                { long long *t = cur; cur = nxt; nxt = t; }
+                { uint8_t *t = fcur; fcur = fnxt; fnxt = t; }
+                size = min(L, size + n);
+            }
+            __syncthreads();
+        }
+
+        int32_t *no = P.nodes_out + (size_t)qi * P.topK;
+        float *so = P.scores_out + (size_t)qi * P.topK;
+        unsigned reranked = 0;
+        if (failed) {
+            for (int i = tid; i < P.topK; i += SEARCH_THREADS) { no[i] = -1; so[i] = 0.f; }
+            if (tid == 0) { P.overflow[qi] = 1; atomicAdd(&P.counters->overflowed, 1ull); }
+        } else {
+            if (tid == 0) P.overflow[qi] = 0;
+            if (P.has_rerank) {
+                // NodeQueue.rerank (NodeQueue.java:168-230) with rerankFloor = 0: exact-score every survivor, keep topK
+                constexpr int NGR = SEARCH_THREADS / 32;
+                const int wgroup = tid >> 5, wlane = tid & 31;
+                for (int i = wgroup; i < size; i += NGR) {
+                    const int32_t f = key_node(cur[i]);
+                    float sc;
+                    if (P.rerank.kind == KIND_F32) sc = score_row<KIND_F32, METRIC>(P.rerank, blobR, f, wlane);
+                    else sc = score_row<KIND_NVQ, METRIC>(P.rerank, blobR, f, wlane);
+                    if (wlane == 0) nxt[i] = topk_key(sc, f);
+                }
+                for (int i = size + tid; i < P.list_pow2; i += SEARCH_THREADS) nxt[i] = KEY_MIN;
+                __syncthreads();
+                bitonic_sort_desc_block(nxt, P.list_pow2);
+                reranked = size;
+                for (int i = tid; i < P.topK; i += SEARCH_THREADS) {
+                    if (i < size) { no[i] = key_node(nxt[i]); so[i] = key_score(nxt[i]); }
+                    else { no[i] = -1; so[i] = 0.f; }
+                }
+            } else {
+                for (int i = tid; i < P.topK; i += SEARCH_THREADS) {
+                    if (i < size) { no[i] = key_node(cur[i]); so[i] = key_score(cur[i]); }
+                    else { no[i] = -1; so[i] = 0.f; }
+                }
+            }
+            if (tid == 0) {
+                atomicAdd(&P.counters->visited, (unsigned long long)visited);
+                atomicAdd(&P.counters->expanded, (unsigned long long)expanded);
+                atomicAdd(&P.counters->expanded_base, (unsigned long long)expanded_base);
+                atomicAdd(&P.counters->reranked, (unsigned long long)reranked);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static int next_pow2i(int v)
+{
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, int list_pow2)
+{
+    size_t b = 0;
+    b += (size_t)blob_floats(approx) * 4;
+    if (rerank) b += (size_t)blob_floats(*rerank) * 4;
+    b += (size_t)list_pow2 * 8 * 2;
+    b += (size_t)MAX_DEGREE * 8 + (size_t)MAX_DEGREE * 4;
+    b += (size_t)list_pow2 * 2;
+    return (b + 15) & ~(size_t)15;
+}
+
+template <int KIND, int METRIC>
+static cudaError_t occupancy_of(size_t smem, int *blocks_per_sm)
+{
+    cudaError_t e = cudaFuncSetAttribute(graph_search_kernel<KIND, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, graph_search_kernel<KIND, METRIC>, SEARCH_THREADS, smem);
+}
+
+#define JV_SEARCH_DISPATCH(kind, metric, CALL)                                                  \
+    do {                                                                                        \
+        if ((kind) == KIND_F32) {                                                               \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN); }       \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT); }              \
+            else { CALL(KIND_F32, JV_METRIC_COSINE); }                                          \
+        } else if ((kind) == KIND_PQ) {                                                         \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_PQ, JV_METRIC_EUCLIDEAN); }        \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_PQ, JV_METRIC_DOT); }               \
+            else { CALL(KIND_PQ, JV_METRIC_COSINE); }                                           \
+        } else if ((kind) == KIND_BQ) {                                                         \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_BQ, JV_METRIC_EUCLIDEAN); }        \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_BQ, JV_METRIC_DOT); }               \
+            else { CALL(KIND_BQ, JV_METRIC_COSINE); }                                           \
+        } else {                                                                                \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_NVQ, JV_METRIC_EUCLIDEAN); }       \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_NVQ, JV_METRIC_DOT); }              \
+            else { CALL(KIND_NVQ, JV_METRIC_COSINE); }                                          \
+        }                                                                                       \
+    } while (0)
+
+cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const GraphDesc &g, int topK, int rerankK, int nq,
+                        int visited_cap_hint, int sm_count, SearchPlan *plan)
+{
+    if (g.degree > MAX_DEGREE || rerankK < 1 || topK < 1 || topK > rerankK) return cudaErrorInvalidValue;
+    plan->threads = SEARCH_THREADS;
+    plan->list_cap = next_pow2i(rerankK);
+    plan->smem_bytes = search_smem_bytes(approx, rerank, plan->list_cap);
+    if (plan->smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
+    int cap = visited_cap_hint > 0 ? visited_cap_hint : next_pow2i(4 * rerankK * (g.degree > 16 ? g.degree : 16));
+    if (cap < 2048) cap = 2048;
+    if (cap > (1 << 22)) cap = 1 << 22;
+    plan->visited_cap = next_pow2i(cap);
+    int bps = 0;
+    cudaError_t e = cudaSuccess;
+    const int metric_for_occ = JV_METRIC_DOT;
+#define CALL(K, M) e = occupancy_of<K, M>(plan->smem_bytes, &bps)
+    JV_SEARCH_DISPATCH(approx.kind, metric_for_occ, CALL);
+#undef CALL
+    if (e != cudaSuccess) return e;
+    if (bps < 1) return cudaErrorInvalidValue;
+    long long ctas = (long long)bps * sm_count;
+    if (ctas > nq) ctas = nq;
+    if (ctas < 1) ctas = 1;
+    plan->ctas = (int)ctas;
+    return cudaSuccess;
+}
+
+size_t search_scratch_bytes(const SearchPlan &p) { return (size_t)p.ctas * p.visited_cap * sizeof(int32_t); }
+
+cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const DataDesc *rerank, int metric, const float *queries_dev,
+                          int nq, int topK, int rerankK, const SearchPlan &plan, void *scratch_dev, int *work_counter_dev,
+                          int32_t *nodes_out_dev, float *scores_out_dev, SearchCounters *counters_dev, uint8_t *overflow_flags_dev,
+                          const int32_t *query_index_dev, int query_stride, cudaStream_t s)
+{
+    if (nq <= 0) return cudaSuccess;
+    SearchParams P;
+    P.query_stride = query_stride > 0 ? query_stride : approx.dim;
+    P.g = g;
+    P.approx = approx;
+    P.has_rerank = rerank ? 1 : 0;
+    P.rerank = rerank ? *rerank : approx;
+    P.metric = metric;
+    P.queries = queries_dev;
+    P.nq = nq;
+    P.topK = topK;
+    P.rerankK = rerankK;
+    P.list_pow2 = plan.list_cap;
+    P.visited_cap = plan.visited_cap;
+    int lg = 0;
+    while ((1 << lg) < plan.visited_cap) lg++;
+    P.visited_shift = 32 - lg;
+    P.visited_tables = reinterpret_cast<int32_t *>(scratch_dev);
+    P.work_counter = work_counter_dev;
+    P.nodes_out = nodes_out_dev;
+    P.scores_out = scores_out_dev;
+    P.counters = counters_dev;
+    P.overflow = overflow_flags_dev;
+    P.query_index = query_index_dev;
+    P.blobA_floats = blob_floats(approx);
+    P.blobR_floats = rerank ? blob_floats(*rerank) : 0;
+    cudaError_t e = cudaMemsetAsync(work_counter_dev, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
+#define CALL(K, M)                                                                                                              \
+    do {                                                                                                                        \
+        e = cudaFuncSetAttribute(graph_search_kernel<K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes); \
+        if (e == cudaSuccess) graph_search_kernel<K, M><<<plan.ctas, SEARCH_THREADS, plan.smem_bytes, s>>>(P);                  \
+    } while (0)
+    JV_SEARCH_DISPATCH(approx.kind, metric, CALL);
+#undef CALL
+    if (e != cudaSuccess) return e;
+    g_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace jv
