@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU kernels on the host cores
+
+Workload (configs[1], `c2`): synthetic 1M x 768 float32, rows i.i.d. N(0,1) L2-normalised (numpy default_rng(20260922)),
+DOT_PRODUCT, Vamana graph M=32 efConstruction=100 overflow 1.2 alpha 1.2 with hierarchy, GraphSearcher top-10 with
+rerankK = 10 x overquery. A "step" = one batch of `nq` queries searched to completion. `c3` is the same data through PQ
+(M=96, k=256) ADC + fp32 rerank; `c4` is BQ Hamming brute force. One JSON line on stdout (rank 0).
+
+value   : queries/s with the query batch already resident in HBM, device time from CUDA events on the launching stream
+e2e     : queries/s through the host-pointer C-ABI call (H2D of the queries and D2H of the results inside the timed region)
+roofline: graph_search_kernel, algorithmic bytes = scored vectors x (row bytes + 8) / device time, vs MEASURED_PEAKS.json
+cpu_baseline: the same traversal (oracle/jv_oracle.c driver) calling the reference's own compiled kernels
+              (oracle/_ref/libjvector.so) on the host cores, on a bounded sample of the same queries.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SEED = 20260922
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def gen_unit_rows(seed, n, dim, chunk=65536):
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, dim), dtype=np.float32)
+    for i in range(0, n, chunk):
+        j = min(n, i + chunk)
+        blk = rng.standard_normal((j - i, dim), dtype=np.float32)
+        blk /= np.linalg.norm(blk, axis=1, keepdims=True)
+        out[i:j] = blk
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recall_at_k(found, truth, k):
+    """jvector-examples/.../util/AccuracyMetrics.java:38-50 (recallFromSearchResults, k = topK)"""
+    hits = 0
+    for f, t in zip(found, truth):
+        hits += len(set(int(x) for x in f[:k] if x >= 0) & set(int(x) for x in t[:k]))
+    return hits / float(len(found) * k)
+
+
+def dist_setup(gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    td = None
+    if world > 1:
+        import torch
+        import torch.distributed as td
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, td
+
+
+def host_graph(gi):
+    """download the device graph into the oracle's host representation (CPU baseline / reference arm only)"""
+    import oracle_lib as o
+    inf = gi.info()
+    _, adj0 = gi.level(0)
+    upper = [gi.level(l) for l in range(1, inf["levels"])]
+    return o.make_graph(adj0, inf["entry_node"], upper if upper else None)
+
+
+def cpu_search(args, base, graph_host, queries, topK, rerankK, pq=None):
+    """The reference arm / cpu_baseline leg: oracle traversal driver + the reference's own compiled kernels."""
+    import oracle_lib as o
+    L = o.load()
+    kind = "port"
+    if os.path.exists(o.REF_SO) and L.jvo_use_ref(o.REF_SO.encode()) == 0:
+        kind = "reference"
+    ds = o.Dataset()
+    ds.kind = 1 if pq else 0
+    ds.metric = o.DOT_PRODUCT
+    ds.dim = base.shape[1]
+    ds.base = o.fp(base)
+    ds.n = base.shape[0]
+    if pq:
+        ds.codebooks, ds.M, ds.k, ds.centroid, ds.codes = o.fp(pq["codebooks"]), pq["M"], 256, None, o.bp(pq["codes"])
+    nq = queries.shape[0]
+    nodes = np.empty((nq, topK), np.int32)
+    scores = np.empty((nq, topK), np.float32)
+    scored = C.c_int64()
+    threads = os.cpu_count() or 1
+    secs = L.jvo_graph_search_batch(C.byref(graph_host), C.byref(ds), o.fp(queries), nq, topK, rerankK, threads, o.ip(nodes), o.fp(scores), C.byref(scored))
+    isa = L.jvo_ref_isa().decode()
+    L.jvo_use_ref(None)
+    return {"seconds": secs, "qps": nq / secs, "scored": int(scored.value), "threads": threads, "kind": kind, "isa": isa, "nodes": nodes}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--nq", type=int, default=10_000)
+    ap.add_argument("--topk", type=int, default=10)
+    ap.add_argument("--overquery", type=int, default=10)
+    ap.add_argument("--gt-queries", type=int, default=1000)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also report overquery 1/2/5/10")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank, world, local, td = dist_setup(args.gpus)
+    if args.impl == "reference" and rank != 0:
+        return 0  # the CPU arm runs on rank 0 alone
+
+    import jvector_b200 as jv
+    from jvector_b200 import _native as nat
+    VSF = jv.VectorSimilarityFunction
+    lib = nat.init(local)
+
+    t0 = time.time()
+    base = gen_unit_rows(SEED, args.n, args.dim)
+    queries = gen_unit_rows(SEED + 1 + rank, args.nq, args.dim)
+    log("[rank %d] data generated in %.1fs" % (rank, time.time() - t0))
+    vec = jv.F32Vectors(base)
+    t0 = time.time()
+    builder = jv.GraphIndexBuilder(VSF.DOT_PRODUCT, M=32, beamWidth=100, neighborOverflow=1.2, alpha=1.2, addHierarchy=True, seed=SEED)
+    gi = builder.build(vec)
+    build_s = time.time() - t0
+    log("[rank %d] graph built in %.1fs (device %.1fs) %s" % (rank, build_s, builder.device_ms / 1e3, gi.info()))
+
+    topK, rerankK = args.topk, args.topk * args.overquery
+    pq = None
+    approx, reranker = vec, None
+    row_bytes = args.dim * 4
+    if args.workload == "c3":
+        import oracle_lib as o
+        M = args.dim // 8
+        rs = np.random.default_rng(SEED + 99)
+        sample = base[rs.choice(args.n, min(args.n, 20000), replace=False)]
+        cb, _, _ = o.train_pq_numpy(rs, sample, M, 256, iters=6)
+        codes = jv.pq_encode_all(base, cb, M, 256)
+        pq = {"codebooks": cb, "codes": codes, "M": M}
+        approx, reranker = jv.PQVectors(codes, cb, args.dim, 256), vec
+
+    # ground truth by exhaustive scoring with the reference's ordering key
+    ngt = min(args.gt_queries, args.nq)
+    gt_nodes, _, _ = jv.topk_bruteforce(vec, VSF.DOT_PRODUCT, queries[:ngt], topK)
+    searcher = jv.GraphSearcher(gi)
+
+    out = {"metric": "queries_per_sec_at_recall@10", "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "%s: synthetic %dx%d float32 unit rows, DOT_PRODUCT, graph M=32 ef=100 overflow=1.2 alpha=1.2 hierarchy, "
+                                  "GraphSearcher top-%d rerankK=%d, %d queries/step/GPU" % (args.workload, args.n, args.dim, topK, rerankK, args.nq),
+                      "parallelism": "replica per GPU, queries sharded (no data-path collective)",
+                      "l2": "inputs %.2f GB >> 126 MB L2 (random row gathers)" % (base.nbytes / 1e9)}}
+
+    if args.impl == "reference":
+        gh = host_graph(gi)
+        nqs = args.cpu_sample or min(args.nq, 1000)
+        for _ in range(args.warmup):
+            cpu_search(args, base, gh, queries[: max(50, nqs // 10)], topK, rerankK, pq)
+        secs, scored, last = 0.0, 0, None
+        for _ in range(args.steps):
+            last = cpu_search(args, base, gh, queries[:nqs], topK, rerankK, pq)
+            secs += last["seconds"]
+            scored += last["scored"]
+        qps = args.steps * nqs / secs
+        rec = recall_at_k(last["nodes"][:ngt], gt_nodes[: min(ngt, nqs)], topK)
+        out.update({"impl": "reference", "value": qps, "ms_per_step": 1e3 * secs / args.steps, "recall_at_10": rec,
+                    "scored_vectors_per_sec": scored / secs,
+                    "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": last["threads"], "kind": last["kind"], "isa": last["isa"],
+                                     "sample": "%d of the %d queries per step, all host threads" % (nqs, args.nq)},
+                    "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "gpu_launches": 0, "setup": "graph built with the device builder (untimed); timed path is CPU only"})
+        print(json.dumps(out), flush=True)
+        return 0
+
+    # ---- device-resident leg: queries already in HBM ----
+    nq = args.nq
+    dq, dn, ds_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    nat.check(lib.jv_device_malloc(C.byref(dq), queries.nbytes))
+    nat.check(lib.jv_device_malloc(C.byref(dn), nq * topK * 4))
+    nat.check(lib.jv_device_malloc(C.byref(ds_), nq * topK * 4))
+    nat.check(lib.jv_memcpy_h2d(dq, queries.ctypes.data, queries.nbytes))
+    st = nat.SearchStats()
+    rr = reranker._h if reranker is not None else None
+
+    def step_device():
+        nat.check(lib.jv_graph_search_batch_device(gi._h, approx._h, rr, int(VSF.DOT_PRODUCT), dq, nq, topK, rerankK, dn, ds_, C.byref(st)))
+        return st.device_ms, st.visited + nq + st.reranked
+
+    def barrier():
+        if td is not None:
+            td.barrier()
+        nat.check(lib.jv_device_synchronize())
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.jv_kernel_launch_count()
+    dev_ms, scored, t0 = 0.0, 0, time.time()
+    for _ in range(args.steps):
+        ms, sc = step_device()
+        dev_ms += ms
+        scored += sc
+    barrier()
+    wall_s = time.time() - t0
+    launches = lib.jv_kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    nodes = np.empty((nq, topK), np.int32)
+    nat.check(lib.jv_memcpy_d2h(nodes.ctypes.data, dn, nodes.nbytes))
+    rec = recall_at_k(nodes[:ngt], gt_nodes, topK)
+
+    # ---- end-to-end leg: pinned host buffers in, host results out, copies inside the timed region ----
+    hq = np.ascontiguousarray(queries)
+    hn = np.empty((nq, topK), np.int32)
+    hs = np.empty((nq, topK), np.float32)
+    for a in (hq, hn, hs):
+        lib.jv_host_register(a.ctypes.data, a.nbytes)
+    st2 = nat.SearchStats()
+
+    def step_e2e():
+        nat.check(lib.jv_graph_search_batch(gi._h, approx._h, rr, int(VSF.DOT_PRODUCT), nat.fp(hq), nq, topK, rerankK, nat.ip(hn), nat.fp(hs), C.byref(st2)))
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.time() - t0
+    for a in (hq, hn, hs):
+        lib.jv_host_unregister(a.ctypes.data)
+
+    # max over ranks
+    if td is not None:
+        import torch
+        t = torch.tensor([dev_ms, e2e_s, wall_s], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        dev_ms, e2e_s, wall_s = [float(x) for x in t.tolist()]
+        c = torch.tensor([float(scored), rec, float(launches)], dtype=torch.float64, device="cuda")
+        td.all_reduce(c, op=td.ReduceOp.SUM)
+        scored, rec, launches = float(c[0]), float(c[1]) / world, int(c[2])
+    total_q = args.steps * nq * world
+    peak, peak_src = measured_peaks()
+    per_unit = (row_bytes + 8) if args.workload == "c2" else None
+    if args.workload == "c2":
+        algo_bytes = scored * per_unit / world  # per GPU
+    else:
+        algo_bytes = ((st.visited + nq) * (approx.M + 8) + st.reranked * (row_bytes + 8)) * args.steps
+    achieved = algo_bytes / (dev_ms / 1e3) / 1e9
+    out.update({"value": total_q / (dev_ms / 1e3), "ms_per_step": dev_ms / args.steps, "recall_at_10": rec,
+                "scored_vectors_per_sec": scored / (dev_ms / 1e3), "visited_per_query": st.visited / float(nq),
+                "wall_ms_per_step": 1e3 * wall_s / args.steps,
+                "e2e": {"value": total_q / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(hq.nbytes), "d2h_bytes_per_step": int(hn.nbytes + hs.nbytes)},
+                "gpu_launches": int(launches), "clocks": clocks, "build_seconds": build_s,
+                "roofline": {"kernel": "graph_search_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_scored_vector": per_unit}})
+
+    if args.sweep and rank == 0:
+        sweep = []
+        for oq in (1, 2, 5, 10):
+            rk = topK * oq
+            nat.check(lib.jv_graph_search_batch_device(gi._h, approx._h, rr, int(VSF.DOT_PRODUCT), dq, nq, topK, rk, dn, ds_, C.byref(st)))
+            nat.check(lib.jv_graph_search_batch_device(gi._h, approx._h, rr, int(VSF.DOT_PRODUCT), dq, nq, topK, rk, dn, ds_, C.byref(st)))
+            nat.check(lib.jv_memcpy_d2h(nodes.ctypes.data, dn, nodes.nbytes))
+            sweep.append({"overquery": oq, "qps": nq / (st.device_ms / 1e3), "recall_at_10": recall_at_k(nodes[:ngt], gt_nodes, topK),
+                          "visited_per_query": st.visited / float(nq)})
+        out["sweep"] = sweep
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        gh = host_graph(gi)
+        nqs = args.cpu_sample or min(nq, 500)
+        cpu_search(args, base, gh, queries[: max(20, nqs // 10)], topK, rerankK, pq)
+        r = cpu_search(args, base, gh, queries[:nqs], topK, rerankK, pq)
+        out["cpu_baseline"] = {"value": r["qps"], "unit": "queries/s", "cores": r["threads"], "kind": r["kind"], "isa": r["isa"],
+                               "scored_vectors_per_sec": r["scored"] / r["seconds"],
+                               "recall_at_10": recall_at_k(r["nodes"][:ngt], gt_nodes[: min(ngt, nqs)], topK),
+                               "sample": "%d of the %d queries of one step, %d host threads, %.1f s" % (nqs, nq, r["threads"], r["seconds"])}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if td is not None:
+        td.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

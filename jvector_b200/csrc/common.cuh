@@ -39,18 +39,28 @@ __device__ __forceinline__ int32_t key_node(long long key) { return (int32_t)~(u
 
 constexpr long long KEY_MIN = (long long)0x8000000000000000ull;
 
+// lanes of the calling thread's WIDTH-wide group (groups never straddle a warp; blocks are 1-D, multiple of 32).
+// Sub-warp groups of one warp may sit in different loop iterations, so shuffles name only their own group.
+template <int WIDTH>
+__device__ __forceinline__ unsigned group_mask()
+{
+    if (WIDTH == 32) return FULL;
+    return ((1u << WIDTH) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(WIDTH - 1));
+}
 template <int WIDTH>
 __device__ __forceinline__ float group_sum(float v)
 {
+    const unsigned m = group_mask<WIDTH>();
 #pragma unroll
-    for (int o = WIDTH / 2; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(FULL, v, o, WIDTH));
+    for (int o = WIDTH / 2; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(m, v, o, WIDTH));
     return v;
 }
 template <int WIDTH>
 __device__ __forceinline__ int group_sum_int(int v)
 {
+    const unsigned m = group_mask<WIDTH>();
 #pragma unroll
-    for (int o = WIDTH / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o, WIDTH);
+    for (int o = WIDTH / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o, WIDTH);
     return v;
 }
 
