@@ -130,6 +130,12 @@ JV_API int jv_score_pairs(jv_dataset ds, int metric, const int32_t *a, const int
 /* exhaustive scoring of every row for nq queries with a fused device-side top-k; keys_out[nq][k] best first,
  * padded with INT64_MIN */
 JV_API int jv_topk_bruteforce(jv_dataset ds, int metric, const float *queries, int nq, int k, int64_t *keys_out);
+/* multi-GPU form: the base is range-sharded, this rank holds rows [id_base, id_base + n); queries and keys stay in
+ * HBM so the keys can be the NCCL send buffer. Node ids inside the keys are global (local id + id_base). */
+JV_API int jv_topk_bruteforce_device(jv_dataset ds, int metric, const float *queries_device, int nq, int k, int64_t id_base,
+                                     int64_t *keys_out_device);
+/* the merge after the all-gather: keys_in [nq][parts * k] (any order) -> keys_out [nq][k] best first */
+JV_API int jv_topk_merge_device(const int64_t *keys_in_device, int nq, int parts, int k, int64_t *keys_out_device);
 
 /* ---- bulk encoders (next to the scoring path: ProductQuantization.encodeAll, BinaryQuantization.encodeAll,
  *      NVQuantization.encodeAll) ---- */

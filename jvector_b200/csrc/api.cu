@@ -402,15 +402,11 @@ int jv_score_pairs(jv_dataset ds, int metric, const int32_t *a, const int32_t *b
     return JV_OK;
 }
 
-int jv_topk_bruteforce(jv_dataset ds, int metric, const float *queries, int nq, int k, int64_t *keys_out)
+// exhaustive top-k with queries and keys in HBM; id_base is added to every node id (range-sharded base)
+static int topk_device(jv_dataset ds, int metric, const float *queries_dev, int nq, int k, int64_t id_base, long long *keys_dev)
 {
-    NEED_INIT();
-    if (!ds || !queries || !keys_out || nq <= 0 || k <= 0) return fail(JV_ERR_INVALID, "topk_bruteforce: bad arguments");
-    if (k > 2048) return fail(JV_ERR_INVALID, "topk_bruteforce: k <= 2048");
-    int rc = check_metric(ds->d, metric);
-    if (rc) return rc;
-    if ((rc = t_ctx.init())) return rc;
     cudaStream_t s = t_ctx.stream;
+    int rc;
     const size_t bf = (size_t)blob_floats(ds->d);
     const int chunk_max = (int)std::max<size_t>(1, std::min<size_t>(4096, ((size_t)512 << 20) / (bf * 4)));
     TopkScratch ts;
@@ -420,27 +416,61 @@ int jv_topk_bruteforce(jv_dataset ds, int metric, const float *queries, int nq, 
     if (ds->d.n <= ts.S) ts.cap = 4096;
     for (int q0 = 0; q0 < nq; q0 += chunk_max) {
         const int cq = std::min(chunk_max, nq - q0);
-        if ((rc = t_ctx.ensure(0, (size_t)cq * ds->d.dim * 4)) || (rc = t_ctx.ensure(4, (size_t)cq * bf * 4)) ||
-            (rc = t_ctx.ensure(1, (size_t)ts.S * 4 + (size_t)cq * ts.S * 4 + 64)) ||
-            (rc = t_ctx.ensure(2, (size_t)cq * 8 + (size_t)cq * 4 + 64 + (size_t)cq * ts.cap * 8)) || (rc = t_ctx.ensure(3, (size_t)cq * k * 8 + 16)))
+        if ((rc = t_ctx.ensure(4, (size_t)cq * bf * 4)) || (rc = t_ctx.ensure(1, (size_t)ts.S * 4 + (size_t)cq * ts.S * 4 + 64)) ||
+            (rc = t_ctx.ensure(2, (size_t)cq * 8 + (size_t)cq * 4 + 64 + (size_t)cq * ts.cap * 8)) || (rc = t_ctx.ensure(3, 64)))
             return rc;
         ts.sample_ids = (int32_t *)t_ctx.dbuf[1];
         ts.sample_scores = (float *)((char *)t_ctx.dbuf[1] + (((size_t)ts.S * 4 + 15) & ~(size_t)15));
         ts.buf = (long long *)t_ctx.dbuf[2];
         ts.thr = ts.buf + (size_t)cq * ts.cap;
         ts.cnt = (int *)(ts.thr + cq);
-        long long *dkeys = (long long *)t_ctx.dbuf[3];
-        int *dflag = (int *)(dkeys + (size_t)cq * k);
-        CK(cudaMemcpyAsync(t_ctx.dbuf[0], queries + (size_t)q0 * ds->d.dim, (size_t)cq * ds->d.dim * 4, cudaMemcpyHostToDevice, s), "H2D queries");
+        int *dflag = (int *)t_ctx.dbuf[3];
         CK(cudaMemsetAsync(dflag, 0, sizeof(int), s), "memset flag");
-        CK(launch_prepare(ds->d, metric, (const float *)t_ctx.dbuf[0], cq, (float *)t_ctx.dbuf[4], s), "prepare");
-        CK(launch_topk_bruteforce(ds->d, metric, (const float *)t_ctx.dbuf[4], cq, k, ts, dkeys, dflag, s), "topk");
+        CK(launch_prepare(ds->d, metric, queries_dev + (size_t)q0 * ds->d.dim, cq, (float *)t_ctx.dbuf[4], s), "prepare");
+        CK(launch_topk_bruteforce(ds->d, metric, (const float *)t_ctx.dbuf[4], cq, k, ts, keys_dev + (size_t)q0 * k, dflag, s), "topk");
+        if (id_base) CK(launch_key_rebase(keys_dev + (size_t)q0 * k, (long long)cq * k, (long long)id_base, s), "rebase");
         int flag = 0;
         CK(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, s), "D2H flag");
-        CK(cudaMemcpyAsync(keys_out + (size_t)q0 * k, dkeys, (size_t)cq * k * 8, cudaMemcpyDeviceToHost, s), "D2H keys");
         CK(cudaStreamSynchronize(s), "sync");
         if (flag) return fail(JV_ERR_OVERFLOW, "topk_bruteforce: candidate buffer overflow (adversarial score distribution)");
     }
+    return JV_OK;
+}
+
+int jv_topk_bruteforce(jv_dataset ds, int metric, const float *queries, int nq, int k, int64_t *keys_out)
+{
+    NEED_INIT();
+    if (!ds || !queries || !keys_out || nq <= 0 || k <= 0) return fail(JV_ERR_INVALID, "topk_bruteforce: bad arguments");
+    if (k > 2048) return fail(JV_ERR_INVALID, "topk_bruteforce: k <= 2048");
+    int rc = check_metric(ds->d, metric);
+    if (rc) return rc;
+    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(0, (size_t)nq * ds->d.dim * 4)) || (rc = t_ctx.ensure(5, (size_t)nq * k * 8))) return rc;
+    cudaStream_t s = t_ctx.stream;
+    CK(cudaMemcpyAsync(t_ctx.dbuf[0], queries, (size_t)nq * ds->d.dim * 4, cudaMemcpyHostToDevice, s), "H2D queries");
+    if ((rc = topk_device(ds, metric, (const float *)t_ctx.dbuf[0], nq, k, 0, (long long *)t_ctx.dbuf[5]))) return rc;
+    CK(cudaMemcpyAsync(keys_out, t_ctx.dbuf[5], (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s), "D2H keys");
+    CK(cudaStreamSynchronize(s), "sync");
+    return JV_OK;
+}
+
+int jv_topk_bruteforce_device(jv_dataset ds, int metric, const float *queries_device, int nq, int k, int64_t id_base, int64_t *keys_out_device)
+{
+    NEED_INIT();
+    if (!ds || !queries_device || !keys_out_device || nq <= 0 || k <= 0 || k > 2048 || id_base < 0) return fail(JV_ERR_INVALID, "topk_bruteforce_device: bad arguments");
+    int rc = check_metric(ds->d, metric);
+    if (rc) return rc;
+    if ((rc = t_ctx.init())) return rc;
+    return topk_device(ds, metric, queries_device, nq, k, id_base, (long long *)keys_out_device);
+}
+
+int jv_topk_merge_device(const int64_t *keys_in_device, int nq, int parts, int k, int64_t *keys_out_device)
+{
+    NEED_INIT();
+    if (!keys_in_device || !keys_out_device || nq <= 0 || parts <= 0 || k <= 0 || (long long)parts * k > 16384) return fail(JV_ERR_INVALID, "topk_merge: bad arguments");
+    int rc;
+    if ((rc = t_ctx.init())) return rc;
+    CK(launch_topk_merge((const long long *)keys_in_device, nq, parts, k, (long long *)keys_out_device, t_ctx.stream), "topk_merge");
+    CK(cudaStreamSynchronize(t_ctx.stream), "sync");
     return JV_OK;
 }
 

@@ -45,6 +45,11 @@ struct TopkScratch {
 cudaError_t launch_topk_bruteforce(const DataDesc &d, int metric, const float *blobs_dev, int nq, int k, const TopkScratch &ts,
                                    long long *keys_out_dev, int *overflow_flag_dev, cudaStream_t s);
 
+// keys[i] -> same score, node id + id_base (KEY_MIN pads untouched)
+cudaError_t launch_key_rebase(long long *keys_dev, long long count, long long id_base, cudaStream_t s);
+// per query: the k best of parts*k keys (the NCCL-gathered per-shard top-k), descending
+cudaError_t launch_topk_merge(const long long *keys_in_dev, int nq, int parts, int k, long long *keys_out_dev, cudaStream_t s);
+
 cudaError_t launch_bq_encode(const float *rows_dev, long long n, int dim, unsigned long long *words_dev, cudaStream_t s);
 cudaError_t launch_pq_encode(const DataDesc &pq, const float *rows_dev, long long n, uint8_t *codes_dev, cudaStream_t s);
 cudaError_t launch_pq_self_magnitudes(const DataDesc &pq, float *mag_dev, cudaStream_t s);

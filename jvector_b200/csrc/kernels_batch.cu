@@ -199,6 +199,111 @@ __global__ void __launch_bounds__(BF_THREADS) topk_filter_kernel(DataDesc d, con
     }
 }
 
+// ---- BQ specialisation: Hamming brute force is popcount-bound, not HBM-bound: one ROW per thread, its
+// words held in registers, the query bit-packs staged in shared memory and read by broadcast; no shuffles. A pair costs
+// W x (LDS.64 broadcast / 32 rows + XOR + POPC + ADD). The exact key is formed only for pairs under the per-query
+// Hamming bound derived from the sample threshold.
+constexpr int BQF_THREADS = 256;
+
+template <int MAXW>
+__global__ void __launch_bounds__(BQF_THREADS) topk_filter_bq_kernel(DataDesc d, const float *__restrict__ blobs, int blob_stride, int nq,
+                                                                     const long long *__restrict__ thr, long long *__restrict__ buf,
+                                                                     int *__restrict__ cnt, int cap)
+{
+    constexpr int BQF_QCHUNK = MAXW <= 16 ? 256 : 128;  // queries staged per pass (<= 32 KB of bit packs)
+    __shared__ unsigned long long qs[BQF_QCHUNK * MAXW];
+    __shared__ int hdmax[BQF_QCHUNK];
+    __shared__ long long sthr[BQF_QCHUNK];
+    const int W = d.W;
+    const long long row_stride = (long long)gridDim.x * BQF_THREADS;
+    for (long long r = (long long)blockIdx.x * BQF_THREADS + threadIdx.x; r - threadIdx.x < d.n; r += row_stride) {
+        unsigned long long rw[MAXW];
+        const bool live = r < d.n;
+        const unsigned long long *row = d.words + (size_t)(live ? r : 0) * W;
+#pragma unroll
+        for (int w = 0; w < MAXW; w++) rw[w] = (live && w < W) ? __ldg(row + w) : 0ull;
+        for (int q0 = 0; q0 < nq; q0 += BQF_QCHUNK) {
+            const int qc = min(BQF_QCHUNK, nq - q0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < qc * MAXW; i += BQF_THREADS) {
+                const int q = i / MAXW, w = i - q * MAXW;
+                qs[i] = w < W ? reinterpret_cast<const unsigned long long *>(blobs + (size_t)(q0 + q) * blob_stride)[w] : 0ull;
+            }
+            for (int q = threadIdx.x; q < qc; q += BQF_THREADS) {
+                const long long t = thr[q0 + q];
+                sthr[q] = t;
+                // largest Hamming distance whose score can still reach the threshold key
+                int h = d.dim;
+                if (t != KEY_MIN) {
+                    const float ts = key_score(t);
+                    h = (int)((1.0f - ts) * (float)d.dim) + 2;
+                    if (h > d.dim) h = d.dim;
+                    while (h >= 0 && bq_score_from_hd(h, d.dim) < ts) h--;
+                }
+                hdmax[q] = h;
+            }
+            __syncthreads();
+            if (live) {
+                for (int q = 0; q < qc; q++) {
+                    int hd = 0;
+#pragma unroll
+                    for (int w = 0; w < MAXW; w++) hd += __popcll(rw[w] ^ qs[q * MAXW + w]);
+                    if (hd <= hdmax[q]) {
+                        const long long key = topk_key(bq_score_from_hd(hd, d.dim), (int32_t)r);
+                        if (key >= sthr[q]) {
+                            const int pos = atomicAdd(&cnt[q0 + q], 1);
+                            if (pos < cap) buf[(size_t)(q0 + q) * cap + pos] = key;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- PQ specialisation: the per-query partial-sums table (LUT, M*k fp32 = 96 KB at M=96) is staged into shared memory
+// with TMA bulk copies (cp.async.bulk + mbarrier; SASS UBLKCP), then code rows stream through 8-lane groups.
+constexpr int PQF_THREADS = 256;
+constexpr int PQF_TILE = 16384;
+
+template <int METRIC>
+__global__ void __launch_bounds__(PQF_THREADS) topk_filter_pq_kernel(DataDesc d, const float *__restrict__ blobs, int blob_stride,
+                                                                     const long long *__restrict__ thr, long long *__restrict__ buf,
+                                                                     int *__restrict__ cnt, int cap)
+{
+    extern __shared__ __align__(128) unsigned char pq_smem[];
+    float *lut = reinterpret_cast<float *>(pq_smem);
+    __shared__ __align__(8) uint64_t bar;
+    const int q = blockIdx.x;
+    const unsigned bytes = (unsigned)blob_stride * 4u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, bytes);
+        const char *src = reinterpret_cast<const char *>(blobs + (size_t)q * blob_stride);
+        for (unsigned off = 0; off < bytes; off += 32768u) bulk_g2s(pq_smem + off, src + off, min(32768u, bytes - off), &bar);
+    }
+    mbar_wait(&bar, 0);
+    constexpr int G = 8, NG = PQF_THREADS / G;
+    const long long r0 = (long long)blockIdx.y * PQF_TILE;
+    const long long r1 = min(d.n, r0 + PQF_TILE);
+    const long long t = thr[q];
+    const int group = threadIdx.x / G, lane = threadIdx.x % G;
+    for (long long r = r0 + group; r < r1; r += NG) {
+        const float sc = score_pq<METRIC>(d, lut, (int)r, lane);
+        if (lane == 0) {
+            const long long key = topk_key(sc, (int32_t)r);
+            if (key >= t) {
+                const int pos = atomicAdd(&cnt[q], 1);
+                if (pos < cap) buf[(size_t)q * cap + pos] = key;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) topk_select_kernel(const long long *__restrict__ buf, const int *__restrict__ cnt, int cap, int cap_pow2, int k,
                                                           long long *__restrict__ keys_out, int *__restrict__ overflow)
 {
@@ -231,16 +336,82 @@ cudaError_t launch_topk_bruteforce(const DataDesc &d, int metric, const float *b
     if ((e = launch_score_ragged(d, metric, blobs_dev, nq, ts.sample_ids, nullptr, S, S, ts.sample_scores, s)) != cudaSuccess) return e;
     const int S2 = next_pow2(S);
     // k-th best of the sample; when the sample IS the data set (n <= S) ask for everything
+    if ((size_t)S2 * sizeof(long long) > 48 * 1024)
+        if ((e = cudaFuncSetAttribute(topk_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2 * (int)sizeof(long long))) != cudaSuccess) return e;
     topk_threshold_kernel<<<nq, 256, (size_t)S2 * sizeof(long long), s>>>(ts.sample_scores, ts.sample_ids, S, S2, (d.n <= S) ? S + 1 : k, ts.thr, ts.cnt);
     g_launches++;
-    dim3 grid(nq, (unsigned)((d.n + BF_TILE - 1) / BF_TILE));
-    if (grid.y > 65535u) return cudaErrorInvalidValue;
+    if (d.kind == KIND_BQ && d.W <= 32) {
+        // popcount-bound: every CTA walks a slice of the rows against ALL queries (rows in registers, queries in smem)
+        long long want = (d.n + BQF_THREADS - 1) / BQF_THREADS;
+        int gridx = (int)(want < 148 * 8 ? want : 148 * 8);
+#define CALLBQ(MW) topk_filter_bq_kernel<MW><<<gridx, BQF_THREADS, 0, s>>>(d, blobs_dev, blob_floats(d), nq, ts.thr, ts.buf, ts.cnt, ts.cap)
+        if (d.W <= 4) CALLBQ(4);
+        else if (d.W <= 8) CALLBQ(8);
+        else if (d.W <= 16) CALLBQ(16);
+        else if (d.W <= 24) CALLBQ(24);
+        else CALLBQ(32);
+#undef CALLBQ
+    } else if (d.kind == KIND_PQ && (size_t)blob_floats(d) * 4 <= 200 * 1024) {
+        dim3 grid(nq, (unsigned)((d.n + PQF_TILE - 1) / PQF_TILE));
+        const int smem = blob_floats(d) * 4;
+#define CALLPQ(M)                                                                                                             \
+    do {                                                                                                                      \
+        if ((e = cudaFuncSetAttribute(topk_filter_pq_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e; \
+        topk_filter_pq_kernel<M><<<grid, PQF_THREADS, smem, s>>>(d, blobs_dev, blob_floats(d), ts.thr, ts.buf, ts.cnt, ts.cap);  \
+    } while (0)
+        if (metric == JV_METRIC_EUCLIDEAN) CALLPQ(JV_METRIC_EUCLIDEAN);
+        else if (metric == JV_METRIC_DOT) CALLPQ(JV_METRIC_DOT);
+        else CALLPQ(JV_METRIC_COSINE);
+#undef CALLPQ
+    } else {
+        dim3 grid(nq, (unsigned)((d.n + BF_TILE - 1) / BF_TILE));
+        if (grid.y > 65535u) return cudaErrorInvalidValue;
 #define CALL(K, M) topk_filter_kernel<K, M><<<grid, BF_THREADS, 0, s>>>(d, blobs_dev, blob_floats(d), ts.thr, ts.buf, ts.cnt, ts.cap)
-    JV_DISPATCH_KIND_METRIC(d.kind, metric, CALL);
+        JV_DISPATCH_KIND_METRIC(d.kind, metric, CALL);
 #undef CALL
+    }
     g_launches++;
     const int cap2 = next_pow2(ts.cap);
+    if ((size_t)cap2 * sizeof(long long) > 48 * 1024)
+        if ((e = cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap2 * (int)sizeof(long long))) != cudaSuccess) return e;
     topk_select_kernel<<<nq, 256, (size_t)cap2 * sizeof(long long), s>>>(ts.buf, ts.cnt, ts.cap, cap2, k, keys_out_dev, overflow_flag_dev);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// the low word of a key is ~node: adding id_base to the node subtracts it from the key (no borrow: node + base < 2^31)
+__global__ void __launch_bounds__(256) key_rebase_kernel(long long *keys, long long count, long long id_base)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count && keys[i] != KEY_MIN) keys[i] -= id_base;
+}
+
+cudaError_t launch_key_rebase(long long *keys_dev, long long count, long long id_base, cudaStream_t s)
+{
+    if (count <= 0) return cudaSuccess;
+    key_rebase_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(keys_dev, count, id_base);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// the only exchange step of the path: per-shard top-k key arrays are all-gathered over NCCL, then merged here
+__global__ void __launch_bounds__(256) topk_merge_kernel(const long long *__restrict__ in, int total, int total_pow2, int k, long long *__restrict__ out)
+{
+    extern __shared__ long long skeys[];
+    const int q = blockIdx.x;
+    for (int i = threadIdx.x; i < total_pow2; i += blockDim.x) skeys[i] = i < total ? in[(size_t)q * total + i] : KEY_MIN;
+    __syncthreads();
+    bitonic_sort_desc(skeys, total_pow2);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) out[(size_t)q * k + i] = i < total ? skeys[i] : KEY_MIN;
+}
+
+cudaError_t launch_topk_merge(const long long *keys_in_dev, int nq, int parts, int k, long long *keys_out_dev, cudaStream_t s)
+{
+    const int total = parts * k, p2 = next_pow2(total);
+    cudaError_t e;
+    if ((size_t)p2 * 8 > 48 * 1024)
+        if ((e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p2 * 8)) != cudaSuccess) return e;
+    topk_merge_kernel<<<nq, 256, (size_t)p2 * 8, s>>>(keys_in_dev, total, p2, k, keys_out_dev);
     g_launches++;
     return cudaGetLastError();
 }

@@ -1,0 +1,102 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): the ONLY exchange step of the path is the final top-k
+merge.
+
+  * graph search (configs 2/3): every rank holds a replica of the base + graph; queries are sharded; no data-path collective.
+  * brute-force first pass (config 4): the base is range-sharded by contiguous node-id range; every rank scores ALL queries
+    against its shard and keeps a local top-k of 64-bit keys (reference ordering key, NodeQueue.java:125-137, node ids made
+    global on the device); ONE all_gather of [nq][k] int64 per rank (NCCL over NVLink on GPUs, gloo in the CPU tests),
+    then a k-way merge per query (device kernel jv_topk_merge_device; `merge_keys_host` is the host restatement the gloo
+    tests use to check the plumbing without a GPU).
+"""
+import numpy as np
+
+
+def shard_range(n, rank, world):
+    """contiguous node-id range [lo, hi) of `rank` (remainder spread over the first ranks)"""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+KEY_MIN = np.iinfo(np.int64).min
+
+
+def rebase_keys_host(keys, id_base):
+    """node id += id_base inside a key (low word is ~node): key -= id_base, pads untouched"""
+    keys = np.asarray(keys, dtype=np.int64)
+    return np.where(keys == KEY_MIN, keys, keys - np.int64(id_base))
+
+
+def merge_keys_host(gathered, k):
+    """gathered: [world][nq][k] keys -> [nq][k] best first (host restatement of topk_merge_kernel)"""
+    g = np.asarray(gathered, dtype=np.int64)
+    world, nq, kk = g.shape
+    allk = np.transpose(g, (1, 0, 2)).reshape(nq, world * kk)
+    allk = np.sort(allk, axis=1)[:, ::-1]
+    out = np.full((nq, k), KEY_MIN, dtype=np.int64)
+    out[:, : min(k, allk.shape[1])] = allk[:, :k]
+    return out
+
+
+def keys_to_nodes_scores(keys):
+    keys = np.asarray(keys, dtype=np.int64)
+    nodes = ((~keys) & 0xffffffff).astype(np.int64)
+    s = (keys >> 32).astype(np.int32)
+    bits = (s ^ ((s >> 31) & 0x7fffffff)).astype(np.int32)
+    nodes = np.where(keys == KEY_MIN, -1, nodes).astype(np.int32)
+    return nodes, bits.view(np.float32)
+
+
+class ShardedBruteForce:
+    """Exhaustive top-k over a base range-sharded across the ranks of a torch.distributed group.
+
+    local_topk(queries, k) -> int64 [nq][k] keys with GLOBAL node ids, as a torch tensor on this rank's device.
+    The default implementation calls the C ABI (jv_topk_bruteforce_device); tests inject an oracle-backed one under gloo."""
+
+    def __init__(self, dist, local_topk, merge=None):
+        self.dist = dist
+        self.local_topk = local_topk
+        self.merge = merge
+
+    def search(self, queries, k):
+        import torch
+        dist = self.dist
+        world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+        local = self.local_topk(queries, k)
+        if world == 1:
+            gathered = local.unsqueeze(0)
+        else:
+            flat = torch.empty((world * local.shape[0], local.shape[1]), dtype=torch.int64, device=local.device)
+            dist.all_gather_into_tensor(flat, local.contiguous())
+            gathered = flat.view(world, local.shape[0], local.shape[1])
+        if self.merge is not None:
+            return self.merge(gathered, k)
+        return torch.from_numpy(merge_keys_host(gathered.cpu().numpy(), k))
+
+
+def gpu_sharded_bruteforce(dist, vectors, vsf, id_base):
+    """ShardedBruteForce over a device-resident shard (`vectors` holds rows [id_base, id_base + n))."""
+    import ctypes as C
+
+    import torch
+
+    from . import _native as nat
+    lib = nat.init()
+
+    def local_topk(queries, k):
+        q = queries if isinstance(queries, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).cuda()
+        q = q.contiguous()
+        keys = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+        torch.cuda.synchronize()
+        nat.check(lib.jv_topk_bruteforce_device(vectors._h, int(vsf), C.c_void_p(q.data_ptr()), q.shape[0], k, int(id_base), C.c_void_p(keys.data_ptr())))
+        return keys
+
+    def merge(gathered, k):
+        world, nq, kk = gathered.shape
+        flat = gathered.permute(1, 0, 2).contiguous()  # [nq][world*k]
+        out = torch.empty((nq, k), dtype=torch.int64, device=gathered.device)
+        torch.cuda.synchronize()
+        nat.check(lib.jv_topk_merge_device(C.c_void_p(flat.data_ptr()), nq, world, kk, C.c_void_p(out.data_ptr())))
+        return out
+
+    return ShardedBruteForce(dist, local_topk, merge)
