@@ -14,7 +14,8 @@ CPP = ["legacy_host.cpp"]
 HEADERS = ["common.cuh", "scorers.cuh", "kernels.h", os.path.join("..", "..", "include", "jvector_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: only explicit fmaf() fuses (NVQ bit tricks and score maps must round like the reference's scalar code)
-NVFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3", "-Xptxas", "-v"]
+EXTRA = os.environ.get("JV_NVCC_EXTRA", "").split()
+NVFLAGS = EXTRA + ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3", "-Xptxas", "-v"]
 
 
 def _newer(target, deps):

@@ -410,20 +410,30 @@ static int topk_device(jv_dataset ds, int metric, const float *queries_dev, int 
     const size_t bf = (size_t)blob_floats(ds->d);
     const int chunk_max = (int)std::max<size_t>(1, std::min<size_t>(4096, ((size_t)512 << 20) / (bf * 4)));
     TopkScratch ts;
-    ts.S = (int)std::min<long long>(ds->d.n, 4096);
-    long long expect = ds->d.n <= ts.S ? ds->d.n : ((long long)k * ds->d.n) / ts.S;
-    ts.cap = expect * 2 > 4096 ? 16384 : 4096;
-    if (ds->d.n <= ts.S) ts.cap = 4096;
+    ts.S = (int)std::min<long long>(ds->d.n, 16384);
+    {
+        // expected survivors of the aggressive threshold (see launch_topk_bruteforce): j n / S with j - 6 sqrt(j) >= k S / n
+        const double f = (double)ts.S / (double)ds->d.n, kf = k * f;
+        int ja = k;
+        for (int j = 1; j < k; j++)
+            if ((double)j - 6.0 * sqrt((double)j) >= kf) { ja = j; break; }
+        const double expect = ds->d.n <= ts.S ? (double)ds->d.n : ja / f;
+        ts.cap = expect * 2 > 8192 ? 16384 : (expect * 2 > 4096 ? 8192 : 4096);
+        if (ts.cap < ts.S && ds->d.n <= ts.S) ts.cap = 16384;
+    }
     for (int q0 = 0; q0 < nq; q0 += chunk_max) {
         const int cq = std::min(chunk_max, nq - q0);
         if ((rc = t_ctx.ensure(4, (size_t)cq * bf * 4)) || (rc = t_ctx.ensure(1, (size_t)ts.S * 4 + (size_t)cq * ts.S * 4 + 64)) ||
-            (rc = t_ctx.ensure(2, (size_t)cq * 8 + (size_t)cq * 4 + 64 + (size_t)cq * ts.cap * 8)) || (rc = t_ctx.ensure(3, 64)))
+            (rc = t_ctx.ensure(2, (size_t)cq * 16 + (size_t)cq * 12 + 64 + (size_t)cq * ts.cap * 8)) || (rc = t_ctx.ensure(3, 64)))
             return rc;
         ts.sample_ids = (int32_t *)t_ctx.dbuf[1];
         ts.sample_scores = (float *)((char *)t_ctx.dbuf[1] + (((size_t)ts.S * 4 + 15) & ~(size_t)15));
         ts.buf = (long long *)t_ctx.dbuf[2];
         ts.thr = ts.buf + (size_t)cq * ts.cap;
-        ts.cnt = (int *)(ts.thr + cq);
+        ts.thr_safe = ts.thr + cq;
+        ts.cnt = (int *)(ts.thr_safe + cq);
+        ts.qlist_a = ts.cnt + cq;
+        ts.qlist_b = ts.qlist_a + cq;
         int *dflag = (int *)t_ctx.dbuf[3];
         CK(cudaMemsetAsync(dflag, 0, sizeof(int), s), "memset flag");
         CK(launch_prepare(ds->d, metric, queries_dev + (size_t)q0 * ds->d.dim, cq, (float *)t_ctx.dbuf[4], s), "prepare");

@@ -38,8 +38,10 @@ struct TopkScratch {
     int32_t *sample_ids;   // [S]
     float *sample_scores;  // [nq][S]
     long long *thr;        // [nq]
+    long long *thr_safe;   // [nq]
     long long *buf;        // [nq][cap]
     int *cnt;              // [nq]
+    int *qlist_a, *qlist_b;  // [nq] each: queries still unresolved after a pass
     int S, cap;
 };
 cudaError_t launch_topk_bruteforce(const DataDesc &d, int metric, const float *blobs_dev, int nq, int k, const TopkScratch &ts,

@@ -156,9 +156,14 @@ __global__ void __launch_bounds__(256) topk_sample_ids_kernel(int32_t *ids, int 
     if (i < S) ids[i] = (int32_t)(((long long)i * n) / S);
 }
 
-// thr[q] = k-th best key of the sample (a lower bound of the final k-th best); KEY_MIN when the sample is too small
+constexpr long long KEY_DONE = 0x7fffffffffffffffLL;  // thr value of a finished query: nothing passes the filter
+
+// Per query: sort the sample; thr = an AGGRESSIVE threshold (the j-th best of the sample, j ~ 3 k S / n + 2 < k), thr_safe = the
+// k-th best of the sample (a guaranteed lower bound of the final k-th best). The filtered pass is exact whenever it finds at
+// least k keys >= thr; otherwise the query is redone with thr_safe (topk_select_kernel decides).
 __global__ void __launch_bounds__(256) topk_threshold_kernel(const float *__restrict__ sample_scores, const int32_t *__restrict__ sample_ids, int S, int S_pow2,
-                                                             int k, long long *__restrict__ thr, int *__restrict__ cnt)
+                                                             int k, int j_aggr, int whole, long long *__restrict__ thr, long long *__restrict__ thr_safe,
+                                                             int *__restrict__ cnt)
 {
     extern __shared__ long long skeys[];
     const int q = blockIdx.x;
@@ -167,7 +172,9 @@ __global__ void __launch_bounds__(256) topk_threshold_kernel(const float *__rest
     __syncthreads();
     bitonic_sort_desc(skeys, S_pow2);
     if (threadIdx.x == 0) {
-        thr[q] = (k <= S) ? skeys[k - 1] : KEY_MIN;
+        const long long safe = (!whole && k <= S) ? skeys[k - 1] : KEY_MIN;
+        thr_safe[q] = safe;
+        thr[q] = (!whole && j_aggr < k && j_aggr <= S) ? skeys[j_aggr - 1] : safe;
         cnt[q] = 0;
     }
 }
@@ -177,15 +184,16 @@ constexpr int BF_TILE = 2048;  // rows per CTA
 
 template <int KIND, int METRIC>
 __global__ void __launch_bounds__(BF_THREADS) topk_filter_kernel(DataDesc d, const float *__restrict__ blobs, int blob_stride, const long long *__restrict__ thr,
-                                                                 long long *__restrict__ buf, int *__restrict__ cnt, int cap)
+                                                                 long long *__restrict__ buf, int *__restrict__ cnt, int cap, const int *__restrict__ qlist)
 {
     constexpr int G = GroupOf<KIND>::value;
     constexpr int NG = BF_THREADS / G;
-    const int q = blockIdx.x;
+    const int q = qlist ? qlist[blockIdx.x] : blockIdx.x;
     const long long r0 = (long long)blockIdx.y * BF_TILE;
     const long long r1 = min(d.n, r0 + BF_TILE);
     const float *blob = blobs + (size_t)q * blob_stride;
     const long long t = thr[q];
+    if (t == KEY_DONE) return;
     const int group = threadIdx.x / G, lane = threadIdx.x % G;
     for (long long r = r0 + group; r < r1; r += NG) {
         const float sc = score_row<KIND, METRIC>(d, blob, (int)r, lane);
@@ -208,11 +216,12 @@ constexpr int BQF_THREADS = 256;
 template <int MAXW>
 __global__ void __launch_bounds__(BQF_THREADS) topk_filter_bq_kernel(DataDesc d, const float *__restrict__ blobs, int blob_stride, int nq,
                                                                      const long long *__restrict__ thr, long long *__restrict__ buf,
-                                                                     int *__restrict__ cnt, int cap)
+                                                                     int *__restrict__ cnt, int cap, const int *__restrict__ qlist)
 {
     constexpr int BQF_QCHUNK = MAXW <= 16 ? 256 : 128;  // queries staged per pass (<= 32 KB of bit packs)
     __shared__ unsigned long long qs[BQF_QCHUNK * MAXW];
     __shared__ int hdmax[BQF_QCHUNK];
+    __shared__ int sq[BQF_QCHUNK];
     __shared__ long long sthr[BQF_QCHUNK];
     const int W = d.W;
     const long long row_stride = (long long)gridDim.x * BQF_THREADS;
@@ -227,14 +236,18 @@ __global__ void __launch_bounds__(BQF_THREADS) topk_filter_bq_kernel(DataDesc d,
             __syncthreads();
             for (int i = threadIdx.x; i < qc * MAXW; i += BQF_THREADS) {
                 const int q = i / MAXW, w = i - q * MAXW;
-                qs[i] = w < W ? reinterpret_cast<const unsigned long long *>(blobs + (size_t)(q0 + q) * blob_stride)[w] : 0ull;
+                const int qq = qlist ? qlist[q0 + q] : q0 + q;
+                qs[i] = w < W ? reinterpret_cast<const unsigned long long *>(blobs + (size_t)qq * blob_stride)[w] : 0ull;
             }
             for (int q = threadIdx.x; q < qc; q += BQF_THREADS) {
-                const long long t = thr[q0 + q];
+                const int qq = qlist ? qlist[q0 + q] : q0 + q;
+                sq[q] = qq;
+                const long long t = thr[qq];
                 sthr[q] = t;
                 // largest Hamming distance whose score can still reach the threshold key
                 int h = d.dim;
-                if (t != KEY_MIN) {
+                if (t == KEY_DONE) h = -1;
+                else if (t != KEY_MIN) {
                     const float ts = key_score(t);
                     h = (int)((1.0f - ts) * (float)d.dim) + 2;
                     if (h > d.dim) h = d.dim;
@@ -251,8 +264,9 @@ __global__ void __launch_bounds__(BQF_THREADS) topk_filter_bq_kernel(DataDesc d,
                     if (hd <= hdmax[q]) {
                         const long long key = topk_key(bq_score_from_hd(hd, d.dim), (int32_t)r);
                         if (key >= sthr[q]) {
-                            const int pos = atomicAdd(&cnt[q0 + q], 1);
-                            if (pos < cap) buf[(size_t)(q0 + q) * cap + pos] = key;
+                            const int qq = sq[q];
+                            const int pos = atomicAdd(&cnt[qq], 1);
+                            if (pos < cap) buf[(size_t)qq * cap + pos] = key;
                         }
                     }
                 }
@@ -269,12 +283,13 @@ constexpr int PQF_TILE = 16384;
 template <int METRIC>
 __global__ void __launch_bounds__(PQF_THREADS) topk_filter_pq_kernel(DataDesc d, const float *__restrict__ blobs, int blob_stride,
                                                                      const long long *__restrict__ thr, long long *__restrict__ buf,
-                                                                     int *__restrict__ cnt, int cap)
+                                                                     int *__restrict__ cnt, int cap, const int *__restrict__ qlist)
 {
     extern __shared__ __align__(128) unsigned char pq_smem[];
     float *lut = reinterpret_cast<float *>(pq_smem);
     __shared__ __align__(8) uint64_t bar;
-    const int q = blockIdx.x;
+    const int q = qlist ? qlist[blockIdx.x] : blockIdx.x;
+    if (thr[q] == KEY_DONE) return;
     const unsigned bytes = (unsigned)blob_stride * 4u;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -304,18 +319,31 @@ __global__ void __launch_bounds__(PQF_THREADS) topk_filter_pq_kernel(DataDesc d,
     }
 }
 
-__global__ void __launch_bounds__(256) topk_select_kernel(const long long *__restrict__ buf, const int *__restrict__ cnt, int cap, int cap_pow2, int k,
-                                                          long long *__restrict__ keys_out, int *__restrict__ overflow)
+__global__ void __launch_bounds__(256) topk_select_kernel(const long long *__restrict__ buf, int *__restrict__ cnt, int cap, int cap_pow2, int k,
+                                                          long long n_rows, long long *__restrict__ thr, const long long *__restrict__ thr_safe,
+                                                          long long *__restrict__ keys_out, int *__restrict__ n_redo, const int *__restrict__ qlist,
+                                                          int *__restrict__ qlist_next)
 {
     extern __shared__ long long skeys[];
-    const int q = blockIdx.x;
+    const int q = qlist ? qlist[blockIdx.x] : blockIdx.x;
+    const long long t = thr[q];
+    if (t == KEY_DONE) return;
     const int c = cnt[q];
-    if (c > cap && threadIdx.x == 0) atomicExch(overflow, 1);
     const int m = min(c, cap);
     for (int i = threadIdx.x; i < cap_pow2; i += blockDim.x) skeys[i] = i < m ? buf[(size_t)q * cap + i] : KEY_MIN;
     __syncthreads();
     bitonic_sort_desc(skeys, cap_pow2);
-    for (int i = threadIdx.x; i < k; i += blockDim.x) keys_out[(size_t)q * k + i] = i < m ? skeys[i] : KEY_MIN;
+    const long long need = n_rows < (long long)k ? n_rows : (long long)k;
+    if (c <= cap && (c >= need || t == thr_safe[q])) {
+        // exact: every key >= thr was captured and there are at least k of them (or the threshold was the guaranteed one)
+        for (int i = threadIdx.x; i < k; i += blockDim.x) keys_out[(size_t)q * k + i] = i < m ? skeys[i] : KEY_MIN;
+        if (threadIdx.x == 0) thr[q] = KEY_DONE;
+    } else if (threadIdx.x == 0) {
+        // too many (buffer overflowed): the k-th best of what was captured is a tighter valid bound; too few: fall back
+        thr[q] = c > cap ? skeys[k - 1] : thr_safe[q];
+        cnt[q] = 0;
+        qlist_next[atomicAdd(n_redo, 1)] = q;
+    }
 }
 
 static int next_pow2(int v)
@@ -335,48 +363,69 @@ cudaError_t launch_topk_bruteforce(const DataDesc &d, int metric, const float *b
     g_launches++;
     if ((e = launch_score_ragged(d, metric, blobs_dev, nq, ts.sample_ids, nullptr, S, S, ts.sample_scores, s)) != cudaSuccess) return e;
     const int S2 = next_pow2(S);
-    // k-th best of the sample; when the sample IS the data set (n <= S) ask for everything
     if ((size_t)S2 * sizeof(long long) > 48 * 1024)
         if ((e = cudaFuncSetAttribute(topk_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2 * (int)sizeof(long long))) != cudaSuccess) return e;
-    topk_threshold_kernel<<<nq, 256, (size_t)S2 * sizeof(long long), s>>>(ts.sample_scores, ts.sample_ids, S, S2, (d.n <= S) ? S + 1 : k, ts.thr, ts.cnt);
-    g_launches++;
-    if (d.kind == KIND_BQ && d.W <= 32) {
-        // popcount-bound: every CTA walks a slice of the rows against ALL queries (rows in registers, queries in smem)
-        long long want = (d.n + BQF_THREADS - 1) / BQF_THREADS;
-        int gridx = (int)(want < 148 * 8 ? want : 148 * 8);
-#define CALLBQ(MW) topk_filter_bq_kernel<MW><<<gridx, BQF_THREADS, 0, s>>>(d, blobs_dev, blob_floats(d), nq, ts.thr, ts.buf, ts.cnt, ts.cap)
-        if (d.W <= 4) CALLBQ(4);
-        else if (d.W <= 8) CALLBQ(8);
-        else if (d.W <= 16) CALLBQ(16);
-        else if (d.W <= 24) CALLBQ(24);
-        else CALLBQ(32);
-#undef CALLBQ
-    } else if (d.kind == KIND_PQ && (size_t)blob_floats(d) * 4 <= 200 * 1024) {
-        dim3 grid(nq, (unsigned)((d.n + PQF_TILE - 1) / PQF_TILE));
-        const int smem = blob_floats(d) * 4;
-#define CALLPQ(M)                                                                                                             \
-    do {                                                                                                                      \
-        if ((e = cudaFuncSetAttribute(topk_filter_pq_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e; \
-        topk_filter_pq_kernel<M><<<grid, PQF_THREADS, smem, s>>>(d, blobs_dev, blob_floats(d), ts.thr, ts.buf, ts.cnt, ts.cap);  \
-    } while (0)
-        if (metric == JV_METRIC_EUCLIDEAN) CALLPQ(JV_METRIC_EUCLIDEAN);
-        else if (metric == JV_METRIC_DOT) CALLPQ(JV_METRIC_DOT);
-        else CALLPQ(JV_METRIC_COSINE);
-#undef CALLPQ
-    } else {
-        dim3 grid(nq, (unsigned)((d.n + BF_TILE - 1) / BF_TILE));
-        if (grid.y > 65535u) return cudaErrorInvalidValue;
-#define CALL(K, M) topk_filter_kernel<K, M><<<grid, BF_THREADS, 0, s>>>(d, blobs_dev, blob_floats(d), ts.thr, ts.buf, ts.cnt, ts.cap)
-        JV_DISPATCH_KIND_METRIC(d.kind, metric, CALL);
-#undef CALL
+    const int whole = d.n <= S ? 1 : 0;
+    // aggressive threshold = j-th best of the sample with the smallest j such that j - 6 sqrt(j) >= k S / n: the j-th best of a
+    // random sample has rank ~ j n / S (std sqrt(j) n / S) in the full set, so fewer than k survivors is a > 6 sigma event
+    int ja = k;
+    if (!whole) {
+        const double kf = (double)k * S / (double)d.n;
+        for (int j = 1; j < k; j++)
+            if ((double)j - 6.0 * sqrt((double)j) >= kf) { ja = j; break; }
     }
+    topk_threshold_kernel<<<nq, 256, (size_t)S2 * sizeof(long long), s>>>(ts.sample_scores, ts.sample_ids, S, S2, k, ja, whole, ts.thr, ts.thr_safe, ts.cnt);
     g_launches++;
     const int cap2 = next_pow2(ts.cap);
     if ((size_t)cap2 * sizeof(long long) > 48 * 1024)
         if ((e = cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap2 * (int)sizeof(long long))) != cudaSuccess) return e;
-    topk_select_kernel<<<nq, 256, (size_t)cap2 * sizeof(long long), s>>>(ts.buf, ts.cnt, ts.cap, cap2, k, keys_out_dev, overflow_flag_dev);
-    g_launches++;
-    return cudaGetLastError();
+    int active = nq;
+    const int *qlist = nullptr;
+    for (int pass = 0; pass < 8; pass++) {
+        int *qnext = (pass & 1) ? ts.qlist_a : ts.qlist_b;
+        if ((e = cudaMemsetAsync(overflow_flag_dev, 0, sizeof(int), s)) != cudaSuccess) return e;
+        if (d.kind == KIND_BQ && d.W <= 32) {
+            // popcount-bound: every CTA walks a slice of the rows against ALL active queries (rows in registers, queries in smem)
+            long long want = (d.n + BQF_THREADS - 1) / BQF_THREADS;
+            int gridx = (int)(want < 148 * 8 ? want : 148 * 8);
+#define CALLBQ(MW) topk_filter_bq_kernel<MW><<<gridx, BQF_THREADS, 0, s>>>(d, blobs_dev, blob_floats(d), active, ts.thr, ts.buf, ts.cnt, ts.cap, qlist)
+            if (d.W <= 4) CALLBQ(4);
+            else if (d.W <= 8) CALLBQ(8);
+            else if (d.W <= 16) CALLBQ(16);
+            else if (d.W <= 24) CALLBQ(24);
+            else CALLBQ(32);
+#undef CALLBQ
+        } else if (d.kind == KIND_PQ && (size_t)blob_floats(d) * 4 <= 200 * 1024) {
+            dim3 grid(active, (unsigned)((d.n + PQF_TILE - 1) / PQF_TILE));
+            const int smem = blob_floats(d) * 4;
+#define CALLPQ(M)                                                                                                             \
+    do {                                                                                                                      \
+        if ((e = cudaFuncSetAttribute(topk_filter_pq_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e; \
+        topk_filter_pq_kernel<M><<<grid, PQF_THREADS, smem, s>>>(d, blobs_dev, blob_floats(d), ts.thr, ts.buf, ts.cnt, ts.cap, qlist);  \
+    } while (0)
+            if (metric == JV_METRIC_EUCLIDEAN) CALLPQ(JV_METRIC_EUCLIDEAN);
+            else if (metric == JV_METRIC_DOT) CALLPQ(JV_METRIC_DOT);
+            else CALLPQ(JV_METRIC_COSINE);
+#undef CALLPQ
+        } else {
+            dim3 grid(active, (unsigned)((d.n + BF_TILE - 1) / BF_TILE));
+            if (grid.y > 65535u) return cudaErrorInvalidValue;
+#define CALL(K, M) topk_filter_kernel<K, M><<<grid, BF_THREADS, 0, s>>>(d, blobs_dev, blob_floats(d), ts.thr, ts.buf, ts.cnt, ts.cap, qlist)
+            JV_DISPATCH_KIND_METRIC(d.kind, metric, CALL);
+#undef CALL
+        }
+        g_launches++;
+        topk_select_kernel<<<active, 256, (size_t)cap2 * sizeof(long long), s>>>(ts.buf, ts.cnt, ts.cap, cap2, k, d.n, ts.thr, ts.thr_safe, keys_out_dev, overflow_flag_dev,
+                                                                                qlist, qnext);
+        g_launches++;
+        int redo = 0;
+        if ((e = cudaMemcpyAsync(&redo, overflow_flag_dev, sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        if (redo == 0) return cudaGetLastError();  // overflow_flag_dev is left at 0
+        active = redo;
+        qlist = qnext;
+    }
+    return cudaGetLastError();  // overflow_flag_dev still holds the number of unresolved queries
 }
 
 // the low word of a key is ~node: adding id_base to the node subtracts it from the key (no borrow: node + base < 2^31)

@@ -187,6 +187,45 @@ __device__ __forceinline__ float score_f32(const DataDesc &d, const float *blob,
     return score_map(METRIC, raw);
 }
 
+// two rows against one query: both rows' loads are issued before either reduction, the query fragment is read once.
+// Accumulation order per row is exactly score_f32_vec's, so a row scores identically in every kernel.
+template <int METRIC>
+__device__ __forceinline__ void score_f32_pair(const DataDesc &d, const float *blob, int nodeA, int nodeB, int lane, float &outA, float &outB)
+{
+    const float4 *ra = reinterpret_cast<const float4 *>(d.rows + (size_t)nodeA * d.stride);
+    const float4 *rb = reinterpret_cast<const float4 *>(d.rows + (size_t)nodeB * d.stride);
+    const float4 *q4 = reinterpret_cast<const float4 *>(blob);
+    const int n4 = d.stride >> 2;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f, na0 = 0.f, na1 = 0.f, nb0 = 0.f, nb1 = 0.f;
+#pragma unroll 3
+    for (int i = lane; i < n4; i += 32) {
+        const float4 x = ldg_stream(ra + i);
+        const float4 y = ldg_stream(rb + i);
+        const float4 q = q4[i];
+        if (METRIC == JV_METRIC_EUCLIDEAN) {
+            float d0 = q.x - x.x, d1 = q.y - x.y, d2 = q.z - x.z, d3 = q.w - x.w;
+            a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
+            d0 = q.x - y.x; d1 = q.y - y.y; d2 = q.z - y.z; d3 = q.w - y.w;
+            b0 = fmaf(d0, d0, b0); b1 = fmaf(d1, d1, b1); b2 = fmaf(d2, d2, b2); b3 = fmaf(d3, d3, b3);
+        } else {
+            a0 = fmaf(q.x, x.x, a0); a1 = fmaf(q.y, x.y, a1); a2 = fmaf(q.z, x.z, a2); a3 = fmaf(q.w, x.w, a3);
+            b0 = fmaf(q.x, y.x, b0); b1 = fmaf(q.y, y.y, b1); b2 = fmaf(q.z, y.z, b2); b3 = fmaf(q.w, y.w, b3);
+            if (METRIC == JV_METRIC_COSINE) {
+                na0 = fmaf(x.x, x.x, na0); na1 = fmaf(x.y, x.y, na1); na0 = fmaf(x.z, x.z, na0); na1 = fmaf(x.w, x.w, na1);
+                nb0 = fmaf(y.x, y.x, nb0); nb1 = fmaf(y.y, y.y, nb1); nb0 = fmaf(y.z, y.z, nb0); nb1 = fmaf(y.w, y.w, nb1);
+            }
+        }
+    }
+    float sa = group_sum<32>((a0 + a1) + (a2 + a3)), sb = group_sum<32>((b0 + b1) + (b2 + b3));
+    if (METRIC == JV_METRIC_COSINE) {
+        const float qn = blob[d.stride];
+        sa = __fdiv_rn(sa, __fsqrt_rn(__fmul_rn(qn, group_sum<32>(na0 + na1))));
+        sb = __fdiv_rn(sb, __fsqrt_rn(__fmul_rn(qn, group_sum<32>(nb0 + nb1))));
+    }
+    outA = score_map(METRIC, sa);
+    outB = score_map(METRIC, sb);
+}
+
 // ------------------------------------------------------------------------------------------------
 // PQ ADC — VectorUtilSupport.assembleAndSum / pqDecodedCosineSimilarity
 // (DefaultVectorUtilSupport.java:303-309; native-c:...:662-724,821-879). 8 lanes per code row, 4 codes per 32-bit load.

@@ -84,10 +84,16 @@ __device__ __forceinline__ void bitonic_sort_desc_block(long long *keys, int n_p
     }
 }
 
-constexpr int SEARCH_THREADS = 256;
+#ifndef JV_SEARCH_THREADS
+#define JV_SEARCH_THREADS 256
+#endif
+#ifndef JV_SEARCH_MINB
+#define JV_SEARCH_MINB 5
+#endif
+constexpr int SEARCH_THREADS = JV_SEARCH_THREADS;
 
 template <int KIND, int METRIC>
-__global__ void __launch_bounds__(SEARCH_THREADS) graph_search_kernel(SearchParams P)
+__global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_kernel(SearchParams P)
 {
     constexpr int G = GroupOf<KIND>::value;
     constexpr int NG = SEARCH_THREADS / G;
@@ -101,7 +107,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS) graph_search_kernel(SearchPara
     uint8_t *flags0 = reinterpret_cast<uint8_t *>(cand_ids + MAX_DEGREE);
     uint8_t *flags1 = flags0 + P.list_pow2;
     __shared__ float red[36];
-    __shared__ int s_q, s_pos, s_n;
+    __shared__ int s_q, s_n;
+    __shared__ int s_posv[2];
 
     const int tid = threadIdx.x;
     const int group = tid / G, lane = tid % G;
@@ -145,18 +152,17 @@ __global__ void __launch_bounds__(SEARCH_THREADS) graph_search_kernel(SearchPara
 
         for (int lvl = P.g.entry_level; lvl >= 0 && !failed; --lvl) {
             const int K = lvl > 0 ? 1 : L;
+            // a new level: every seen node is a candidate again (setEntryPointsFromPreviousLayer), so the first unexpanded
+            // entry is entry 0. s_posv[sel] = first unexpanded position inside the window, maintained by the merge.
             for (int i = tid; i < size; i += SEARCH_THREADS) fcur[i] = 0;
+            int sel = 0;
+            if (tid == 0) { s_posv[0] = 0; s_posv[1] = INT_MAX; s_n = 0; }
+            __syncthreads();
             for (;;) {
-                if (tid == 0) { s_pos = INT_MAX; s_n = 0; }
-                __syncthreads();
-                const int lim = min(size, K);
-                for (int i = tid; i < lim; i += SEARCH_THREADS)
-                    if (!fcur[i]) { atomicMin(&s_pos, i); break; }
-                __syncthreads();
-                const int p = s_pos;
+                const int p = s_posv[sel];
                 if (p == INT_MAX) break;  // stopSearch: every node of the best-K window is expanded
                 const int node = key_node(cur[p]);
-                if (tid == 0) fcur[p] = 1;
+                if (tid == 0) { fcur[p] = 1; s_posv[sel ^ 1] = INT_MAX; }
                 expanded++;
                 if (lvl == 0) expanded_base++;
                 const int32_t *nb;
@@ -171,35 +177,90 @@ __global__ void __launch_bounds__(SEARCH_THREADS) graph_search_kernel(SearchPara
                         const int32_t f = __ldg(nb + t);
                         if (f >= 0 && visited_insert(table, vmask, P.visited_shift, f)) cand_ids[atomicAdd(&s_n, 1)] = f;
                     }
+                // Speculation by the otherwise idle warps: the entries right behind p are the likeliest to be expanded next.
+                // Touch their adjacency rows (-> L2/L1) and, for the small code rows of PQ / BQ (bandwidth is idle on those
+                // paths: the traversal is a latency chain), prefetch their neighbours' rows into L2. Reads only; results unchanged.
+                if (lvl == 0) {
+                    const int w = tid >> 5;
+                    if (w >= 1 && w <= 3) {
+                        const int pp = p + w;
+                        if (pp < size && !fcur[pp]) {
+                            const int32_t *nb2 = P.g.adj0 + (size_t)key_node(cur[pp]) * degree;
+                            for (int t = tid & 31; t < degree; t += 32) {
+                                const int32_t f = __ldg(nb2 + t);
+                                if (KIND == KIND_PQ && f >= 0) {
+                                    const char *a = reinterpret_cast<const char *>(P.approx.codes + (size_t)f * P.approx.code_stride);
+                                    prefetch_l2(a);
+                                    prefetch_l2(a + P.approx.M - 1);
+                                } else if (KIND == KIND_BQ && f >= 0) {
+                                    const char *a = reinterpret_cast<const char *>(P.approx.words + (size_t)f * P.approx.W);
+                                    for (int o = 0; o < P.approx.W * 8; o += 128) prefetch_l2(a + o);
+                                    prefetch_l2(a + P.approx.W * 8 - 1);
+                                }
+                            }
+                        }
+                    }
+                }
                 __syncthreads();
                 const int n = s_n;
                 table_cnt += n;
                 if (table_cnt * 2 > P.visited_cap) { failed = true; break; }
-                for (int i = group; i < n; i += NG) {
-                    const int32_t f = cand_ids[i];
-                    const float sc = score_row<KIND, METRIC>(P.approx, blobA, f, lane);
-                    if (lane == 0) cand_keys[i] = topk_key(sc, f);
+                if (KIND == KIND_F32) {
+                    // two rows per warp at a time: twice the loads in flight, query fragment read once
+                    for (int i = group; i < n; i += 2 * NG) {
+                        const int32_t fa = cand_ids[i];
+                        const bool two = i + NG < n;
+                        const int32_t fb = two ? cand_ids[i + NG] : fa;
+                        float sa, sb;
+                        score_f32_pair<METRIC>(P.approx, blobA, fa, fb, lane, sa, sb);
+                        if (lane == 0) {
+                            cand_keys[i] = topk_key(sa, fa);
+                            if (two) cand_keys[i + NG] = topk_key(sb, fb);
+                        }
+                    }
+                } else {
+                    for (int i = group; i < n; i += NG) {
+                        const int32_t f = cand_ids[i];
+                        const float sc = score_row<KIND, METRIC>(P.approx, blobA, f, lane);
+                        if (lane == 0) cand_keys[i] = topk_key(sc, f);
+                    }
                 }
                 __syncthreads();
                 visited += n;
-                // rank-merge (old list is sorted; candidates are few): every element computes its slot directly
+                // rank-merge (old list is sorted; candidates are few): every element computes its slot directly and the
+                // first unexpanded slot of the next window falls out of the same pass
+                const int newsize = min(L, size + n);
+                const int lim = min(newsize, K);
+                int mypos = INT_MAX;
                 for (int i = tid; i < size; i += SEARCH_THREADS) {
                     const long long k = cur[i];
                     int c = 0;
                     for (int j = 0; j < n; j++) c += (cand_keys[j] > k);
                     const int np = i + c;
-                    if (np < L) { nxt[np] = k; fnxt[np] = fcur[i]; }
+                    if (np < L) {
+                        const uint8_t fl = fcur[i];
+                        nxt[np] = k;
+                        fnxt[np] = fl;
+                        if (!fl && np < lim) mypos = min(mypos, np);
+                    }
                 }
                 for (int j = tid; j < n; j += SEARCH_THREADS) {
                     const long long k = cand_keys[j];
                     int c = count_greater_desc(cur, size, k);
                     for (int jj = 0; jj < n; jj++) c += (cand_keys[jj] > k);
-                    if (c < L) { nxt[c] = k; fnxt[c] = 0; }
+                    if (c < L) {
+                        nxt[c] = k;
+                        fnxt[c] = 0;
+                        if (c < lim) mypos = min(mypos, c);
+                    }
                 }
+                if (mypos != INT_MAX) atomicMin(&s_posv[sel ^ 1], mypos);
+                if (tid == 0) s_n = 0;
                 __syncthreads();
                 { long long *t = cur; cur = nxt; nxt = t; }
                 { uint8_t *t = fcur; fcur = fnxt; fnxt = t; }
-                size = min(L, size + n);
+                size = newsize;
+                sel ^= 1;
             }
             __syncthreads();
         }

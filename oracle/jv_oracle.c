@@ -981,6 +981,51 @@ double jvo_graph_search_batch(const jvo_graph *g, const jvo_dataset *ds, const f
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
+
+/* ---- multi-threaded BQ brute force (CPU baseline of config 4): per query, scan every row with the scalar popcount loop of
+ *      base:vector/DefaultVectorUtilSupport.java:342-348, keep the best k by the reference key in a bounded min-heap ---- */
+typedef struct { const uint64_t *words; int64_t n; int W, dim; const uint64_t *q; int q0, q1, k; int64_t *keys; } bq_job;
+
+static void *bq_worker(void *arg)
+{
+    bq_job *j = (bq_job *)arg;
+    for (int qi = j->q0; qi < j->q1; qi++) {
+        kheap h;
+        kh_init(&h, j->k, j->k, 0);
+        const uint64_t *qw = j->q + (size_t)qi * j->W;
+        for (int64_t r = 0; r < j->n; r++) {
+            float sc = jvo_bq_score(qw, j->words + (size_t)r * j->W, j->W, j->dim);
+            int64_t key = jvo_topk_key(sc, (int32_t)r);
+            if (h.size < j->k || key > h.a[1]) kh_push(&h, key);
+        }
+        int64_t *out = j->keys + (size_t)qi * j->k;
+        int c = h.size;
+        for (int i = c; i < j->k; i++) out[i] = INT64_MIN;
+        for (int i = c - 1; i >= 0; i--) out[i] = kh_pop(&h);
+        free(h.a);
+    }
+    return NULL;
+}
+
+double jvo_bq_bruteforce_batch(const uint64_t *words, int64_t n, int dim, const uint64_t *qwords, int nq, int k, int threads, int64_t *keys_out)
+{
+    int W = (dim + 63) / 64;
+    if (threads < 1) threads = 1;
+    if (threads > nq) threads = nq > 0 ? nq : 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    bq_job *jobs = (bq_job *)calloc((size_t)threads, sizeof(bq_job));
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (bq_job){words, n, W, dim, qwords, (int)((int64_t)nq * t / threads), (int)((int64_t)nq * (t + 1) / threads), k, keys_out};
+        pthread_create(&th[t], NULL, bq_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    free(th); free(jobs);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
 /* ============================================================================================
  * Vamana diversity — base:graph/diversity/VamanaDiversityProvider.java:45-95 (diverseBefore = 0)
  * ========================================================================================== */

@@ -131,6 +131,9 @@ double jvo_graph_search_batch(const jvo_graph *g, const jvo_dataset *ds, const f
                               int topK, int rerankK, int threads, int32_t *nodes_out, float *scores_out,
                               int64_t *scored_total);
 
+/* multi-threaded BQ brute force, keys_out [nq][k] best first; returns seconds */
+double jvo_bq_bruteforce_batch(const uint64_t *words, int64_t n, int dim, const uint64_t *qwords, int nq, int k, int threads, int64_t *keys_out);
+
 /* single-threaded Vamana build (no hierarchy when levels_out==1) following GraphIndexBuilder.addGraphNode;
  * exact f32 scoring. adj_out: [n][degree] -1 padded. Returns entry node. */
 int32_t jvo_graph_build_f32(int metric, const float *base, int32_t n, int dim, int degree, int beam,

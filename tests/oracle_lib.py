@@ -126,6 +126,7 @@ def load():
     sig("jvo_scorer_free", None, P)
     sig("jvo_graph_search", I, C.POINTER(Graph), P, P, I, I, i32p, f32p, C.POINTER(Stats))
     sig("jvo_graph_search_batch", C.c_double, C.POINTER(Graph), C.POINTER(Dataset), f32p, I, I, I, I, i32p, f32p, i64p)
+    sig("jvo_bq_bruteforce_batch", C.c_double, u64p, C.c_int64, I, u64p, I, I, I, i64p)
     sig("jvo_graph_build_f32", C.c_int32, I, f32p, C.c_int32, I, I, I, F, F, i32p)
     sig("jvo_retain_diverse", I, f32p, i32p, I, f32p, I, F, u8p)
     _lib = L
@@ -241,10 +242,11 @@ def train_pq_numpy(rng, data, M, k=256, iters=6):
         for _ in range(iters):
             d = (sub * sub).sum(1)[:, None] - 2 * sub @ cent.T + (cent * cent).sum(1)[None, :]
             a = d.argmin(1)
-            for c in range(k):
-                sel = a == c
-                if sel.any():
-                    cent[c] = sub[sel].mean(0)
+            cnt = np.bincount(a, minlength=k).astype(np.float32)
+            sums = np.zeros((k, sizes[m]), dtype=np.float32)
+            np.add.at(sums, a, sub)
+            nz = cnt > 0
+            cent[nz] = sums[nz] / cnt[nz, None]
         out[k * offsets[m]: k * (offsets[m] + sizes[m])] = cent.reshape(-1)
     return out, sizes, offsets
 

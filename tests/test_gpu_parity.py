@@ -439,3 +439,73 @@ def test_errors(jv):
     with pytest.raises(jv.JVectorB200Error):
         jv.topk_bruteforce(vec, o.DOT_PRODUCT, rows[:1], 0)
     vec.close()
+
+
+# ------------------------------------------------------------------------------------------------ specialised brute force
+def test_pq_bruteforce_tma_lut(jv, oracle):
+    # PQ ADC brute force: LUT staged into shared memory by TMA bulk copies; keys must order exactly like the oracle's
+    rng = np.random.default_rng(31)
+    n, dim, M, k = 5000, 64, 16, 256
+    data, cb, sizes, offsets, cen, codes, _ = _pq(rng, oracle, n, dim, M, False)
+    queries = o.random_unit_vectors(rng, 6, dim)
+    pqv = jv.PQVectors(codes, cb, dim, k)
+    mag = np.empty(M * k, np.float32)
+    oracle.jvo_pq_self_magnitudes(fp(cb), ip(sizes), ip(offsets), M, k, fp(mag))
+    for metric in METRICS:
+        nodes, scores, keys = jv.topk_bruteforce(pqv, metric, queries, 20)
+        lm = o.EUCLIDEAN if metric == o.EUCLIDEAN else o.DOT_PRODUCT
+        for qi in range(6):
+            lut = np.empty(M * k, np.float32)
+            oracle.jvo_pq_lut(fp(cb), ip(sizes), ip(offsets), M, k, None, fp(queries[qi]), dim, lm, fp(lut))
+            bmag = oracle.jvo_dot_f32(fp(queries[qi]), fp(queries[qi]), dim)
+            sc = np.array([oracle.jvo_pq_score_lut(metric, fp(lut), fp(mag), bmag, k, bp(codes[i]), M) for i in range(n)], np.float32)
+            order = np.argsort(-o.keys_of(sc, np.arange(n)).astype(np.float64), kind="stable")[:20]
+            close(scores[qi], sc[order])
+            assert len(set(nodes[qi]) & set(order.tolist())) >= 18  # fp32 near-ties may swap the tail
+    pqv.close()
+
+
+def test_sharded_bruteforce_single_rank_device(jv, oracle):
+    # the N = 1 degenerate of the multi-GPU path: device-resident queries/keys, global id rebasing, device merge kernel
+    import torch
+
+    from jvector_b200 import parallel as par
+    rng = np.random.default_rng(9)
+    n, dim, W = 4000, 256, 4
+    data = rng.standard_normal((n, dim)).astype(np.float32)
+    queries = rng.standard_normal((5, dim)).astype(np.float32)
+    words = jv.bq_encode_all(data)
+    halves = [jv.BQVectors(words[:2000], dim), jv.BQVectors(words[2000:], dim)]
+    qd = torch.from_numpy(queries).cuda()
+    parts = [par.gpu_sharded_bruteforce(None, halves[i], o.COSINE, 2000 * i).local_topk(qd, 15) for i in range(2)]
+    merged = par.gpu_sharded_bruteforce(None, halves[0], o.COSINE, 0).merge(torch.stack(parts), 15).cpu().numpy()
+    full = jv.BQVectors(words, dim)
+    _, _, want = jv.topk_bruteforce(full, o.COSINE, queries, 15)
+    assert np.array_equal(merged, want)  # integer ordering: bit-exact across the shard boundary
+    for v in halves + [full]:
+        v.close()
+
+
+def test_device_builder_quality_vs_reference_builder(jv, oracle):
+    # the batched device builder must give a graph as searchable as the reference's sequential insert (oracle restatement)
+    rng = np.random.default_rng(17)
+    n, dim, lat = 6000, 64, 12
+    A = rng.standard_normal((lat, dim)).astype(np.float32)
+    def gen(m):
+        x = rng.standard_normal((m, lat)).astype(np.float32) @ A + 0.3 * rng.standard_normal((m, dim)).astype(np.float32)
+        return np.ascontiguousarray(x / np.linalg.norm(x, axis=1, keepdims=True), dtype=np.float32)
+    data, queries = gen(n), gen(200)
+    vec = jv.F32Vectors(data)
+    gt, _, _ = jv.topk_bruteforce(vec, o.DOT_PRODUCT, queries, 10)
+    adj = np.empty((n, 16), np.int32)
+    entry = oracle.jvo_graph_build_f32(o.DOT_PRODUCT, fp(data), n, dim, 16, 60, 1.2, 1.2, ip(adj))
+    g_ref = jv.GraphIndex(adj, entry)
+    g_dev = jv.GraphIndexBuilder(o.DOT_PRODUCT, M=16, beamWidth=60, neighborOverflow=1.2, alpha=1.2).build(vec)
+    rec = {}
+    for name, g in (("ref", g_ref), ("dev", g_dev)):
+        res = jv.GraphSearcher(g).search(vec, queries, o.DOT_PRODUCT, 10, 30)
+        rec[name] = np.mean([len(set(res.nodes[i]) & set(gt[i])) / 10.0 for i in range(200)])
+        rec[name + "_visited"] = res.visitedCount / 200.0
+    assert rec["dev"] >= rec["ref"] - 0.03, rec
+    assert rec["dev_visited"] <= 1.25 * rec["ref_visited"], rec
+    vec.close()
