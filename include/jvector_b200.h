@@ -187,6 +187,8 @@ typedef struct {
     int max_batch;     /* 0 = default */
 } jv_build_params;
 JV_API int jv_graph_build(jv_dataset f32, int metric, const jv_build_params *params, jv_graph *out, double *device_ms);
+/* counters of this thread's last jv_graph_build (level 0): vectors scored by the insert searches, batches, back-links dropped */
+JV_API int jv_graph_build_stats(int64_t *scored_vectors, int64_t *batches, int64_t *dropped_backlinks);
 
 /* device-memory helpers for callers that keep queries/results in HBM (bench `value` leg) */
 JV_API int jv_device_malloc(void **out, size_t bytes);

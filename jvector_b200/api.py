@@ -292,4 +292,7 @@ class GraphIndexBuilder:
         ms = C.c_double()
         check(lib.jv_graph_build(vectors._h, int(self.vsf), C.byref(self.params), C.byref(h), C.byref(ms)))
         self.device_ms = ms.value
+        s, b, d = C.c_int64(), C.c_int64(), C.c_int64()
+        lib.jv_graph_build_stats(C.byref(s), C.byref(b), C.byref(d))
+        self.scored_vectors, self.batches, self.dropped_backlinks = s.value, b.value, d.value
         return GraphIndex(_handle=h)

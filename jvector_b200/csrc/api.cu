@@ -71,6 +71,7 @@ struct ThreadCtx {
     }
 };
 thread_local ThreadCtx t_ctx;
+thread_local BuildStats t_build_stats = {0, 0, 0, 0};
 
 int round4(int v) { return (v + 3) & ~3; }
 
@@ -781,6 +782,7 @@ int jv_graph_build(jv_dataset f32, int metric, const jv_build_params *params, jv
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    t_build_stats = bs;
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "build_graph_flat"); }
     g->g.n = n; g->g.degree = degree; g->g.levels = 1; g->g.entry_node = 0; g->g.entry_level = 0; g->g.adj0 = g->adj0;
     if (params->add_hierarchy && n > 1) {
@@ -839,6 +841,14 @@ int jv_graph_build(jv_dataset f32, int metric, const jv_build_params *params, jv
     }
     if (device_ms) *device_ms = ms;
     *out = g;
+    return JV_OK;
+}
+
+int jv_graph_build_stats(int64_t *scored_vectors, int64_t *batches, int64_t *dropped_backlinks)
+{
+    if (scored_vectors) *scored_vectors = t_build_stats.searched;
+    if (batches) *batches = t_build_stats.batches;
+    if (dropped_backlinks) *dropped_backlinks = t_build_stats.dropped_backlinks;
     return JV_OK;
 }
 

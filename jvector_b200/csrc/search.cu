@@ -177,10 +177,11 @@ __global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_k
                         const int32_t f = __ldg(nb + t);
                         if (f >= 0 && visited_insert(table, vmask, P.visited_shift, f)) cand_ids[atomicAdd(&s_n, 1)] = f;
                     }
-                // Speculation by the otherwise idle warps: the entries right behind p are the likeliest to be expanded next.
-                // Touch their adjacency rows (-> L2/L1) and, for the small code rows of PQ / BQ (bandwidth is idle on those
-                // paths: the traversal is a latency chain), prefetch their neighbours' rows into L2. Reads only; results unchanged.
-                if (lvl == 0) {
+                // Speculation by the otherwise idle warps (PQ / BQ only: their traversal is a latency chain and HBM is idle, while
+                // the fp32 / NVQ paths are bandwidth-bound and must not waste it): the entries right behind p are the likeliest to
+                // be expanded next, so touch their adjacency rows and prefetch their neighbours' code rows into L2.
+                // Reads only; results unchanged.
+                if (lvl == 0 && (KIND == KIND_PQ || KIND == KIND_BQ)) {
                     const int w = tid >> 5;
                     if (w >= 1 && w <= 3) {
                         const int pp = p + w;

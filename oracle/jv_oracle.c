@@ -513,6 +513,9 @@ typedef float (*fn_pqcos)(const unsigned char *, int, size_t, int, const float *
 typedef float (*fn_nvq)(const float *, const unsigned char *, size_t, float, float, float, float);
 typedef int64_t (*fn_nvqcos)(const float *, const unsigned char *, size_t, float, float, float, float, const float *);
 typedef void (*fn_shuf)(float *, size_t);
+typedef void (*fn_nvqq)(const float *, size_t, float, float, float, float, unsigned char *);
+typedef float (*fn_nvql)(const float *, size_t, float, float, float, float, int);
+typedef float (*fn_nvqu)(const float *, size_t, float, float, int);
 typedef const char *(*fn_str)(void);
 
 static struct {
@@ -525,6 +528,9 @@ static struct {
     fn_nvq nvq_dot, nvq_l2;
     fn_nvqcos nvq_cos;
     fn_shuf shuffle;
+    fn_nvqq nvq_quant;
+    fn_nvql nvq_lossf;
+    fn_nvqu nvq_uloss;
     fn_str isa;
 } REF;
 
@@ -546,6 +552,9 @@ int jvo_use_ref(const char *path)
     REF.nvq_l2 = (fn_nvq)dlsym(h, "nvq_square_l2_distance_8bit");
     REF.nvq_cos = (fn_nvqcos)dlsym(h, "nvq_cosine_8bit_packed");
     REF.shuffle = (fn_shuf)dlsym(h, "nvq_shuffle_query_in_place_8bit");
+    REF.nvq_quant = (fn_nvqq)dlsym(h, "nvq_quantize_8bit");
+    REF.nvq_lossf = (fn_nvql)dlsym(h, "nvq_loss");
+    REF.nvq_uloss = (fn_nvqu)dlsym(h, "nvq_uniform_loss");
     REF.isa = (fn_str)dlsym(h, "jvector_simd_get_active_isa");
     if (!REF.dot || !REF.l2 || !REF.cos || !REF.adc || !REF.ps_dot || !REF.ps_l2 || !REF.ps_mag || !REF.pqcos ||
         !REF.nvq_dot || !REF.nvq_l2 || !REF.nvq_cos || !REF.shuffle || !REF.isa) {
@@ -1019,6 +1028,72 @@ double jvo_bq_bruteforce_batch(const uint64_t *words, int64_t n, int dim, const 
     for (int t = 0; t < threads; t++) {
         jobs[t] = (bq_job){words, n, W, dim, qwords, (int)((int64_t)nq * t / threads), (int)((int64_t)nq * (t + 1) / threads), k, keys_out};
         pthread_create(&th[t], NULL, bq_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    free(th); free(jobs);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+
+/* ---- multi-threaded NVQ encode (CPU baseline of config 5's encode step): NVQuantization.encodeAll parallel stream
+ *      (base:quantization/NVQuantization.java:185-193) -> quantizeTo (:524-578), through the reference kernels when loaded ---- */
+typedef struct { const float *rows; int64_t r0, r1; int dim, nsub, learn; const float *mean; float *params; uint8_t *bytes; } nvq_job;
+
+static void nvq_encode_sub_ref(const float *v, int n, int learn, float *params_out, uint8_t *bytes_out)
+{
+    float minv = 3.402823466e+38f, maxv = -3.402823466e+38f;
+    for (int i = 0; i < n; i++) { if (v[i] < minv) minv = v[i]; if (v[i] > maxv) maxv = v[i]; }
+    float growth = 1e-2f;
+    if (learn) {
+        float baseline = REF.nvq_uloss(v, (size_t)n, minv, maxv, 8);
+        float coarse = 1e-2f, best = 1.40129846e-45f;
+        for (float gr = 1e-6f; gr < 20.f; gr += 1.f) {
+            float lv = baseline / REF.nvq_lossf(v, (size_t)n, gr, 0.f, minv, maxv, 8);
+            if (lv > best) { best = lv; coarse = gr; }
+        }
+        float fine = coarse;
+        for (float gr = coarse - 1; gr < coarse + 1; gr += 0.1f) {
+            float lv = baseline / REF.nvq_lossf(v, (size_t)n, gr, 0.f, minv, maxv, 8);
+            if (lv > best) { best = lv; fine = gr; }
+        }
+        growth = fine;
+    }
+    REF.nvq_quant(v, (size_t)n, growth, 0.f, minv, maxv, bytes_out);
+    params_out[0] = minv; params_out[1] = maxv; params_out[2] = growth; params_out[3] = 0.f;
+}
+
+static void *nvq_worker(void *arg)
+{
+    nvq_job *j = (nvq_job *)arg;
+    int *sizes = (int *)malloc(sizeof(int) * j->nsub * 2), *offsets = sizes + j->nsub;
+    float *c = (float *)malloc(sizeof(float) * j->dim);
+    jvo_pq_layout(j->dim, j->nsub, sizes, offsets);
+    for (int64_t r = j->r0; r < j->r1; r++) {
+        const float *v = j->rows + (size_t)r * j->dim;
+        if (REF.h) {
+            for (int i = 0; i < j->dim; i++) c[i] = v[i] - j->mean[i];
+            for (int s = 0; s < j->nsub; s++)
+                nvq_encode_sub_ref(c + offsets[s], sizes[s], j->learn, j->params + ((size_t)r * j->nsub + s) * 4, j->bytes + (size_t)r * j->dim + offsets[s]);
+        } else {
+            jvo_nvq_encode(v, j->mean, j->dim, j->nsub, j->learn, j->params + (size_t)r * j->nsub * 4, j->bytes + (size_t)r * j->dim);
+        }
+    }
+    free(c); free(sizes);
+    return NULL;
+}
+
+double jvo_nvq_encode_batch(const float *rows, int64_t n, int dim, int nsub, const float *mean, int learn, int threads, float *params_out, uint8_t *bytes_out)
+{
+    if (threads < 1) threads = 1;
+    if (threads > n) threads = n > 0 ? (int)n : 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    nvq_job *jobs = (nvq_job *)calloc((size_t)threads, sizeof(nvq_job));
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (nvq_job){rows, n * t / threads, n * (t + 1) / threads, dim, nsub, learn, mean, params_out, bytes_out};
+        pthread_create(&th[t], NULL, nvq_worker, &jobs[t]);
     }
     for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
     clock_gettime(CLOCK_MONOTONIC, &t1);

@@ -131,6 +131,9 @@ double jvo_graph_search_batch(const jvo_graph *g, const jvo_dataset *ds, const f
                               int topK, int rerankK, int threads, int32_t *nodes_out, float *scores_out,
                               int64_t *scored_total);
 
+/* multi-threaded NVQ encode (reference kernels when jvo_use_ref was called); returns seconds */
+double jvo_nvq_encode_batch(const float *rows, int64_t n, int dim, int nsub, const float *mean, int learn, int threads, float *params_out, uint8_t *bytes_out);
+
 /* multi-threaded BQ brute force, keys_out [nq][k] best first; returns seconds */
 double jvo_bq_bruteforce_batch(const uint64_t *words, int64_t n, int dim, const uint64_t *qwords, int nq, int k, int threads, int64_t *keys_out);
 
