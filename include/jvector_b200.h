@@ -144,6 +144,10 @@ JV_API int jv_pq_encode_batch(const float *rows, int64_t n, int dim, int M, int 
                               const float *centroid, uint8_t *codes_out);
 JV_API int jv_nvq_encode_batch(const float *rows, int64_t n, int dim, int nsub, const float *mean, int learn,
                                float *params_out, uint8_t *bytes_out);
+/* the same encoders over rows that are already resident in HBM (a registered fp32 data set): no host->device copy */
+JV_API int jv_bq_encode_dataset(jv_dataset f32, uint64_t *words_out);
+JV_API int jv_pq_encode_dataset(jv_dataset f32, int M, int k, const float *codebooks, const float *centroid, uint8_t *codes_out);
+JV_API int jv_nvq_encode_dataset(jv_dataset f32, int nsub, const float *mean, int learn, float *params_out, uint8_t *bytes_out);
 
 /* ---- graph: ImmutableGraphIndex adjacency in HBM + GraphSearcher traversal on the device ---- */
 /* adj0: [n][degree] int32, -1 padded (level 0). */

@@ -174,7 +174,12 @@ def topk_bruteforce(vectors, vsf, queries, k):
 
 
 def bq_encode_all(rows):
+    """BinaryQuantization.encodeAll. rows: a host array, or F32Vectors already resident in HBM (no upload)."""
     lib = nat.init()
+    if isinstance(rows, F32Vectors):
+        out = np.empty((rows.size(), (rows.dimension() + 63) // 64), dtype=np.uint64)
+        check(lib.jv_bq_encode_dataset(rows._h, wp(out)))
+        return out
     rows = c32(rows)
     out = np.empty((rows.shape[0], (rows.shape[1] + 63) // 64), dtype=np.uint64)
     check(lib.jv_bq_encode_batch(fp(rows), rows.shape[0], rows.shape[1], wp(out)))
@@ -182,19 +187,30 @@ def bq_encode_all(rows):
 
 
 def pq_encode_all(rows, codebooks, M, k=256, centroid=None):
+    """ProductQuantization.encodeAll. rows: a host array, or F32Vectors already resident in HBM (no upload)."""
     lib = nat.init()
-    rows = c32(rows)
     codebooks = c32(codebooks).reshape(-1)
     cen = c32(centroid) if centroid is not None else None
+    if isinstance(rows, F32Vectors):
+        out = np.empty((rows.size(), M), dtype=np.uint8)
+        check(lib.jv_pq_encode_dataset(rows._h, M, k, fp(codebooks), fp(cen), bp(out)))
+        return out
+    rows = c32(rows)
     out = np.empty((rows.shape[0], M), dtype=np.uint8)
     check(lib.jv_pq_encode_batch(fp(rows), rows.shape[0], rows.shape[1], M, k, fp(codebooks), fp(cen), bp(out)))
     return out
 
 
 def nvq_encode_all(rows, mean, nsub, learn=True):
+    """NVQuantization.encodeAll. rows: a host array, or F32Vectors already resident in HBM (no upload)."""
     lib = nat.init()
-    rows = c32(rows)
     mean = c32(mean)
+    if isinstance(rows, F32Vectors):
+        params = np.empty((rows.size(), nsub, 4), dtype=np.float32)
+        out = np.empty((rows.size(), rows.dimension()), dtype=np.uint8)
+        check(lib.jv_nvq_encode_dataset(rows._h, nsub, fp(mean), 1 if learn else 0, fp(params), bp(out)))
+        return params, out
+    rows = c32(rows)
     params = np.empty((rows.shape[0], nsub, 4), dtype=np.float32)
     out = np.empty(rows.shape, dtype=np.uint8)
     check(lib.jv_nvq_encode_batch(fp(rows), rows.shape[0], rows.shape[1], nsub, fp(mean), 1 if learn else 0, fp(params), bp(out)))

@@ -486,17 +486,64 @@ int jv_topk_merge_device(const int64_t *keys_in_device, int nq, int parts, int k
 }
 
 // ------------------------------------------------------------------------------------------------ encoders
+static int bq_encode_impl(const float *rows_host, const float *rows_dev, int row_stride, int64_t n, int dim, uint64_t *words_out)
+{
+    int rc;
+    const int W = (dim + 63) / 64;
+    if ((rc = t_ctx.init()) || (rows_host && (rc = t_ctx.ensure(0, (size_t)n * dim * 4))) || (rc = t_ctx.ensure(1, (size_t)n * W * 8))) return rc;
+    cudaStream_t s = t_ctx.stream;
+    if (rows_host) {
+        CK(cudaMemcpyAsync(t_ctx.dbuf[0], rows_host, (size_t)n * dim * 4, cudaMemcpyHostToDevice, s), "H2D rows");
+        rows_dev = (const float *)t_ctx.dbuf[0];
+        row_stride = dim;
+    }
+    CK(launch_bq_encode(rows_dev, n, dim, row_stride, (unsigned long long *)t_ctx.dbuf[1], s), "bq_encode");
+    CK(cudaMemcpyAsync(words_out, t_ctx.dbuf[1], (size_t)n * W * 8, cudaMemcpyDeviceToHost, s), "D2H words");
+    CK(cudaStreamSynchronize(s), "sync");
+    return JV_OK;
+}
+
 int jv_bq_encode_batch(const float *rows, int64_t n, int dim, uint64_t *words_out)
 {
     NEED_INIT();
     if (!rows || !words_out || n <= 0 || dim <= 0) return fail(JV_ERR_INVALID, "bq_encode: bad arguments");
+    return bq_encode_impl(rows, nullptr, 0, n, dim, words_out);
+}
+
+int jv_bq_encode_dataset(jv_dataset f32, uint64_t *words_out)
+{
+    NEED_INIT();
+    if (!f32 || f32->d.kind != KIND_F32 || !words_out) return fail(JV_ERR_INVALID, "bq_encode_dataset: needs an fp32 data set");
+    return bq_encode_impl(nullptr, f32->d.rows, f32->d.stride, f32->d.n, f32->d.dim, words_out);
+}
+
+static int pq_encode_impl(const float *rows, const float *rows_dev, int row_stride, int64_t n, int dim, int M, int k, const float *codebooks,
+                          const float *centroid, uint8_t *codes_out)
+{
     int rc;
-    const int W = (dim + 63) / 64;
-    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(0, (size_t)n * dim * 4)) || (rc = t_ctx.ensure(1, (size_t)n * W * 8))) return rc;
+    std::vector<int> sizes, offsets;
+    pq_layout(dim, M, sizes, offsets);
+    const size_t cb_bytes = (size_t)k * dim * 4;
+    const size_t aux = cb_bytes + (size_t)dim * 4 + (size_t)M * 8 + 64;
+    if ((rc = t_ctx.init()) || (rows && (rc = t_ctx.ensure(0, (size_t)n * dim * 4))) || (rc = t_ctx.ensure(1, (size_t)n * M)) || (rc = t_ctx.ensure(2, aux))) return rc;
     cudaStream_t s = t_ctx.stream;
-    CK(cudaMemcpyAsync(t_ctx.dbuf[0], rows, (size_t)n * dim * 4, cudaMemcpyHostToDevice, s), "H2D rows");
-    CK(launch_bq_encode((const float *)t_ctx.dbuf[0], n, dim, (unsigned long long *)t_ctx.dbuf[1], s), "bq_encode");
-    CK(cudaMemcpyAsync(words_out, t_ctx.dbuf[1], (size_t)n * W * 8, cudaMemcpyDeviceToHost, s), "D2H words");
+    char *a = (char *)t_ctx.dbuf[2];
+    float *dcb = (float *)a, *dcen = (float *)(a + cb_bytes);
+    int *dsz = (int *)(a + cb_bytes + (size_t)dim * 4), *doff = dsz + M;
+    if (rows) {
+        CK(cudaMemcpyAsync(t_ctx.dbuf[0], rows, (size_t)n * dim * 4, cudaMemcpyHostToDevice, s), "H2D rows");
+        rows_dev = (const float *)t_ctx.dbuf[0];
+        row_stride = dim;
+    }
+    CK(cudaMemcpyAsync(dcb, codebooks, cb_bytes, cudaMemcpyHostToDevice, s), "H2D codebooks");
+    if (centroid) CK(cudaMemcpyAsync(dcen, centroid, (size_t)dim * 4, cudaMemcpyHostToDevice, s), "H2D centroid");
+    CK(cudaMemcpyAsync(dsz, sizes.data(), (size_t)M * 4, cudaMemcpyHostToDevice, s), "H2D sizes");
+    CK(cudaMemcpyAsync(doff, offsets.data(), (size_t)M * 4, cudaMemcpyHostToDevice, s), "H2D offsets");
+    DataDesc d;
+    memset(&d, 0, sizeof(d));
+    d.kind = KIND_PQ; d.dim = dim; d.n = n; d.M = M; d.k = k; d.codebooks = dcb; d.sub_sizes = dsz; d.sub_offsets = doff; d.centroid = centroid ? dcen : nullptr;
+    CK(launch_pq_encode(d, rows_dev, n, row_stride, (uint8_t *)t_ctx.dbuf[1], s), "pq_encode");
+    CK(cudaMemcpyAsync(codes_out, t_ctx.dbuf[1], (size_t)n * M, cudaMemcpyDeviceToHost, s), "D2H codes");
     CK(cudaStreamSynchronize(s), "sync");
     return JV_OK;
 }
@@ -505,26 +552,42 @@ int jv_pq_encode_batch(const float *rows, int64_t n, int dim, int M, int k, cons
 {
     NEED_INIT();
     if (!rows || !codebooks || !codes_out || n <= 0 || dim <= 0 || M <= 0 || M > dim || k <= 0 || k > 256) return fail(JV_ERR_INVALID, "pq_encode: bad arguments");
+    return pq_encode_impl(rows, nullptr, 0, n, dim, M, k, codebooks, centroid, codes_out);
+}
+
+int jv_pq_encode_dataset(jv_dataset f32, int M, int k, const float *codebooks, const float *centroid, uint8_t *codes_out)
+{
+    NEED_INIT();
+    if (!f32 || f32->d.kind != KIND_F32 || !codebooks || !codes_out || M <= 0 || M > f32->d.dim || k <= 0 || k > 256)
+        return fail(JV_ERR_INVALID, "pq_encode_dataset: bad arguments");
+    return pq_encode_impl(nullptr, f32->d.rows, f32->d.stride, f32->d.n, f32->d.dim, M, k, codebooks, centroid, codes_out);
+}
+
+static int nvq_encode_impl(const float *rows, const float *rows_dev, int row_stride, int64_t n, int dim, int nsub, const float *mean, int learn,
+                           float *params_out, uint8_t *bytes_out)
+{
     int rc;
     std::vector<int> sizes, offsets;
-    pq_layout(dim, M, sizes, offsets);
-    const size_t cb_bytes = (size_t)k * dim * 4;
-    const size_t aux = cb_bytes + (size_t)dim * 4 + (size_t)M * 8 + 64;
-    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(0, (size_t)n * dim * 4)) || (rc = t_ctx.ensure(1, (size_t)n * M)) || (rc = t_ctx.ensure(2, aux))) return rc;
+    pq_layout(dim, nsub, sizes, offsets);
+    const size_t aux = (size_t)dim * 4 + (size_t)nsub * 8 + 64;
+    if ((rc = t_ctx.init()) || (rows && (rc = t_ctx.ensure(0, (size_t)n * dim * 4))) || (rc = t_ctx.ensure(1, (size_t)n * dim)) ||
+        (rc = t_ctx.ensure(2, aux)) || (rc = t_ctx.ensure(3, (size_t)n * nsub * 16)))
+        return rc;
     cudaStream_t s = t_ctx.stream;
     char *a = (char *)t_ctx.dbuf[2];
-    float *dcb = (float *)a, *dcen = (float *)(a + cb_bytes);
-    int *dsz = (int *)(a + cb_bytes + (size_t)dim * 4), *doff = dsz + M;
-    CK(cudaMemcpyAsync(t_ctx.dbuf[0], rows, (size_t)n * dim * 4, cudaMemcpyHostToDevice, s), "H2D rows");
-    CK(cudaMemcpyAsync(dcb, codebooks, cb_bytes, cudaMemcpyHostToDevice, s), "H2D codebooks");
-    if (centroid) CK(cudaMemcpyAsync(dcen, centroid, (size_t)dim * 4, cudaMemcpyHostToDevice, s), "H2D centroid");
-    CK(cudaMemcpyAsync(dsz, sizes.data(), (size_t)M * 4, cudaMemcpyHostToDevice, s), "H2D sizes");
-    CK(cudaMemcpyAsync(doff, offsets.data(), (size_t)M * 4, cudaMemcpyHostToDevice, s), "H2D offsets");
-    DataDesc d;
-    memset(&d, 0, sizeof(d));
-    d.kind = KIND_PQ; d.dim = dim; d.n = n; d.M = M; d.k = k; d.codebooks = dcb; d.sub_sizes = dsz; d.sub_offsets = doff; d.centroid = centroid ? dcen : nullptr;
-    CK(launch_pq_encode(d, (const float *)t_ctx.dbuf[0], n, (uint8_t *)t_ctx.dbuf[1], s), "pq_encode");
-    CK(cudaMemcpyAsync(codes_out, t_ctx.dbuf[1], (size_t)n * M, cudaMemcpyDeviceToHost, s), "D2H codes");
+    float *dmean = (float *)a;
+    int *dsz = (int *)(a + (size_t)dim * 4), *doff = dsz + nsub;
+    if (rows) {
+        CK(cudaMemcpyAsync(t_ctx.dbuf[0], rows, (size_t)n * dim * 4, cudaMemcpyHostToDevice, s), "H2D rows");
+        rows_dev = (const float *)t_ctx.dbuf[0];
+        row_stride = dim;
+    }
+    CK(cudaMemcpyAsync(dmean, mean, (size_t)dim * 4, cudaMemcpyHostToDevice, s), "H2D mean");
+    CK(cudaMemcpyAsync(dsz, sizes.data(), (size_t)nsub * 4, cudaMemcpyHostToDevice, s), "H2D sizes");
+    CK(cudaMemcpyAsync(doff, offsets.data(), (size_t)nsub * 4, cudaMemcpyHostToDevice, s), "H2D offsets");
+    CK(launch_nvq_encode(rows_dev, n, row_stride, nsub, dsz, doff, dmean, learn, (float *)t_ctx.dbuf[3], (uint8_t *)t_ctx.dbuf[1], dim, s), "nvq_encode");
+    CK(cudaMemcpyAsync(params_out, t_ctx.dbuf[3], (size_t)n * nsub * 16, cudaMemcpyDeviceToHost, s), "D2H params");
+    CK(cudaMemcpyAsync(bytes_out, t_ctx.dbuf[1], (size_t)n * dim, cudaMemcpyDeviceToHost, s), "D2H bytes");
     CK(cudaStreamSynchronize(s), "sync");
     return JV_OK;
 }
@@ -533,26 +596,15 @@ int jv_nvq_encode_batch(const float *rows, int64_t n, int dim, int nsub, const f
 {
     NEED_INIT();
     if (!rows || !mean || !params_out || !bytes_out || n <= 0 || dim <= 0 || nsub <= 0 || nsub > dim) return fail(JV_ERR_INVALID, "nvq_encode: bad arguments");
-    int rc;
-    std::vector<int> sizes, offsets;
-    pq_layout(dim, nsub, sizes, offsets);
-    const size_t aux = (size_t)dim * 4 + (size_t)nsub * 8 + 64;
-    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(0, (size_t)n * dim * 4)) || (rc = t_ctx.ensure(1, (size_t)n * dim)) ||
-        (rc = t_ctx.ensure(2, aux)) || (rc = t_ctx.ensure(3, (size_t)n * nsub * 16)))
-        return rc;
-    cudaStream_t s = t_ctx.stream;
-    char *a = (char *)t_ctx.dbuf[2];
-    float *dmean = (float *)a;
-    int *dsz = (int *)(a + (size_t)dim * 4), *doff = dsz + nsub;
-    CK(cudaMemcpyAsync(t_ctx.dbuf[0], rows, (size_t)n * dim * 4, cudaMemcpyHostToDevice, s), "H2D rows");
-    CK(cudaMemcpyAsync(dmean, mean, (size_t)dim * 4, cudaMemcpyHostToDevice, s), "H2D mean");
-    CK(cudaMemcpyAsync(dsz, sizes.data(), (size_t)nsub * 4, cudaMemcpyHostToDevice, s), "H2D sizes");
-    CK(cudaMemcpyAsync(doff, offsets.data(), (size_t)nsub * 4, cudaMemcpyHostToDevice, s), "H2D offsets");
-    CK(launch_nvq_encode((const float *)t_ctx.dbuf[0], n, dim, nsub, dsz, doff, dmean, learn, (float *)t_ctx.dbuf[3], (uint8_t *)t_ctx.dbuf[1], dim, s), "nvq_encode");
-    CK(cudaMemcpyAsync(params_out, t_ctx.dbuf[3], (size_t)n * nsub * 16, cudaMemcpyDeviceToHost, s), "D2H params");
-    CK(cudaMemcpyAsync(bytes_out, t_ctx.dbuf[1], (size_t)n * dim, cudaMemcpyDeviceToHost, s), "D2H bytes");
-    CK(cudaStreamSynchronize(s), "sync");
-    return JV_OK;
+    return nvq_encode_impl(rows, nullptr, 0, n, dim, nsub, mean, learn, params_out, bytes_out);
+}
+
+int jv_nvq_encode_dataset(jv_dataset f32, int nsub, const float *mean, int learn, float *params_out, uint8_t *bytes_out)
+{
+    NEED_INIT();
+    if (!f32 || f32->d.kind != KIND_F32 || !mean || !params_out || !bytes_out || nsub <= 0 || nsub > f32->d.dim)
+        return fail(JV_ERR_INVALID, "nvq_encode_dataset: bad arguments");
+    return nvq_encode_impl(nullptr, f32->d.rows, f32->d.stride, f32->d.n, f32->d.dim, nsub, mean, learn, params_out, bytes_out);
 }
 
 // ------------------------------------------------------------------------------------------------ graph

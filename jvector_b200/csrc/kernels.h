@@ -52,10 +52,10 @@ cudaError_t launch_key_rebase(long long *keys_dev, long long count, long long id
 // per query: the k best of parts*k keys (the NCCL-gathered per-shard top-k), descending
 cudaError_t launch_topk_merge(const long long *keys_in_dev, int nq, int parts, int k, long long *keys_out_dev, cudaStream_t s);
 
-cudaError_t launch_bq_encode(const float *rows_dev, long long n, int dim, unsigned long long *words_dev, cudaStream_t s);
-cudaError_t launch_pq_encode(const DataDesc &pq, const float *rows_dev, long long n, uint8_t *codes_dev, cudaStream_t s);
+cudaError_t launch_bq_encode(const float *rows_dev, long long n, int dim, int row_stride, unsigned long long *words_dev, cudaStream_t s);
+cudaError_t launch_pq_encode(const DataDesc &pq, const float *rows_dev, long long n, int row_stride, uint8_t *codes_dev, cudaStream_t s);
 cudaError_t launch_pq_self_magnitudes(const DataDesc &pq, float *mag_dev, cudaStream_t s);
-cudaError_t launch_nvq_encode(const float *rows_dev, long long n, int dim, int nsub, const int *sizes_dev, const int *offsets_dev,
+cudaError_t launch_nvq_encode(const float *rows_dev, long long n, int row_stride, int nsub, const int *sizes_dev, const int *offsets_dev,
                               const float *mean_dev, int learn, float *params_dev, uint8_t *bytes_dev, int byte_stride, cudaStream_t s);
 
 // ---- search.cu ----

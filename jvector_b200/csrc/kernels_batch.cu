@@ -469,7 +469,7 @@ cudaError_t launch_topk_merge(const long long *keys_in_dev, int nq, int parts, i
 // bulk encoders
 // ------------------------------------------------------------------------------------------------
 // BinaryQuantization.encodeTo (BinaryQuantization.java:96-109): one warp per 32 dimensions via ballot
-__global__ void __launch_bounds__(256) bq_encode_kernel(const float *__restrict__ rows, long long n, int dim, unsigned *__restrict__ halves, int halves_per_row)
+__global__ void __launch_bounds__(256) bq_encode_kernel(const float *__restrict__ rows, long long n, int dim, int row_stride, unsigned *__restrict__ halves, int halves_per_row)
 {
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -478,18 +478,18 @@ __global__ void __launch_bounds__(256) bq_encode_kernel(const float *__restrict_
     const long long r = warp / halves_per_row;
     const int h = (int)(warp - r * halves_per_row);
     const int idx = h * 32 + lane;
-    const bool bit = idx < dim && rows[r * dim + idx] > 0.f;
+    const bool bit = idx < dim && rows[r * row_stride + idx] > 0.f;
     const unsigned b = __ballot_sync(FULL, bit);
     if (lane == 0) halves[warp] = b;
 }
 
-cudaError_t launch_bq_encode(const float *rows_dev, long long n, int dim, unsigned long long *words_dev, cudaStream_t s)
+cudaError_t launch_bq_encode(const float *rows_dev, long long n, int dim, int row_stride, unsigned long long *words_dev, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
     const int hp = 2 * ((dim + 63) / 64);
     const long long warps = n * hp;
     const long long blocks = (warps * 32 + 255) / 256;
-    bq_encode_kernel<<<(unsigned)blocks, 256, 0, s>>>(rows_dev, n, dim, reinterpret_cast<unsigned *>(words_dev), hp);
+    bq_encode_kernel<<<(unsigned)blocks, 256, 0, s>>>(rows_dev, n, dim, row_stride, reinterpret_cast<unsigned *>(words_dev), hp);
     g_launches++;
     return cudaGetLastError();
 }
@@ -497,7 +497,7 @@ cudaError_t launch_bq_encode(const float *rows_dev, long long n, int dim, unsign
 // ProductQuantization.encode (ProductQuantization.java:507-520): code[m] = argmin_c ||v[off_m..] - centroid_{m,c}||^2, first
 // minimum wins. One warp per (row, subspace); lanes stride over the k centroids, then an arg-min shuffle that prefers
 // the smaller index on ties.
-__global__ void __launch_bounds__(256) pq_encode_kernel(DataDesc pq, const float *__restrict__ rows, long long n, uint8_t *__restrict__ codes)
+__global__ void __launch_bounds__(256) pq_encode_kernel(DataDesc pq, const float *__restrict__ rows, long long n, int row_stride, uint8_t *__restrict__ codes)
 {
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(256) pq_encode_kernel(DataDesc pq, const float
     const long long r = warp / pq.M;
     const int m = (int)(warp - r * pq.M);
     const int sz = pq.sub_sizes[m], off = pq.sub_offsets[m];
-    const float *v = rows + r * pq.dim + off;
+    const float *v = rows + r * row_stride + off;
     const float *cb = pq.codebooks + (size_t)pq.k * off;
     float best = __int_as_float(0x7f800000);
     int bi = 0x7fffffff;
@@ -530,13 +530,13 @@ __global__ void __launch_bounds__(256) pq_encode_kernel(DataDesc pq, const float
     if (lane == 0) codes[r * pq.M + m] = (uint8_t)(bi == 0x7fffffff ? 0 : bi);
 }
 
-cudaError_t launch_pq_encode(const DataDesc &pq, const float *rows_dev, long long n, uint8_t *codes_dev, cudaStream_t s)
+cudaError_t launch_pq_encode(const DataDesc &pq, const float *rows_dev, long long n, int row_stride, uint8_t *codes_dev, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
     const long long warps = n * pq.M;
     const long long blocks = (warps * 32 + 255) / 256;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-    pq_encode_kernel<<<(unsigned)blocks, 256, 0, s>>>(pq, rows_dev, n, codes_dev);
+    pq_encode_kernel<<<(unsigned)blocks, 256, 0, s>>>(pq, rows_dev, n, row_stride, codes_dev);
     g_launches++;
     return cudaGetLastError();
 }
@@ -580,7 +580,7 @@ __device__ __forceinline__ float nvq_loss_warp(const float *v, const float *mean
     return group_sum<32>(s);
 }
 
-__global__ void __launch_bounds__(256) nvq_encode_kernel(const float *__restrict__ rows, long long n, int dim, int nsub, const int *__restrict__ sizes,
+__global__ void __launch_bounds__(256) nvq_encode_kernel(const float *__restrict__ rows, long long n, int row_stride, int nsub, const int *__restrict__ sizes,
                                                          const int *__restrict__ offsets, const float *__restrict__ mean, int learn,
                                                          float *__restrict__ params, uint8_t *__restrict__ bytes, int byte_stride)
 {
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(256) nvq_encode_kernel(const float *__restrict
     const long long r = warp / nsub;
     const int sv = (int)(warp - r * nsub);
     const int sz = sizes[sv], off = offsets[sv];
-    const float *v = rows + r * dim + off;
+    const float *v = rows + r * row_stride + off;
     const float *mu = mean + off;
     float minv = 3.402823466e+38f, maxv = -3.402823466e+38f;
     for (int i = lane; i < sz; i += 32) {
@@ -648,14 +648,14 @@ __global__ void __launch_bounds__(256) nvq_encode_kernel(const float *__restrict
     }
 }
 
-cudaError_t launch_nvq_encode(const float *rows_dev, long long n, int dim, int nsub, const int *sizes_dev, const int *offsets_dev,
+cudaError_t launch_nvq_encode(const float *rows_dev, long long n, int row_stride, int nsub, const int *sizes_dev, const int *offsets_dev,
                               const float *mean_dev, int learn, float *params_dev, uint8_t *bytes_dev, int byte_stride, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
     const long long warps = n * nsub;
     const long long blocks = (warps * 32 + 255) / 256;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-    nvq_encode_kernel<<<(unsigned)blocks, 256, 0, s>>>(rows_dev, n, dim, nsub, sizes_dev, offsets_dev, mean_dev, learn, params_dev, bytes_dev, byte_stride);
+    nvq_encode_kernel<<<(unsigned)blocks, 256, 0, s>>>(rows_dev, n, row_stride, nsub, sizes_dev, offsets_dev, mean_dev, learn, params_dev, bytes_dev, byte_stride);
     g_launches++;
     return cudaGetLastError();
 }

@@ -509,3 +509,19 @@ def test_device_builder_quality_vs_reference_builder(jv, oracle):
     assert rec["dev"] >= rec["ref"] - 0.03, rec
     assert rec["dev_visited"] <= 1.25 * rec["ref_visited"], rec
     vec.close()
+
+
+def test_encoders_from_resident_dataset(jv, oracle):
+    # the *_dataset encoders read rows already in HBM (padded row stride when dim % 4 != 0) and must equal the host-row forms
+    rng = np.random.default_rng(41)
+    for dim, M, nsub in ((100, 7, 3), (768, 96, 2)):
+        data = o.random_unit_vectors(rng, 150, dim)
+        vec = jv.F32Vectors(data)
+        assert np.array_equal(jv.bq_encode_all(vec), jv.bq_encode_all(data))
+        cb, sizes, offsets = o.train_pq_numpy(rng, data, M, 256, iters=1)
+        assert np.array_equal(jv.pq_encode_all(vec, cb, M, 256), jv.pq_encode_all(data, cb, M, 256))
+        mean = data.mean(0).astype(np.float32)
+        p1, b1 = jv.nvq_encode_all(vec, mean, nsub, True)
+        p2, b2 = jv.nvq_encode_all(data, mean, nsub, True)
+        assert np.array_equal(p1, p2) and np.array_equal(b1, b2)
+        vec.close()
