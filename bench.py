@@ -37,6 +37,10 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE graph_search_kernel launch, from the committed ncu --set full captures
+# (profiles/r1_ncu_search_c2.md, profiles/r1_ncu_search_c3.md); key = (workload, n, nq, rerankK, dist)
+NCU_TRAFFIC = {("c2", 1_000_000, 10_000, 100, "latent"): 94.728e9, ("c3", 1_000_000, 10_000, 100, "latent"): 6.035e9}
+
 LATENT = 32      # intrinsic dimensionality of the synthetic embedding model
 NOISE = 0.25     # isotropic noise relative to the per-coordinate signal
 
@@ -435,9 +439,13 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 
-    rank, world, local, td = dist_setup(args.gpus)
-    if args.impl == "reference" and rank != 0:
-        return 0  # the CPU arm runs on rank 0 alone
+    if args.impl == "reference":
+        # the CPU arm runs on rank 0 alone; the other ranks exit without joining any process group
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        rank, world, local, td = 0, 1, int(os.environ.get("LOCAL_RANK", "0")), None
+    else:
+        rank, world, local, td = dist_setup(args.gpus)
 
     import jvector_b200 as jv
     from jvector_b200 import _native as nat
@@ -594,7 +602,8 @@ def main():
                 "e2e": {"value": total_q / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(hq.nbytes), "d2h_bytes_per_step": int(hn.nbytes + hs.nbytes)},
                 "gpu_launches": int(launches), "clocks": clocks, "build_seconds": build_s,
                 "roofline": {"kernel": "graph_search_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_scored_vector": per_unit}})
+                             "traffic": NCU_TRAFFIC.get((args.workload, args.n, args.nq, rerankK, args.dist)), "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": algo_bytes / args.steps, "algorithmic_bytes_per_scored_vector": per_unit}})
 
     if args.sweep and rank == 0:
         sweep = []
