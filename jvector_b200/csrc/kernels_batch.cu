@@ -150,6 +150,58 @@ __device__ __forceinline__ void bitonic_sort_desc(long long *keys, int n_pow2)
     }
 }
 
+// Leaves the P largest of keys[0..n_pow2) sorted descending in keys[0..P) (P, n_pow2 powers of two, P <= n_pow2):
+// sort every P-chunk (alternating directions), then halve: element-wise max of neighbouring chunks is a bitonic sequence
+// holding the best P of the pair; re-sort it with one bitonic merge. ~ (log^2 P + 2 log P) / 2 full-width stages instead of
+// log^2 n / 2 — the thresholds only need the top max(j, k) of the sample / candidate buffer, not a full sort.
+__device__ __forceinline__ void bitonic_top_desc(long long *keys, int n_pow2, int P)
+{
+    if (P >= n_pow2) { bitonic_sort_desc(keys, n_pow2); return; }
+    // phase 1: bitonic sort of each P-chunk; chunk c descending when c is even, ascending when odd
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const long long a = keys[i], b = keys[ixj];
+                    const bool desc = (i & k) == 0;  // at k == P this alternates per chunk: even chunks descending, odd ascending
+                    if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // phase 2: repeatedly merge chunk pairs (desc, asc) -> best P of the pair, compacted to the front
+    for (int len = n_pow2; len > P; len >>= 1) {
+        const int chunks = len / P;  // even
+        // max(desc chunk 2c, asc chunk 2c+1) element-wise is bitonic and holds the best P of the 2P
+        for (int i = threadIdx.x; i < (chunks >> 1) * P; i += blockDim.x) {
+            const int c = i / P, o = i - c * P;
+            const long long a = keys[(2 * c) * P + o], b = keys[(2 * c + 1) * P + o];
+            keys[(2 * c) * P + o] = a > b ? a : b;
+        }
+        __syncthreads();
+        // compact surviving chunks to the front: chunk 2c -> chunk c (c > 0 only; in-place copy is ordered by a barrier)
+        for (int c = 1; c < (chunks >> 1); c++) {
+            for (int o = threadIdx.x; o < P; o += blockDim.x) keys[c * P + o] = keys[(2 * c) * P + o];
+            __syncthreads();
+        }
+        // bitonic merge of every surviving chunk; alternate directions again unless it is the last one
+        const int surv = chunks >> 1;
+        for (int j = P >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < surv * P; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const long long a = keys[i], b = keys[ixj];
+                    const bool desc = surv == 1 || (((i / P) & 1) == 0);
+                    if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) topk_sample_ids_kernel(int32_t *ids, int S, long long n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,7 +222,11 @@ __global__ void __launch_bounds__(256) topk_threshold_kernel(const float *__rest
     for (int i = threadIdx.x; i < S_pow2; i += blockDim.x)
         skeys[i] = i < S ? topk_key(sample_scores[(size_t)q * S + i], sample_ids[i]) : KEY_MIN;
     __syncthreads();
-    bitonic_sort_desc(skeys, S_pow2);
+    {
+        int P = 1;
+        while (P < k) P <<= 1;
+        bitonic_top_desc(skeys, S_pow2, P);  // j_aggr <= k: both thresholds live in the top k of the sample
+    }
     if (threadIdx.x == 0) {
         const long long safe = (!whole && k <= S) ? skeys[k - 1] : KEY_MIN;
         thr_safe[q] = safe;
@@ -332,7 +388,11 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const long long *__res
     const int m = min(c, cap);
     for (int i = threadIdx.x; i < cap_pow2; i += blockDim.x) skeys[i] = i < m ? buf[(size_t)q * cap + i] : KEY_MIN;
     __syncthreads();
-    bitonic_sort_desc(skeys, cap_pow2);
+    {
+        int P = 1;
+        while (P < k) P <<= 1;
+        bitonic_top_desc(skeys, cap_pow2, P);  // only the best k are emitted (or used as the tightened threshold)
+    }
     const long long need = n_rows < (long long)k ? n_rows : (long long)k;
     if (c <= cap && (c >= need || t == thr_safe[q])) {
         // exact: every key >= thr was captured and there are at least k of them (or the threshold was the guaranteed one)

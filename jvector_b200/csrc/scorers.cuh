@@ -91,28 +91,53 @@ __device__ inline void prepare_blob(const DataDesc &d, int metric, const float *
         float qn = block_sum(acc, red);
         if (tid == 0) { blob[d.stride] = qn; blob[d.stride + 1] = 0.f; blob[d.stride + 2] = 0.f; blob[d.stride + 3] = 0.f; }
     } else if (d.kind == KIND_PQ) {
-        // LUT[m*k + c] = metric(centroid_{m,c}, q'[off_m..]) — PQDecoder.java:48-53, DefaultVectorUtilSupport.java:351-365
+        // LUT[m*k + c] = metric(centroid_{m,c}, q'[off_m..]) — PQDecoder.java:48-53, DefaultVectorUtilSupport.java:351-365.
+        // One warp per sub-space m (its sizes / offset / query fragment are warp-uniform), lanes stride over the k centroids:
+        // every lane streams one contiguous centroid, 128-bit loads when the sub-vector allows it. Accumulation order over the
+        // sub-vector is sequential (j = 0..sz-1) for every entry.
         const int total = d.M * d.k;
-        for (int e = tid; e < total; e += nt) {
-            const int m = e / d.k, c = e - m * d.k;
+        const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+        for (int m = warp; m < d.M; m += nw) {
             const int sz = d.sub_sizes[m], off = d.sub_offsets[m];
-            const float *cen = d.codebooks + (size_t)d.k * off + (size_t)c * sz;
-            float s = 0.f;
-            if (metric == JV_METRIC_EUCLIDEAN) {
-                for (int j = 0; j < sz; j++) {
+            const float *cb = d.codebooks + (size_t)d.k * off;
+            if (sz == 8 && ((off & 3) == 0)) {
+                float qv[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
                     float qq = q[off + j];
                     if (d.centroid) qq = __fsub_rn(qq, d.centroid[off + j]);
-                    float df = __fsub_rn(cen[j], qq);
-                    s = fmaf(df, df, s);
+                    qv[j] = qq;
+                }
+#pragma unroll 4
+                for (int c = lane; c < d.k; c += 32) {
+                    const float4 a = __ldg(reinterpret_cast<const float4 *>(cb + (size_t)c * 8));
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(cb + (size_t)c * 8) + 1);
+                    const float cen[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (metric == JV_METRIC_EUCLIDEAN) {
+                            const float df = __fsub_rn(cen[j], qv[j]);
+                            s = fmaf(df, df, s);
+                        } else s = fmaf(cen[j], qv[j], s);
+                    }
+                    blob[m * d.k + c] = s;
                 }
             } else {
-                for (int j = 0; j < sz; j++) {
-                    float qq = q[off + j];
-                    if (d.centroid) qq = __fsub_rn(qq, d.centroid[off + j]);
-                    s = fmaf(cen[j], qq, s);
+                for (int c = lane; c < d.k; c += 32) {
+                    const float *cen = cb + (size_t)c * sz;
+                    float s = 0.f;
+                    for (int j = 0; j < sz; j++) {
+                        float qq = q[off + j];
+                        if (d.centroid) qq = __fsub_rn(qq, d.centroid[off + j]);
+                        if (metric == JV_METRIC_EUCLIDEAN) {
+                            const float df = __fsub_rn(cen[j], qq);
+                            s = fmaf(df, df, s);
+                        } else s = fmaf(cen[j], qq, s);
+                    }
+                    blob[m * d.k + c] = s;
                 }
             }
-            blob[e] = s;
         }
         float acc = 0.f;  // bMagnitude = <q', q'> (PQDecoder.java:119)
         for (int i = tid; i < d.dim; i += nt) {

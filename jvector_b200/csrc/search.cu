@@ -16,6 +16,7 @@
 // Every hop is: read one adjacency row -> filter through visited -> score the survivors with the row scorers of
 // scorers.cuh (one lane group per candidate) -> parallel rank-merge into the list.
 #include <limits.h>
+#include <stdio.h>
 
 #include "kernels.h"
 
@@ -41,6 +42,7 @@ struct SearchParams {
     uint8_t *overflow;
     const int32_t *query_index;
     int blobA_floats, blobR_floats;
+    unsigned long long *dbg;  // JV_SEARCH_PROFILE builds only: per-phase cycle totals
 };
 
 __device__ __forceinline__ bool visited_insert(int32_t *t, unsigned mask, int shift, int32_t v)
@@ -92,6 +94,15 @@ __device__ __forceinline__ void bitonic_sort_desc_block(long long *keys, int n_p
 #endif
 constexpr int SEARCH_THREADS = JV_SEARCH_THREADS;
 
+// optional phase timers (tools/: build with JV_NVCC_EXTRA=-DJV_SEARCH_PROFILE); compiled out of the product build
+#ifdef JV_SEARCH_PROFILE
+#define JV_T(var) const long long var = clock64()
+#define JV_ACC(slot, a, b) do { if (threadIdx.x == 0) dbg_local[slot] += (unsigned long long)((b) - (a)); } while (0)
+#else
+#define JV_T(var)
+#define JV_ACC(slot, a, b)
+#endif
+
 template <int KIND, int METRIC>
 __global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_kernel(SearchParams P)
 {
@@ -124,7 +135,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_k
         if (wq >= P.nq) break;
         const int qi = P.query_index ? P.query_index[wq] : wq;
         const float *q = P.queries + (size_t)qi * P.query_stride;
-
+#ifdef JV_SEARCH_PROFILE
+        unsigned long long dbg_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+        JV_T(t_q0);
         prepare_blob(P.approx, P.metric, q, blobA, red);
         if (P.has_rerank) prepare_blob(P.rerank, P.metric, q, blobR, red);
         {
@@ -133,6 +147,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_k
             for (int i = tid; i < (P.visited_cap >> 2); i += SEARCH_THREADS) t4[i] = m1;
         }
         __syncthreads();
+        JV_T(t_q1);
+        JV_ACC(0, t_q0, t_q1);
 
         long long *cur = keys0, *nxt = keys1;
         uint8_t *fcur = flags0, *fnxt = flags1;
@@ -161,6 +177,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_k
             for (;;) {
                 const int p = s_posv[sel];
                 if (p == INT_MAX) break;  // stopSearch: every node of the best-K window is expanded
+                JV_T(t_i0);
                 const int node = key_node(cur[p]);
                 if (tid == 0) { fcur[p] = 1; s_posv[sel ^ 1] = INT_MAX; }
                 expanded++;
@@ -203,6 +220,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_k
                     }
                 }
                 __syncthreads();
+                JV_T(t_i1);
+                JV_ACC(1, t_i0, t_i1);
                 const int n = s_n;
                 table_cnt += n;
                 if (table_cnt * 2 > P.visited_cap) { failed = true; break; }
@@ -227,37 +246,52 @@ __global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_k
                     }
                 }
                 __syncthreads();
+                JV_T(t_i2);
+                JV_ACC(2, t_i1, t_i2);
                 visited += n;
                 // rank-merge (old list is sorted; candidates are few): every element computes its slot directly and the
                 // first unexpanded slot of the next window falls out of the same pass
                 const int newsize = min(L, size + n);
                 const int lim = min(newsize, K);
                 int mypos = INT_MAX;
-                for (int i = tid; i < size; i += SEARCH_THREADS) {
-                    const long long k = cur[i];
-                    int c = 0;
-                    for (int j = 0; j < n; j++) c += (cand_keys[j] > k);
-                    const int np = i + c;
-                    if (np < L) {
-                        const uint8_t fl = fcur[i];
-                        nxt[np] = k;
-                        fnxt[np] = fl;
-                        if (!fl && np < lim) mypos = min(mypos, np);
-                    }
-                }
-                for (int j = tid; j < n; j += SEARCH_THREADS) {
-                    const long long k = cand_keys[j];
-                    int c = count_greater_desc(cur, size, k);
-                    for (int jj = 0; jj < n; jj++) c += (cand_keys[jj] > k);
-                    if (c < L) {
-                        nxt[c] = k;
-                        fnxt[c] = 0;
-                        if (c < lim) mypos = min(mypos, c);
+                // one work item per thread: items [0, size) are old entries, [size, size + n) the new candidates, so the
+                // two kinds run on different warps instead of back to back on warp 0
+                for (int it = tid; it < size + n; it += SEARCH_THREADS) {
+                    if (it < size) {
+                        const long long k = cur[it];
+                        int c = 0;
+#pragma unroll 8
+                        for (int j = 0; j < n; j++) c += (cand_keys[j] > k);
+                        const int np = it + c;
+                        if (np < L) {
+                            const uint8_t fl = fcur[it];
+                            nxt[np] = k;
+                            fnxt[np] = fl;
+                            if (!fl && np < lim) mypos = min(mypos, np);
+                        }
+                    } else {
+                        const long long k = cand_keys[it - size];
+                        int c = count_greater_desc(cur, size, k);
+#pragma unroll 8
+                        for (int jj = 0; jj < n; jj++) c += (cand_keys[jj] > k);
+                        if (c < L) {
+                            nxt[c] = k;
+                            fnxt[c] = 0;
+                            if (c < lim) mypos = min(mypos, c);
+                            // a new candidate that lands at the very front is the likeliest next expansion: start pulling
+                            // its adjacency row towards L2 now (128 B; reads only)
+                            if (c < 2 && lvl == 0) prefetch_l2(P.g.adj0 + (size_t)key_node(k) * degree);
+                        }
                     }
                 }
                 if (mypos != INT_MAX) atomicMin(&s_posv[sel ^ 1], mypos);
                 if (tid == 0) s_n = 0;
                 __syncthreads();
+                JV_T(t_i3);
+                JV_ACC(3, t_i2, t_i3);
+#ifdef JV_SEARCH_PROFILE
+                if (tid == 0) { dbg_local[5] += 1; dbg_local[6] += (unsigned long long)n; }
+#endif
                 { long long *t = cur; cur = nxt; nxt = t; }
                 { uint8_t *t = fcur; fcur = fnxt; fnxt = t; }
                 size = newsize;
@@ -266,6 +300,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_k
             __syncthreads();
         }
 
+        JV_T(t_r0);
         int32_t *no = P.nodes_out + (size_t)qi * P.topK;
         float *so = P.scores_out + (size_t)qi * P.topK;
         unsigned reranked = 0;
@@ -278,12 +313,35 @@ __global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_k
                 // NodeQueue.rerank (NodeQueue.java:168-230) with rerankFloor = 0: exact-score every survivor, keep topK
                 constexpr int NGR = SEARCH_THREADS / 32;
                 const int wgroup = tid >> 5, wlane = tid & 31;
-                for (int i = wgroup; i < size; i += NGR) {
-                    const int32_t f = key_node(cur[i]);
-                    float sc;
-                    if (P.rerank.kind == KIND_F32) sc = score_row<KIND_F32, METRIC>(P.rerank, blobR, f, wlane);
-                    else sc = score_row<KIND_NVQ, METRIC>(P.rerank, blobR, f, wlane);
-                    if (wlane == 0) nxt[i] = topk_key(sc, f);
+                if (KIND == KIND_PQ || KIND == KIND_BQ) {
+                    // the approximate walk left HBM idle: pull every survivor's exact row towards L2 before the rescoring loop
+                    const int lines = P.rerank.kind == KIND_F32 ? (P.rerank.stride * 4 + 127) / 128 : (P.rerank.byte_stride + 127) / 128;
+                    for (int t = tid; t < size * lines; t += SEARCH_THREADS) {
+                        const int i = t / lines, l = t - i * lines;
+                        const int32_t f = key_node(cur[i]);
+                        const char *a = P.rerank.kind == KIND_F32 ? reinterpret_cast<const char *>(P.rerank.rows + (size_t)f * P.rerank.stride)
+                                                                  : reinterpret_cast<const char *>(P.rerank.bytes + (size_t)f * P.rerank.byte_stride);
+                        prefetch_l2(a + (size_t)l * 128);
+                    }
+                }
+                if (P.rerank.kind == KIND_F32) {
+                    for (int i = wgroup; i < size; i += 2 * NGR) {
+                        const int32_t fa = key_node(cur[i]);
+                        const bool two = i + NGR < size;
+                        const int32_t fb = two ? key_node(cur[i + NGR]) : fa;
+                        float sa, sb;
+                        score_f32_pair<METRIC>(P.rerank, blobR, fa, fb, wlane, sa, sb);
+                        if (wlane == 0) {
+                            nxt[i] = topk_key(sa, fa);
+                            if (two) nxt[i + NGR] = topk_key(sb, fb);
+                        }
+                    }
+                } else {
+                    for (int i = wgroup; i < size; i += NGR) {
+                        const int32_t f = key_node(cur[i]);
+                        const float sc = score_row<KIND_NVQ, METRIC>(P.rerank, blobR, f, wlane);
+                        if (wlane == 0) nxt[i] = topk_key(sc, f);
+                    }
                 }
                 for (int i = size + tid; i < P.list_pow2; i += SEARCH_THREADS) nxt[i] = KEY_MIN;
                 __syncthreads();
@@ -307,6 +365,15 @@ __global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_k
             }
         }
         __syncthreads();
+#ifdef JV_SEARCH_PROFILE
+        {
+            JV_T(t_r1);
+            JV_ACC(4, t_r0, t_r1);
+            JV_ACC(7, t_q0, t_r1);
+            if (tid == 0 && P.dbg)
+                for (int i = 0; i < 8; i++) atomicAdd(&P.dbg[i], dbg_local[i]);
+        }
+#endif
     }
 }
 
@@ -417,6 +484,13 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
     P.query_index = query_index_dev;
     P.blobA_floats = blob_floats(approx);
     P.blobR_floats = rerank ? blob_floats(*rerank) : 0;
+    P.dbg = nullptr;
+#ifdef JV_SEARCH_PROFILE
+    static unsigned long long *dbg_dev = nullptr;
+    if (!dbg_dev) cudaMalloc(&dbg_dev, 8 * sizeof(unsigned long long));
+    cudaMemsetAsync(dbg_dev, 0, 8 * sizeof(unsigned long long), s);
+    P.dbg = dbg_dev;
+#endif
     cudaError_t e = cudaMemsetAsync(work_counter_dev, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
 #define CALL(K, M)                                                                                                              \
@@ -428,6 +502,16 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
 #undef CALL
     if (e != cudaSuccess) return e;
     g_launches++;
+#ifdef JV_SEARCH_PROFILE
+    {
+        unsigned long long h[8];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, P.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        const double it = h[5] ? (double)h[5] : 1.0, nqd = (double)nq;
+        fprintf(stderr, "[search profile] kind=%d nq=%d iterations/q=%.1f scored/it=%.1f cycles/it: gather=%.0f score=%.0f merge=%.0f | per query: prepare+clear=%.0f rerank+out=%.0f total=%.0f\n",
+                approx.kind, nq, it / nqd, (double)h[6] / it, (double)h[1] / it, (double)h[2] / it, (double)h[3] / it, (double)h[0] / nqd, (double)h[4] / nqd, (double)h[7] / nqd);
+    }
+#endif
     return cudaGetLastError();
 }
 
