@@ -263,6 +263,57 @@ __global__ void __launch_bounds__(BF_THREADS) topk_filter_kernel(DataDesc d, con
     }
 }
 
+// Hamming distance of MAXW 64-bit words by a Harley-Seal carry-save adder tree over the 32-bit halves: 16 XORed words are
+// compressed into ones/twos/fours/eights/sixteens bit-planes with 15 CSAs (2 LOP3 each) and ONE popcount, instead of 16
+// popcounts. POPC issues at a quarter of the LOP3 rate on this part, so the pair loop moves from the popcount pipe to the
+// ALU pipe. Exact integer arithmetic: the result equals sum(popcll(r[w] ^ q[w])).
+__device__ __forceinline__ void csa32(unsigned &h, unsigned &l, unsigned a, unsigned b, unsigned c)
+{
+    const unsigned u = a ^ b;
+    h = (a & b) | (u & c);
+    l = u ^ c;
+}
+
+template <int MAXW>
+__device__ __forceinline__ int hamming_csa(const unsigned long long (&r)[MAXW], const unsigned long long *q)
+{
+    static_assert(MAXW % 8 == 0, "16 32-bit halves per block");
+    unsigned ones = 0, twos = 0, fours = 0, eights = 0;
+    int total16 = 0;
+#pragma unroll
+    for (int b = 0; b < MAXW / 8; b++) {
+        unsigned d[16];
+        const ulonglong2 *q2 = reinterpret_cast<const ulonglong2 *>(q) + b * 4;  // 128-bit shared loads: half the LDS issue slots
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const ulonglong2 qq = q2[i];
+            const unsigned long long x = r[b * 8 + 2 * i] ^ qq.x, y = r[b * 8 + 2 * i + 1] ^ qq.y;
+            d[4 * i] = (unsigned)x;
+            d[4 * i + 1] = (unsigned)(x >> 32);
+            d[4 * i + 2] = (unsigned)y;
+            d[4 * i + 3] = (unsigned)(y >> 32);
+        }
+        unsigned twosA, twosB, foursA, foursB, eightsA, eightsB, sixteens;
+        csa32(twosA, ones, ones, d[0], d[1]);
+        csa32(twosB, ones, ones, d[2], d[3]);
+        csa32(foursA, twos, twos, twosA, twosB);
+        csa32(twosA, ones, ones, d[4], d[5]);
+        csa32(twosB, ones, ones, d[6], d[7]);
+        csa32(foursB, twos, twos, twosA, twosB);
+        csa32(eightsA, fours, fours, foursA, foursB);
+        csa32(twosA, ones, ones, d[8], d[9]);
+        csa32(twosB, ones, ones, d[10], d[11]);
+        csa32(foursA, twos, twos, twosA, twosB);
+        csa32(twosA, ones, ones, d[12], d[13]);
+        csa32(twosB, ones, ones, d[14], d[15]);
+        csa32(foursB, twos, twos, twosA, twosB);
+        csa32(eightsB, fours, fours, foursA, foursB);
+        csa32(sixteens, eights, eights, eightsA, eightsB);
+        total16 += __popc(sixteens);
+    }
+    return 16 * total16 + 8 * __popc(eights) + 4 * __popc(fours) + 2 * __popc(twos) + __popc(ones);
+}
+
 // ---- BQ specialisation: Hamming brute force is popcount-bound, not HBM-bound: one ROW per thread, its
 // words held in registers, the query bit-packs staged in shared memory and read by broadcast; no shuffles. A pair costs
 // W x (LDS.64 broadcast / 32 rows + XOR + POPC + ADD). The exact key is formed only for pairs under the per-query
@@ -275,7 +326,7 @@ __global__ void __launch_bounds__(BQF_THREADS) topk_filter_bq_kernel(DataDesc d,
                                                                      int *__restrict__ cnt, int cap, const int *__restrict__ qlist)
 {
     constexpr int BQF_QCHUNK = MAXW <= 16 ? 256 : 128;  // queries staged per pass (<= 32 KB of bit packs)
-    __shared__ unsigned long long qs[BQF_QCHUNK * MAXW];
+    __shared__ __align__(16) unsigned long long qs[BQF_QCHUNK * MAXW];
     __shared__ int hdmax[BQF_QCHUNK];
     __shared__ int sq[BQF_QCHUNK];
     __shared__ long long sthr[BQF_QCHUNK];
@@ -314,9 +365,13 @@ __global__ void __launch_bounds__(BQF_THREADS) topk_filter_bq_kernel(DataDesc d,
             __syncthreads();
             if (live) {
                 for (int q = 0; q < qc; q++) {
-                    int hd = 0;
+                    int hd;
+                    if constexpr (MAXW >= 8) hd = hamming_csa<MAXW>(rw, qs + q * MAXW);
+                    else {
+                        hd = 0;
 #pragma unroll
-                    for (int w = 0; w < MAXW; w++) hd += __popcll(rw[w] ^ qs[q * MAXW + w]);
+                        for (int w = 0; w < MAXW; w++) hd += __popcll(rw[w] ^ qs[q * MAXW + w]);
+                    }
                     if (hd <= hdmax[q]) {
                         const long long key = topk_key(bq_score_from_hd(hd, d.dim), (int32_t)r);
                         if (key >= sthr[q]) {
