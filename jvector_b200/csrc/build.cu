@@ -8,13 +8,15 @@
 // stands, (2) a Vamana robust prune of the beam, (3) back-links into the chosen neighbours, re-pruning a neighbour
 // whose list exceeds overflow * M. Here a BATCH of nodes plays the role of the concurrently inserting threads:
 //   search  : graph_search_kernel (search.cu) over the batch, one CTA per inserted node, beam = efConstruction
-//   prune   : prune_kernel, one CTA per node: scores -> sort by the reference key -> retainDiverse with the selected
-//             rows cached in shared memory (the candidate x selected score matrix of SURVEY §3.2 seam v)
+//   prune   : prune_kernel, one CTA per node: scores -> sort by the reference key -> retainDiverse restated over a running
+//             max-similarity per candidate, updated in bulk whenever a neighbour is selected (SURVEY §3.2 seam v)
 //   backlink: append u to adj[v] for every chosen v (atomic slot), then prune_kernel again over every v whose list
 //             passed overflow * M
 // Batches grow geometrically (x1.5) up to max_batch so early nodes see a connected graph. Neighbour lists in the
 // reference are concurrency-order dependent, so parity is on scores and on the recall of the resulting graph
 // (SURVEY §8d C5), not on identical adjacency.
+#include <limits.h>
+
 #include <vector>
 
 #include "kernels.h"
@@ -91,21 +93,33 @@ __device__ __forceinline__ float pair_rows(const float4 *__restrict__ c, const f
     return score_map(METRIC, s);
 }
 
+// retainDiverse (VamanaDiversityProvider.java:45-95), restated so that the pair scores can be produced in bulk:
+//   isDiverse(c) at alpha  <=>  max over the selected s of sim(c, s)  <=  score(c) * alpha.
+// Keep M[c] = that running maximum. Selecting a candidate s updates M[c] for every still-eligible c in parallel (one warp
+// per candidate, the new row cached in shared memory); the sequential part of the reference loop shrinks to "find the next
+// c at or after the cursor with M[c] <= score(c) * alpha", a flag scan. A candidate whose M[c] already exceeds
+// score(c) * alpha_max can never be selected in any pass (M only grows) and is dropped from further updates. The selection
+// sequence — and therefore the neighbour list — is exactly the reference loop's, including the alpha = 1.0, 1.2 passes.
 template <int METRIC>
 __global__ void __launch_bounds__(PRUNE_THREADS) prune_kernel(PruneParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *blob = reinterpret_cast<float *>(smem_raw);                  // stride + 4
-    long long *keys = reinterpret_cast<long long *>(blob + P.d.stride + 4);  // PRUNE_MAXC
-    int32_t *sel_ids = reinterpret_cast<int32_t *>(keys + PRUNE_MAXC);      // degree (<= 128)
-    uint8_t *selected = reinterpret_cast<uint8_t *>(sel_ids + 128);         // PRUNE_MAXC
-    float *sel_rows = reinterpret_cast<float *>(selected + PRUNE_MAXC);     // degree * stride (when sel_in_smem)
+    float *blob = reinterpret_cast<float *>(smem_raw);                       // stride + 4
+    float *newrow = blob + P.d.stride + 4;                                   // stride: the most recently selected row
+    long long *keys = reinterpret_cast<long long *>(newrow + P.d.stride);    // PRUNE_MAXC
+    float *maxsim = reinterpret_cast<float *>(keys + PRUNE_MAXC);            // PRUNE_MAXC
+    int32_t *sel_ids = reinterpret_cast<int32_t *>(maxsim + PRUNE_MAXC);     // 128
+    uint8_t *state = reinterpret_cast<uint8_t *>(sel_ids + 128);             // PRUNE_MAXC: 0 eligible, 1 selected, 2 dropped
     __shared__ float red[36];
+    __shared__ int s_next;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = PRUNE_THREADS / 32;
     const int total = P.count_ptr ? *P.count_ptr : P.count;
     const int n4 = P.d.stride >> 2;
+    // the last alpha the reference loop reaches: 1.0, 1.2, ... while <= alpha + 1e-6
+    float alpha_max = 1.0f;
+    for (float a = 1.0f; a <= P.alpha + 1e-6f; a += 0.2f) alpha_max = a;
 
     for (int it = blockIdx.x; it < total; it += gridDim.x) {
         const int v = P.mode == 0 ? P.node_base + it : P.list[it];
@@ -120,26 +134,28 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_kernel(PruneParams P)
         }
         nc = min(nc, PRUNE_MAXC);
         prepare_blob(P.d, P.metric, P.d.rows + (size_t)v * P.d.stride, blob, red);
-        // exact scores of the candidates against v, as sortable keys
-        for (int i = warp; i < PRUNE_MAXC; i += NW) {
-            long long key = KEY_MIN;
-            if (i < nc) {
-                const int32_t c = cand[i];
-                if (c >= 0 && c != v) {
-                    const float sc = score_f32<METRIC>(P.d, blob, c, lane);
-                    key = topk_key(sc, c);
-                }
+        // exact scores of the candidates against v, as sortable keys (two rows per warp at a time)
+        for (int i = warp; i < PRUNE_MAXC; i += 2 * NW) {
+            const int i2 = i + NW;
+            const int32_t ca = i < nc ? cand[i] : -1, cb = i2 < nc ? cand[i2] : -1;
+            const bool va = ca >= 0 && ca != v, vb = cb >= 0 && cb != v;
+            long long ka = KEY_MIN, kb = KEY_MIN;
+            if (va || vb) {
+                float sa, sb;
+                score_f32_pair<METRIC>(P.d, blob, va ? ca : cb, vb ? cb : ca, lane, sa, sb);
+                if (va) ka = topk_key(sa, ca);
+                if (vb) kb = topk_key(sb, cb);
             }
-            if (lane == 0) keys[i] = key;
+            if (lane == 0) {
+                keys[i] = ka;
+                if (i2 < PRUNE_MAXC) keys[i2] = kb;
+            }
         }
         __syncthreads();
         bitonic_sort_desc_prune(keys, PRUNE_MAXC);
-        // number of valid, distinct candidates (duplicates are adjacent after the sort)
-        for (int i = tid; i < PRUNE_MAXC; i += PRUNE_THREADS) selected[i] = 0;
-        __syncthreads();
-        int nvalid = 0;
+        // valid keys form a prefix (KEY_MIN sorts last); duplicates are adjacent after the sort and are dropped
+        int nvalid;
         {
-            // valid keys form a prefix (KEY_MIN sorts last)
             int lo = 0, hi = PRUNE_MAXC;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
@@ -148,36 +164,45 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_kernel(PruneParams P)
             }
             nvalid = lo;
         }
-        // retainDiverse (VamanaDiversityProvider.java:45-79), diverseBefore = 0
+        for (int i = tid; i < PRUNE_MAXC; i += PRUNE_THREADS) {
+            maxsim[i] = -3.0e38f;
+            state[i] = (i < nvalid && !(i > 0 && keys[i - 1] == keys[i])) ? 0 : 2;
+        }
+        __syncthreads();
+
         int nsel = 0;
         float currentAlpha = 1.0f;
         while (currentAlpha <= P.alpha + 1e-6f && nsel < P.degree) {
-            for (int i = 0; i < nvalid && nsel < P.degree; i++) {
-                if (selected[i]) continue;
-                const long long key = keys[i];
-                if (i > 0 && keys[i - 1] == key) continue;  // duplicate candidate
-                const int32_t c = key_node(key);
-                const float cscore = key_score(key);
+            int cursor = 0;
+            while (nsel < P.degree) {
+                // next eligible candidate at or after the cursor that is diverse at this alpha
+                if (tid == 0) s_next = INT_MAX;
+                __syncthreads();
+                for (int i = cursor + tid; i < nvalid; i += PRUNE_THREADS)
+                    if (state[i] == 0 && !(maxsim[i] > __fmul_rn(key_score(keys[i]), currentAlpha))) { atomicMin(&s_next, i); break; }
+                __syncthreads();
+                const int pick = s_next;
+                if (pick == INT_MAX) break;
+                const int32_t c = key_node(keys[pick]);
                 const float4 *crow = reinterpret_cast<const float4 *>(P.d.rows + (size_t)c * P.d.stride);
-                // isDiverse: no selected neighbour is closer to the candidate than the base node is (x alpha)
-                int bad = 0;
-                const float limit = __fmul_rn(cscore, currentAlpha);
-                for (int j = warp; j < nsel; j += NW) {
-                    const float4 *srow = P.sel_in_smem ? reinterpret_cast<const float4 *>(sel_rows + (size_t)j * P.d.stride)
-                                                       : reinterpret_cast<const float4 *>(P.d.rows + (size_t)sel_ids[j] * P.d.stride);
-                    const float ps = pair_rows<METRIC>(crow, srow, n4, lane);
-                    if (ps > limit) bad = 1;
-                }
-                bad = __syncthreads_or(bad);
-                if (!bad) {
-                    if (tid == 0) { selected[i] = 1; sel_ids[nsel] = c; }
-                    if (P.sel_in_smem) {
-                        float4 *dst = reinterpret_cast<float4 *>(sel_rows + (size_t)nsel * P.d.stride);
-                        for (int t = tid; t < n4; t += PRUNE_THREADS) dst[t] = __ldg(crow + t);
+                if (tid == 0) { state[pick] = 1; sel_ids[nsel] = c; }
+                for (int t = tid; t < n4; t += PRUNE_THREADS) reinterpret_cast<float4 *>(newrow)[t] = __ldg(crow + t);
+                nsel++;
+                cursor = pick + 1;
+                __syncthreads();
+                if (nsel >= P.degree) break;
+                // fold the new neighbour into every still-eligible candidate's running maximum
+                for (int i = warp; i < nvalid; i += NW) {
+                    if (state[i] != 0) continue;
+                    const float4 *row = reinterpret_cast<const float4 *>(P.d.rows + (size_t)key_node(keys[i]) * P.d.stride);
+                    const float ps = pair_rows<METRIC>(row, reinterpret_cast<const float4 *>(newrow), n4, lane);
+                    if (lane == 0) {
+                        const float m = fmaxf(maxsim[i], ps);
+                        maxsim[i] = m;
+                        if (m > __fmul_rn(key_score(keys[i]), alpha_max)) state[i] = 2;  // can never become diverse
                     }
-                    nsel++;
-                    __syncthreads();
                 }
+                __syncthreads();
             }
             currentAlpha += 0.2f;
         }
@@ -187,7 +212,7 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_kernel(PruneParams P)
             int w = 0;
             int32_t *row = P.adj + (size_t)v * P.row_cap;
             for (int i = 0; i < nvalid; i++)
-                if (selected[i]) row[w++] = key_node(keys[i]);
+                if (state[i] == 1) row[w++] = key_node(keys[i]);
             for (int i = w; i < P.row_cap; i++) row[i] = -1;
             P.deg[v] = w;
             if (P.mode == 1 && P.mark) P.mark[v] = 0;
@@ -233,8 +258,9 @@ __global__ void __launch_bounds__(256) compact_adj_kernel(const int32_t *adj, co
 
 static size_t prune_smem_bytes(const DataDesc &d, int degree, bool sel_in_smem)
 {
-    size_t b = (size_t)(d.stride + 4) * 4 + (size_t)PRUNE_MAXC * 8 + 128 * 4 + PRUNE_MAXC;
-    if (sel_in_smem) b += (size_t)degree * d.stride * 4;
+    (void)degree;
+    (void)sel_in_smem;
+    size_t b = (size_t)(d.stride + 4) * 4 + (size_t)d.stride * 4 + (size_t)PRUNE_MAXC * 8 + (size_t)PRUNE_MAXC * 4 + 128 * 4 + PRUNE_MAXC;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -285,7 +311,7 @@ cudaError_t build_graph_flat(const DataDesc &d, int metric, const BuildParams &b
     BuildStats st = {0, 0, 0, 0};
     bool sel_in_smem = prune_smem_bytes(d, degree, true) <= 200 * 1024;
     const size_t psmem = prune_smem_bytes(d, degree, sel_in_smem);
-    const int prune_grid = sm_count * (psmem > 100 * 1024 ? 1 : 2);
+    const int prune_grid = sm_count * 5;  // ~10 KB of shared memory per CTA: register-limited residency
 
     JV_TRY(cudaMalloc(&adj, (size_t)n * row_cap * sizeof(int32_t)));
     JV_TRY(cudaMemsetAsync(adj, 0xff, (size_t)n * row_cap * sizeof(int32_t), s));
