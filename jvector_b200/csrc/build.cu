@@ -221,6 +221,201 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_kernel(PruneParams P)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// prune_gram_kernel: the same retainDiverse, with the candidate x candidate similarity matrix produced up front by a
+// shared-memory tiled Gram product on the CUDA cores (SURVEY §3.2 seam v: "compute the full candidate x candidate matrix
+// and replay the sequential selection"). Rows are read ONCE (nc x 3 KB from L2) instead of once per selected neighbour;
+// the selection loop then only touches shared memory. TILE = 128 candidates (beam) or 64 (re-prune of an adjacency row).
+// Thread (ty, tx) of the 16 x 16 grid owns C[ty + 16 a][tx + 16 b]; K is walked in 32-float chunks staged in shared memory
+// (row pitch 36 floats: 128-bit loads of a quarter-warp hit distinct banks).
+// ------------------------------------------------------------------------------------------------
+constexpr int GRAM_KC = 32;
+constexpr int GRAM_PITCH = 36;
+
+template <int METRIC, int TILE>
+__global__ void __launch_bounds__(PRUNE_THREADS) prune_gram_kernel(PruneParams P)
+{
+    constexpr int NB = TILE / 16;       // rows / cols per thread
+    constexpr int CP = TILE + 1;        // pitch of the similarity matrix
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *blob = reinterpret_cast<float *>(smem_raw);                         // stride + 4
+    float *tileA = blob + P.d.stride + 4;                                      // TILE * GRAM_PITCH
+    float *C = tileA + TILE * GRAM_PITCH;                                      // TILE * CP
+    long long *keys = reinterpret_cast<long long *>(C + TILE * CP + ((TILE * CP) & 1));  // TILE (8-byte aligned)
+    float *maxsim = reinterpret_cast<float *>(keys + TILE);                    // TILE
+    int32_t *ids = reinterpret_cast<int32_t *>(maxsim + TILE);                 // TILE
+    uint8_t *state = reinterpret_cast<uint8_t *>(ids + TILE);                  // TILE
+    __shared__ float red[36];
+    __shared__ int s_next;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+    constexpr int NW = PRUNE_THREADS / 32;
+    const int total = P.count_ptr ? *P.count_ptr : P.count;
+    float alpha_max = 1.0f;
+    for (float a = 1.0f; a <= P.alpha + 1e-6f; a += 0.2f) alpha_max = a;
+
+    for (int it = blockIdx.x; it < total; it += gridDim.x) {
+        const int v = P.mode == 0 ? P.node_base + it : P.list[it];
+        const int32_t *cand;
+        int nc;
+        if (P.mode == 0) {
+            cand = P.cand + (size_t)it * P.cand_stride;
+            nc = P.cand_stride;
+        } else {
+            cand = P.adj + (size_t)v * P.row_cap;
+            nc = min(P.deg[v], P.row_cap);
+        }
+        nc = min(nc, TILE);
+        prepare_blob(P.d, P.metric, P.d.rows + (size_t)v * P.d.stride, blob, red);
+        for (int i = warp; i < TILE; i += 2 * NW) {
+            const int i2 = i + NW;
+            const int32_t ca = i < nc ? cand[i] : -1, cb = (i2 < TILE && i2 < nc) ? cand[i2] : -1;
+            const bool va = ca >= 0 && ca != v, vb = cb >= 0 && cb != v;
+            long long ka = KEY_MIN, kb = KEY_MIN;
+            if (va || vb) {
+                float sa, sb;
+                score_f32_pair<METRIC>(P.d, blob, va ? ca : cb, vb ? cb : ca, lane, sa, sb);
+                if (va) ka = topk_key(sa, ca);
+                if (vb) kb = topk_key(sb, cb);
+            }
+            if (lane == 0) {
+                keys[i] = ka;
+                if (i2 < TILE) keys[i2] = kb;
+            }
+        }
+        __syncthreads();
+        bitonic_sort_desc_prune(keys, TILE);
+        int nvalid;
+        {
+            int lo = 0, hi = TILE;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (keys[mid] != KEY_MIN) lo = mid + 1;
+                else hi = mid;
+            }
+            nvalid = lo;
+        }
+        for (int i = tid; i < TILE; i += PRUNE_THREADS) {
+            maxsim[i] = -3.0e38f;
+            state[i] = (i < nvalid && !(i > 0 && keys[i - 1] == keys[i])) ? 0 : 2;
+            ids[i] = i < nvalid ? key_node(keys[i]) : -1;
+        }
+        __syncthreads();
+
+        // ---- Gram matrix of the candidate rows ----
+        float acc[NB][NB];
+#pragma unroll
+        for (int a = 0; a < NB; a++)
+#pragma unroll
+            for (int b = 0; b < NB; b++) acc[a][b] = 0.f;
+        for (int k0 = 0; k0 < P.d.stride; k0 += GRAM_KC) {
+            // stage rows [0, TILE) x [k0, k0 + KC): TILE * 8 float4, zero beyond nvalid / beyond the row
+            for (int t = tid; t < TILE * (GRAM_KC / 4); t += PRUNE_THREADS) {
+                const int r = t / (GRAM_KC / 4), c4 = t - r * (GRAM_KC / 4);
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int32_t node = ids[r];
+                if (node >= 0 && k0 + 4 * c4 < P.d.stride) val = __ldg(reinterpret_cast<const float4 *>(P.d.rows + (size_t)node * P.d.stride + k0) + c4);
+                *reinterpret_cast<float4 *>(tileA + r * GRAM_PITCH + 4 * c4) = val;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k4 = 0; k4 < GRAM_KC / 4; k4++) {
+                float4 av[NB], bv[NB];
+#pragma unroll
+                for (int a = 0; a < NB; a++) av[a] = *reinterpret_cast<const float4 *>(tileA + (ty + 16 * a) * GRAM_PITCH + 4 * k4);
+#pragma unroll
+                for (int b = 0; b < NB; b++) bv[b] = *reinterpret_cast<const float4 *>(tileA + (tx + 16 * b) * GRAM_PITCH + 4 * k4);
+#pragma unroll
+                for (int a = 0; a < NB; a++)
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {
+                        acc[a][b] = fmaf(av[a].x, bv[b].x, acc[a][b]);
+                        acc[a][b] = fmaf(av[a].y, bv[b].y, acc[a][b]);
+                        acc[a][b] = fmaf(av[a].z, bv[b].z, acc[a][b]);
+                        acc[a][b] = fmaf(av[a].w, bv[b].w, acc[a][b]);
+                    }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int a = 0; a < NB; a++)
+#pragma unroll
+            for (int b = 0; b < NB; b++) C[(ty + 16 * a) * CP + tx + 16 * b] = acc[a][b];
+        __syncthreads();
+        // raw dot products -> the reference's similarity scores (needs the diagonal for L2 / cosine)
+        if (METRIC != JV_METRIC_DOT) {
+            float diag_r[NB], diag_c[NB];
+#pragma unroll
+            for (int a = 0; a < NB; a++) diag_r[a] = C[(ty + 16 * a) * CP + ty + 16 * a];
+#pragma unroll
+            for (int b = 0; b < NB; b++) diag_c[b] = C[(tx + 16 * b) * CP + tx + 16 * b];
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < NB; a++)
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    float raw;
+                    if (METRIC == JV_METRIC_EUCLIDEAN) raw = fmaxf(0.f, __fadd_rn(__fadd_rn(diag_r[a], diag_c[b]), -2.0f * acc[a][b]));
+                    else raw = __fdiv_rn(acc[a][b], __fsqrt_rn(__fmul_rn(diag_r[a], diag_c[b])));
+                    C[(ty + 16 * a) * CP + tx + 16 * b] = score_map(METRIC, raw);
+                }
+        } else {
+#pragma unroll
+            for (int a = 0; a < NB; a++)
+#pragma unroll
+                for (int b = 0; b < NB; b++) C[(ty + 16 * a) * CP + tx + 16 * b] = score_map(METRIC, acc[a][b]);
+        }
+        __syncthreads();
+
+        // ---- the sequential selection, now over shared memory only ----
+        int nsel = 0;
+        float currentAlpha = 1.0f;
+        while (currentAlpha <= P.alpha + 1e-6f && nsel < P.degree) {
+            int cursor = 0;
+            while (nsel < P.degree) {
+                if (tid == 0) s_next = INT_MAX;
+                __syncthreads();
+                for (int i = cursor + tid; i < nvalid; i += PRUNE_THREADS)
+                    if (state[i] == 0 && !(maxsim[i] > __fmul_rn(key_score(keys[i]), currentAlpha))) { atomicMin(&s_next, i); break; }
+                __syncthreads();
+                const int pick = s_next;
+                if (pick == INT_MAX) break;
+                nsel++;
+                cursor = pick + 1;
+                for (int i = tid; i < nvalid; i += PRUNE_THREADS) {
+                    if (i == pick) state[i] = 1;
+                    else if (state[i] == 0) {
+                        const float m = fmaxf(maxsim[i], C[i * CP + pick]);
+                        maxsim[i] = m;
+                        if (m > __fmul_rn(key_score(keys[i]), alpha_max)) state[i] = 2;
+                    }
+                }
+                __syncthreads();
+            }
+            currentAlpha += 0.2f;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int w = 0;
+            int32_t *row = P.adj + (size_t)v * P.row_cap;
+            for (int i = 0; i < nvalid; i++)
+                if (state[i] == 1) row[w++] = ids[i];
+            for (int i = w; i < P.row_cap; i++) row[i] = -1;
+            P.deg[v] = w;
+            if (P.mode == 1 && P.mark) P.mark[v] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+template <int TILE>
+static size_t gram_smem_bytes(const DataDesc &d)
+{
+    size_t b = (size_t)(d.stride + 4) * 4 + (size_t)TILE * GRAM_PITCH * 4 + ((size_t)TILE * (TILE + 1) + 1) * 4 + (size_t)TILE * 8 + (size_t)TILE * 4 + (size_t)TILE * 4 + TILE;
+    return (b + 15) & ~(size_t)15;
+}
+
 // back-links: for every selected neighbour v of a new node u append u to v's row (ConcurrentNeighborMap.backlink)
 __global__ void __launch_bounds__(256) backlink_kernel(int32_t *adj, int *deg, int row_cap, int degree, int node_base, int count, int hard_max,
                                                        int *mark, int32_t *prune_list, int *prune_count, unsigned long long *dropped)
@@ -267,9 +462,21 @@ static size_t prune_smem_bytes(const DataDesc &d, int degree, bool sel_in_smem)
 template <int METRIC>
 static cudaError_t launch_prune_t(const PruneParams &P, int grid, size_t smem, cudaStream_t s)
 {
-    cudaError_t e = cudaFuncSetAttribute(prune_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    prune_kernel<METRIC><<<grid, PRUNE_THREADS, smem, s>>>(P);
+    // candidate sets that fit a tile go through the Gram-matrix kernel; anything larger keeps the incremental kernel
+    const int ncmax = P.mode == 0 ? P.cand_stride : P.row_cap;
+    cudaError_t e;
+    if (ncmax <= 64) {
+        const size_t gs = gram_smem_bytes<64>(P.d);
+        if ((e = cudaFuncSetAttribute(prune_gram_kernel<METRIC, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs)) != cudaSuccess) return e;
+        prune_gram_kernel<METRIC, 64><<<grid, PRUNE_THREADS, gs, s>>>(P);
+    } else if (ncmax <= 128) {
+        const size_t gs = gram_smem_bytes<128>(P.d);
+        if ((e = cudaFuncSetAttribute(prune_gram_kernel<METRIC, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs)) != cudaSuccess) return e;
+        prune_gram_kernel<METRIC, 128><<<grid, PRUNE_THREADS, gs, s>>>(P);
+    } else {
+        if ((e = cudaFuncSetAttribute(prune_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        prune_kernel<METRIC><<<grid, PRUNE_THREADS, smem, s>>>(P);
+    }
     g_launches++;
     return cudaGetLastError();
 }
