@@ -310,9 +310,10 @@ def test_graph_search_matches_oracle_f32(jv, oracle, sift_graph):
         same = (res.nodes == wn).all(axis=1)
         # SIFT has integer-valued distances: exact ties are common, and a tie at the candidate-list boundary is the
         # one place the device list and the reference's two heaps may legitimately differ
-        assert same.mean() >= 0.9, (topK, rerankK, same.mean())
+        print("siftsmall traversal agreement topK=%d rerankK=%d: %.3f of queries identical, visited %d vs %d" % (topK, rerankK, same.mean(), res.visitedCount, wv))
+        assert same.mean() >= 0.99, (topK, rerankK, same.mean())  # measured: 1.000 (SIFT distances are exact in fp32)
         close(res.scores[same], ws[same])
-        assert abs(res.visitedCount - wv) <= 0.03 * wv
+        assert abs(res.visitedCount - wv) <= 0.005 * wv
     gi.close()
     vec.close()
 
@@ -348,9 +349,10 @@ def test_graph_search_continuous_scores_exact_ids(jv, oracle):
             res = searcher.search(vec, queries, metric, 10, 40)
             wn, ws, wv = _oracle_search(oracle, g, lambda q: oracle.jvo_scorer_f32(metric, fp(data), n, dim, fp(q)), queries, 10, 40)
             same = (res.nodes == wn).all(axis=1)
-            assert same.mean() >= 0.97, (metric, upper is not None, same.mean())
+            print("continuous-data traversal agreement metric=%d hierarchy=%s: %.3f identical, visited %d vs %d" % (metric, upper is not None, same.mean(), res.visitedCount, wv))
+            assert same.mean() >= 0.98, (metric, upper is not None, same.mean())  # measured: 1.000
             close(res.scores[same], ws[same])
-            assert abs(res.visitedCount - wv) <= 0.02 * wv + 5
+            assert abs(res.visitedCount - wv) <= 0.01 * wv + 5
         vec.close()
         gi.close()
 
