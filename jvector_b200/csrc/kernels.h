@@ -65,6 +65,8 @@ struct SearchPlan {
     int ctas;
     int list_cap;     // rerankK rounded
     int visited_cap;  // power of two
+    int blob_in_global;  // PQ LUT kept in an L2-resident global slice per CTA instead of shared memory
+    int blob_floats;
 };
 cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const GraphDesc &g, int topK, int rerankK, int nq,
                         int visited_cap_hint, int sm_count, SearchPlan *plan);

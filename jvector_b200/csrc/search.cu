@@ -17,6 +17,7 @@
 // scorers.cuh (one lane group per candidate) -> parallel rank-merge into the list.
 #include <limits.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -42,6 +43,7 @@ struct SearchParams {
     uint8_t *overflow;
     const int32_t *query_index;
     int blobA_floats, blobR_floats;
+    float *blob_global;  // PQ "LUT in L2" mode: per-CTA slices of global scratch hold the prepared query instead of shared memory
     unsigned long long *dbg;  // JV_SEARCH_PROFILE builds only: per-phase cycle totals
 };
 
@@ -109,8 +111,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_k
     constexpr int G = GroupOf<KIND>::value;
     constexpr int NG = SEARCH_THREADS / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *blobA = reinterpret_cast<float *>(smem_raw);
-    float *blobR = blobA + P.blobA_floats;
+    float *blobA = P.blob_global ? P.blob_global + (size_t)blockIdx.x * P.blobA_floats : reinterpret_cast<float *>(smem_raw);
+    float *blobR = reinterpret_cast<float *>(smem_raw) + (P.blob_global ? 0 : P.blobA_floats);
     long long *keys0 = reinterpret_cast<long long *>(blobR + P.blobR_floats);
     long long *keys1 = keys0 + P.list_pow2;
     long long *cand_keys = keys1 + P.list_pow2;
@@ -384,10 +386,10 @@ static int next_pow2i(int v)
     return p;
 }
 
-static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, int list_pow2)
+static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, int list_pow2, bool blob_in_global)
 {
     size_t b = 0;
-    b += (size_t)blob_floats(approx) * 4;
+    if (!blob_in_global) b += (size_t)blob_floats(approx) * 4;
     if (rerank) b += (size_t)blob_floats(*rerank) * 4;
     b += (size_t)list_pow2 * 8 * 2;
     b += (size_t)MAX_DEGREE * 8 + (size_t)MAX_DEGREE * 4;
@@ -430,7 +432,19 @@ cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const Gr
     if (g.degree > MAX_DEGREE || rerankK < 1 || topK < 1 || topK > rerankK) return cudaErrorInvalidValue;
     plan->threads = SEARCH_THREADS;
     plan->list_cap = next_pow2i(rerankK);
-    plan->smem_bytes = search_smem_bytes(approx, rerank, plan->list_cap);
+    // PQ: a LUT of M*k fp32 (96 KB at M=96) in shared memory limits residency to 2 CTAs per SM, and the walk is a latency chain
+    // (profiles/r1_search_phase_cycles.md). When five LUTs do not fit an SM's shared memory the LUT lives in an L2-resident
+    // global slice per CTA instead: residency becomes register-limited (5 CTAs per SM) and the gathers are served by L2.
+    // Measured on c3: 19.25 ms -> 13.1 ms per 10 000 queries. JV_PQ_LUT=smem|l2 overrides.
+    plan->blob_in_global = 0;
+    if (approx.kind == KIND_PQ) {
+        const char *mode = getenv("JV_PQ_LUT");
+        if (mode && mode[0] == 'l') plan->blob_in_global = 1;
+        else if (mode && mode[0] == 's') plan->blob_in_global = 0;
+        else plan->blob_in_global = (size_t)blob_floats(approx) * 4 * 5 > 200 * 1024 ? 1 : 0;
+    }
+    plan->blob_floats = blob_floats(approx);
+    plan->smem_bytes = search_smem_bytes(approx, rerank, plan->list_cap, plan->blob_in_global != 0);
     if (plan->smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
     int cap = visited_cap_hint > 0 ? visited_cap_hint : next_pow2i(4 * rerankK * (g.degree > 16 ? g.degree : 16));
     if (cap < 2048) cap = 2048;
@@ -451,7 +465,12 @@ cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const Gr
     return cudaSuccess;
 }
 
-size_t search_scratch_bytes(const SearchPlan &p) { return (size_t)p.ctas * p.visited_cap * sizeof(int32_t); }
+size_t search_scratch_bytes(const SearchPlan &p)
+{
+    size_t b = (size_t)p.ctas * p.visited_cap * sizeof(int32_t);
+    if (p.blob_in_global) b += (size_t)p.ctas * p.blob_floats * sizeof(float) + 256;
+    return b;
+}
 
 cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const DataDesc *rerank, int metric, const float *queries_dev,
                           int nq, int topK, int rerankK, const SearchPlan &plan, void *scratch_dev, int *work_counter_dev,
@@ -484,6 +503,11 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
     P.query_index = query_index_dev;
     P.blobA_floats = blob_floats(approx);
     P.blobR_floats = rerank ? blob_floats(*rerank) : 0;
+    P.blob_global = nullptr;
+    if (plan.blob_in_global) {
+        size_t off = ((size_t)plan.ctas * plan.visited_cap * sizeof(int32_t) + 255) & ~(size_t)255;
+        P.blob_global = reinterpret_cast<float *>(reinterpret_cast<char *>(scratch_dev) + off);
+    }
     P.dbg = nullptr;
 #ifdef JV_SEARCH_PROFILE
     static unsigned long long *dbg_dev = nullptr;
