@@ -94,6 +94,9 @@ __device__ __forceinline__ void bitonic_sort_desc_block(long long *keys, int n_p
 #ifndef JV_SEARCH_MINB
 #define JV_SEARCH_MINB 5
 #endif
+#ifndef JV_SEARCH_MINB_PQ
+#define JV_SEARCH_MINB_PQ 6  // tools/sweep_pq_minb.sh: 5 -> 777k q/s, 6 -> 817k, 8 -> 592k (c3, LUT in L2)
+#endif
 constexpr int SEARCH_THREADS = JV_SEARCH_THREADS;
 
 // optional phase timers (tools/: build with JV_NVCC_EXTRA=-DJV_SEARCH_PROFILE); compiled out of the product build
@@ -106,7 +109,7 @@ constexpr int SEARCH_THREADS = JV_SEARCH_THREADS;
 #endif
 
 template <int KIND, int METRIC>
-__global__ void __launch_bounds__(SEARCH_THREADS, JV_SEARCH_MINB) graph_search_kernel(SearchParams P)
+__global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_MINB_PQ : JV_SEARCH_MINB)) graph_search_kernel(SearchParams P)
 {
     constexpr int G = GroupOf<KIND>::value;
     constexpr int NG = SEARCH_THREADS / G;
