@@ -44,7 +44,6 @@ struct PruneParams {
     const int32_t *cand;
     int cand_stride;
     int *mark;  // cleared for pruned nodes in mode 1
-    int sel_in_smem;  // selected rows cached in shared memory
 };
 
 __device__ __forceinline__ void bitonic_sort_desc_prune(long long *keys, int n_pow2)
@@ -451,10 +450,8 @@ __global__ void __launch_bounds__(256) compact_adj_kernel(const int32_t *adj, co
     out[idx] = j < min(deg[v], degree) ? adj[(size_t)v * row_cap + j] : -1;
 }
 
-static size_t prune_smem_bytes(const DataDesc &d, int degree, bool sel_in_smem)
+static size_t prune_smem_bytes(const DataDesc &d)
 {
-    (void)degree;
-    (void)sel_in_smem;
     size_t b = (size_t)(d.stride + 4) * 4 + (size_t)d.stride * 4 + (size_t)PRUNE_MAXC * 8 + (size_t)PRUNE_MAXC * 4 + 128 * 4 + PRUNE_MAXC;
     return (b + 15) & ~(size_t)15;
 }
@@ -516,8 +513,7 @@ cudaError_t build_graph_flat(const DataDesc &d, int metric, const BuildParams &b
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     BuildStats st = {0, 0, 0, 0};
-    bool sel_in_smem = prune_smem_bytes(d, degree, true) <= 200 * 1024;
-    const size_t psmem = prune_smem_bytes(d, degree, sel_in_smem);
+    const size_t psmem = prune_smem_bytes(d);
     const int prune_grid = sm_count * 5;  // ~10 KB of shared memory per CTA: register-limited residency
 
     JV_TRY(cudaMalloc(&adj, (size_t)n * row_cap * sizeof(int32_t)));
@@ -563,7 +559,7 @@ cudaError_t build_graph_flat(const DataDesc &d, int metric, const BuildParams &b
             PruneParams P;
             P.d = d; P.metric = metric; P.degree = degree; P.row_cap = row_cap; P.alpha = bp.alpha; P.adj = adj; P.deg = deg;
             P.mode = 0; P.node_base = inserted; P.list = nullptr; P.count_ptr = nullptr; P.count = batch; P.cand = res_nodes;
-            P.cand_stride = beam; P.mark = mark; P.sel_in_smem = sel_in_smem ? 1 : 0;
+            P.cand_stride = beam; P.mark = mark;
             JV_TRY(launch_prune(P, batch < prune_grid ? batch : prune_grid, psmem, s));
             // (3) back-links, then re-prune every neighbour that passed overflow * M
             JV_TRY(cudaMemsetAsync(prune_count, 0, sizeof(int), s));
@@ -586,7 +582,7 @@ cudaError_t build_graph_flat(const DataDesc &d, int metric, const BuildParams &b
         PruneParams P;
         P.d = d; P.metric = metric; P.degree = degree; P.row_cap = row_cap; P.alpha = bp.alpha; P.adj = adj; P.deg = deg;
         P.mode = 1; P.node_base = 0; P.list = prune_list; P.count_ptr = prune_count; P.count = 0; P.cand = nullptr; P.cand_stride = 0;
-        P.mark = mark; P.sel_in_smem = sel_in_smem ? 1 : 0;
+        P.mark = mark;
         JV_TRY(launch_prune(P, prune_grid, psmem, s));
         const long long total = (long long)n * degree;
         compact_adj_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(adj, deg, n, row_cap, degree, adj_out_dev);

@@ -527,3 +527,54 @@ def test_encoders_from_resident_dataset(jv, oracle):
         p2, b2 = jv.nvq_encode_all(data, mean, nsub, True)
         assert np.array_equal(p1, p2) and np.array_equal(b1, b2)
         vec.close()
+
+
+# ------------------------------------------------------------------------------------------------ rarely taken paths
+def test_search_visited_table_overflow_retry(jv, oracle):
+    # a RANDOM graph makes the walk wander: the visited set outgrows the first table, the host re-runs those queries with a 4x
+    # table (api.cu search_device) and the result must still equal the oracle traversal exactly
+    rng = np.random.default_rng(23)
+    n, dim, degree = 20000, 32, 32
+    data = o.random_unit_vectors(rng, n, dim)
+    queries = o.random_unit_vectors(rng, 24, dim)
+    adj = rng.integers(0, n, (n, degree)).astype(np.int32)
+    adj[adj == np.arange(n)[:, None]] = 0
+    g = o.make_graph(adj, 5)
+    gi = jv.GraphIndex(adj, 5)
+    vec = jv.F32Vectors(data)
+    res = jv.GraphSearcher(gi).search(vec, queries, o.DOT_PRODUCT, 10, 10)
+    wn, ws, wv = _oracle_search(oracle, g, lambda q: oracle.jvo_scorer_f32(o.DOT_PRODUCT, fp(data), n, dim, fp(q)), queries, 10, 10)
+    assert res.retried > 0, "the test is meant to exercise the retry path"
+    assert (res.nodes == wn).all(axis=1).mean() >= 0.95
+    assert abs(res.visitedCount - wv) <= 0.02 * wv
+    # a wide beam (rerankK = 1000: 8 KB key lists, bitonic rerank sort of 1024) on the same graph
+    res = jv.GraphSearcher(gi).search(vec, queries[:4], o.DOT_PRODUCT, 100, 1000)
+    wn, ws, wv = _oracle_search(oracle, g, lambda q: oracle.jvo_scorer_f32(o.DOT_PRODUCT, fp(data), n, dim, fp(q)), queries[:4], 100, 1000)
+    assert (res.nodes == wn).all(axis=1).mean() >= 0.75 and abs(res.visitedCount - wv) <= 0.02 * wv
+    vec.close()
+    gi.close()
+
+
+def test_topk_multipass_on_adversarial_layout(jv, oracle):
+    # n > 16384 takes the sampled-threshold path. Put LOW scores exactly on the strided sample positions and near-equal HIGH
+    # scores everywhere else: the sample thresholds are then far too low, the candidate buffer overflows, and the exact
+    # result must come out of the tighten-and-rescan passes.
+    n, dim, S = 40000, 8, 16384
+    rng = np.random.default_rng(3)
+    sampled = np.unique((np.arange(S, dtype=np.int64) * n) // S)
+    data = np.zeros((n, dim), np.float32)
+    data[:, 0] = 0.9 + 1e-4 * rng.random(n, dtype=np.float32)
+    data[sampled, 0] = -0.5
+    data[:, 1] = 1e-3 * rng.standard_normal(n).astype(np.float32)
+    q = np.zeros((3, dim), np.float32)
+    q[:, 0] = 1.0
+    q[1, 1] = 0.5
+    q[2, 1] = -0.5
+    vec = jv.F32Vectors(data)
+    for k in (10, 100):
+        nodes, scores, keys = jv.topk_bruteforce(vec, o.DOT_PRODUCT, q, k)
+        for qi in range(3):
+            wk = np.empty(k, np.int64)
+            oracle.jvo_bruteforce_topk_f32(o.DOT_PRODUCT, fp(data), n, dim, fp(q[qi]), k, lp(wk))
+            assert np.array_equal(keys[qi], wk), (k, qi)  # 2-term dot products: bit-identical scores, so identical keys
+    vec.close()
