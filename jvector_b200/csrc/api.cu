@@ -721,7 +721,10 @@ static int search_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int
     cudaStream_t s = t_ctx.stream;
     const DataDesc *rr = reranker ? &reranker->d : nullptr;
     SearchPlan plan;
-    CK(plan_search(approx->d, rr, g->g, topK, rerankK, nq, 0, g_sm_count, &plan), "plan_search");
+    // JV_VISITED_CAP: first visited-table size (testing / tuning knob; queries that outgrow it are re-run below with 4x)
+    const char *cap_env = getenv("JV_VISITED_CAP");
+    const int cap_hint = cap_env ? atoi(cap_env) : 0;
+    CK(plan_search(approx->d, rr, g->g, topK, rerankK, nq, cap_hint > 0 ? cap_hint : 0, g_sm_count, &plan), "plan_search");
     const size_t aux = sizeof(SearchCounters) + 64 + (size_t)nq + (size_t)nq * 4 + 64;
     if ((rc = t_ctx.ensure(5, search_scratch_bytes(plan))) || (rc = t_ctx.ensure(3, aux))) return rc;
     char *a = (char *)t_ctx.dbuf[3];

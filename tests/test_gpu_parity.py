@@ -542,8 +542,13 @@ def test_search_visited_table_overflow_retry(jv, oracle):
     g = o.make_graph(adj, 5)
     gi = jv.GraphIndex(adj, 5)
     vec = jv.F32Vectors(data)
-    res = jv.GraphSearcher(gi).search(vec, queries, o.DOT_PRODUCT, 10, 10)
-    wn, ws, wv = _oracle_search(oracle, g, lambda q: oracle.jvo_scorer_f32(o.DOT_PRODUCT, fp(data), n, dim, fp(q)), queries, 10, 10)
+    import os
+    os.environ["JV_VISITED_CAP"] = "2048"  # first table: 2048 slots, a query is declared overflowed at 1024 visited nodes
+    try:
+        res = jv.GraphSearcher(gi).search(vec, queries, o.DOT_PRODUCT, 10, 50)
+    finally:
+        del os.environ["JV_VISITED_CAP"]
+    wn, ws, wv = _oracle_search(oracle, g, lambda q: oracle.jvo_scorer_f32(o.DOT_PRODUCT, fp(data), n, dim, fp(q)), queries, 10, 50)
     assert res.retried > 0, "the test is meant to exercise the retry path"
     assert (res.nodes == wn).all(axis=1).mean() >= 0.95
     assert abs(res.visitedCount - wv) <= 0.02 * wv
