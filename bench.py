@@ -21,6 +21,13 @@ import argparse
 import ctypes as C
 import json
 import os
+
+# several ranks share one host: keep each rank's BLAS / OpenMP pools to its share of the cores (data generation only)
+_world = int(os.environ.get("WORLD_SIZE", "1"))
+if _world > 1:
+    _share = str(max(1, (os.cpu_count() or 1) // _world))
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.setdefault(_v, _share)
 import subprocess
 import sys
 import threading
