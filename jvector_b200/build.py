@@ -10,7 +10,7 @@ LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libjvector_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CU = ["kernels_batch.cu", "search.cu", "build.cu", "api.cu"]
-CPP = ["legacy_host.cpp"]
+CPP = ["legacy_host.cpp", "legacy_simd.cpp"]
 HEADERS = ["common.cuh", "scorers.cuh", "kernels.h", os.path.join("..", "..", "include", "jvector_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: only explicit fmaf() fuses (NVQ bit tricks and score maps must round like the reference's scalar code)
@@ -40,7 +40,9 @@ def build(force=False, verbose=False):
             if src.endswith(".cu"):
                 cmd = [NVCC] + ARCH + NVFLAGS + ["-c", s, "-o", o]
             else:
-                cmd = [NVCC, "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden,-O3,-mfma,-ffp-contract=off", "-c", s, "-o", o]
+                # legacy_host.cpp: explicit fmaf only (NVQ bit tricks); legacy_simd.cpp: let the vectoriser fuse (target_clones pick the ISA)
+                host = "-fPIC,-fvisibility=hidden,-O3,-ffp-contract=fast,-fno-math-errno" if src == "legacy_simd.cpp" else "-fPIC,-fvisibility=hidden,-O3,-mfma,-ffp-contract=off"
+                cmd = [NVCC, "-O3", "-std=c++17", "-Xcompiler", host, "-c", s, "-o", o]
             jobs.append((src, cmd))
 
     def run(job):

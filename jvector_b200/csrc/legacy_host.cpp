@@ -58,38 +58,7 @@ struct Nvq {
 
 extern "C" {
 
-float dot_product_f32(const float *a, size_t aoffset, const float *b, size_t boffset, size_t length)
-{
-    a += aoffset; b += boffset;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    size_t i = 0;
-    for (; i + 4 <= length; i += 4) {
-        s0 = fmaf(a[i], b[i], s0); s1 = fmaf(a[i + 1], b[i + 1], s1); s2 = fmaf(a[i + 2], b[i + 2], s2); s3 = fmaf(a[i + 3], b[i + 3], s3);
-    }
-    for (; i < length; i++) s0 = fmaf(a[i], b[i], s0);
-    return (s0 + s1) + (s2 + s3);
-}
-
-float euclidean_f32(const float *a, size_t aoffset, const float *b, size_t boffset, size_t length)
-{
-    a += aoffset; b += boffset;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    size_t i = 0;
-    for (; i + 4 <= length; i += 4) {
-        const float d0 = a[i] - b[i], d1 = a[i + 1] - b[i + 1], d2 = a[i + 2] - b[i + 2], d3 = a[i + 3] - b[i + 3];
-        s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
-    }
-    for (; i < length; i++) { const float d = a[i] - b[i]; s0 = fmaf(d, d, s0); }
-    return (s0 + s1) + (s2 + s3);
-}
-
-float cosine_f32(const float *a, size_t aoffset, const float *b, size_t boffset, size_t length)
-{
-    a += aoffset; b += boffset;
-    float s = 0.f, aa = 0.f, bb = 0.f;
-    for (size_t i = 0; i < length; i++) { s = fmaf(a[i], b[i], s); aa = fmaf(a[i], a[i], aa); bb = fmaf(b[i], b[i], bb); }
-    return s / sqrtf(aa * bb);
-}
+// dot_product_f32 / euclidean_f32 / cosine_f32 live in legacy_simd.cpp (vectorised, multi-versioned)
 
 void add_in_place_f32(float *v1, const float *v2, size_t length) { for (size_t i = 0; i < length; i++) v1[i] += v2[i]; }
 void add_scalar_in_place_f32(float *v1, float value, size_t length) { for (size_t i = 0; i < length; i++) v1[i] += value; }
