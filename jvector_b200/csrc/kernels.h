@@ -8,8 +8,8 @@
 
 namespace jv {
 
-extern std::atomic<long long> g_launches;
-constexpr int MAX_DEGREE = 128;  // widest adjacency row the search kernel accepts  // kernels launched by this library (jv_kernel_launch_count)
+extern std::atomic<long long> g_launches;  // kernels launched by this library (jv_kernel_launch_count)
+constexpr int MAX_DEGREE = 128;            // widest adjacency row the search kernel accepts
 
 struct GraphDesc {
     int32_t n;
