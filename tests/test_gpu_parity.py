@@ -583,3 +583,20 @@ def test_topk_multipass_on_adversarial_layout(jv, oracle):
             oracle.jvo_bruteforce_topk_f32(o.DOT_PRODUCT, fp(data), n, dim, fp(q[qi]), k, lp(wk))
             assert np.array_equal(keys[qi], wk), (k, qi)  # 2-term dot products: bit-identical scores, so identical keys
     vec.close()
+
+
+def test_device_builder_golden_neighbour_lists(jv):
+    # tests:graph/TestVectorGraph.java:457-526 testDiversity — the reference's golden neighbour lists (M=4, beamWidth=10, overflow 1.0,
+    # alpha 1.0, 7 unit-circle vectors). The device builder's first batches hold ONE node each (batch = max(1, inserted / 2)), i.e. they
+    # are sequential inserts, so the states after 3 and after 4 nodes must equal the reference's, list for list.
+    ang = np.array([0.5, 0.75, 0.2, 0.9, 0.8, 0.77, 0.6]) * np.pi
+    vec = np.ascontiguousarray(np.stack([np.cos(ang), np.sin(ang)], 1), dtype=np.float32)
+    expected = {3: {0: [1, 2], 1: [0], 2: [0]}, 4: {0: [1, 2], 1: [0, 3], 2: [0], 3: [1]}}
+    for n, want in expected.items():
+        v = jv.F32Vectors(vec[:n])
+        g = jv.GraphIndexBuilder(o.DOT_PRODUCT, M=4, beamWidth=10, neighborOverflow=1.0, alpha=1.0).build(v)
+        _, adj = g.level(0)
+        for node, nbrs in want.items():
+            assert sorted(int(x) for x in adj[node] if x >= 0) == nbrs, (n, node, adj[node].tolist(), nbrs)
+        g.close()
+        v.close()

@@ -352,3 +352,23 @@ def test_graph_build_and_search_siftsmall(oracle, sift):
         truth = set(np.argsort(d, kind="stable")[:10].tolist())
         hits += len(truth & set(nodes.tolist()))
     assert hits / 500.0 > 0.9  # tests:graph/TestVectorGraph.java:672
+
+
+def test_builder_known_answer_diversity(oracle):
+    # tests:graph/TestVectorGraph.java:457-526 testDiversity — golden neighbour lists of GraphIndexBuilder(DOT_PRODUCT, M=4, beamWidth=10,
+    # neighborOverflow=1.0, alpha=1.0) over 7 unit-circle vectors, checked after each insert. The oracle builder inserts sequentially, so
+    # building the first n vectors reproduces the state after addGraphNode(n-1).
+    ang = np.array([0.5, 0.75, 0.2, 0.9, 0.8, 0.77, 0.6]) * np.pi
+    vec = np.ascontiguousarray(np.stack([np.cos(ang), np.sin(ang)], 1), dtype=np.float32)
+    expected = {
+        3: {0: [1, 2], 1: [0], 2: [0]},
+        4: {0: [1, 2], 1: [0, 3], 2: [0], 3: [1]},
+        5: {0: [1, 2], 1: [0, 3, 4], 2: [0], 3: [1, 4], 4: [1, 3]},
+        6: {0: [1, 2], 1: [0, 3, 4, 5], 2: [0], 3: [1, 4], 4: [1, 3, 5], 5: [1, 4]},
+    }
+    for n, want in expected.items():
+        adj = np.empty((n, 4), np.int32)
+        oracle.jvo_graph_build_f32(o.DOT_PRODUCT, fp(vec), n, 2, 4, 10, 1.0, 1.0, ip(adj))
+        for node, nbrs in want.items():
+            got = sorted(int(x) for x in adj[node] if x >= 0)
+            assert got == nbrs, (n, node, got, nbrs)
