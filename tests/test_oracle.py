@@ -372,3 +372,21 @@ def test_builder_known_answer_diversity(oracle):
         for node, nbrs in want.items():
             got = sorted(int(x) for x in adj[node] if x >= 0)
             assert got == nbrs, (n, node, got, nbrs)
+
+
+def test_builder_known_answer_fallback_and_3d(oracle):
+    # tests:graph/TestVectorGraph.java:533-611 — EUCLIDEAN, M=2, beamWidth=10, overflow 1.0, alpha 1.0
+    # testDiversityFallback: a new closer neighbour displaces the farthest one although every neighbour stays diverse
+    v = np.array([[0, 0, 0], [0, 10, 0], [0, 0, 20], [10, 0, 0], [0, 4, 0]], np.float32)
+    for n, want in ((3, {0: [1, 2], 1: [0], 2: [0]}), (4, {0: [1, 3], 1: [0], 2: [0], 3: [0]})):
+        adj = np.empty((n, 2), np.int32)
+        oracle.jvo_graph_build_f32(o.EUCLIDEAN, fp(np.ascontiguousarray(v[:n])), n, 3, 2, 10, 1.0, 1.0, ip(adj))
+        for node, nbrs in want.items():
+            assert sorted(int(x) for x in adj[node] if x >= 0) == nbrs, ("fallback", n, node, adj[node].tolist())
+    # testDiversity3d: a neighbour BECOMES non-diverse when a newer, better neighbour arrives
+    v = np.array([[0, 0, 0], [0, 10, 0], [0, 0, 20], [0, 9, 0]], np.float32)
+    for n, want in ((3, {0: [1, 2], 1: [0], 2: [0]}), (4, {0: [2, 3], 1: [0, 3], 2: [0], 3: [0, 1]})):
+        adj = np.empty((n, 2), np.int32)
+        oracle.jvo_graph_build_f32(o.EUCLIDEAN, fp(np.ascontiguousarray(v[:n])), n, 3, 2, 10, 1.0, 1.0, ip(adj))
+        for node, nbrs in want.items():
+            assert sorted(int(x) for x in adj[node] if x >= 0) == nbrs, ("3d", n, node, adj[node].tolist())
