@@ -174,10 +174,32 @@ typedef struct {
 JV_API int jv_graph_search_batch(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric,
                                  const float *queries, int nq, int topK, int rerankK,
                                  int32_t *nodes_out, float *scores_out, jv_search_stats *stats);
+/* GraphSearcher.search(scoreProvider, topK, rerankK, threshold, rerankFloor, acceptOrds) — base:graph/GraphSearcher.java:166-181.
+ * accept_bits: bit (node & 31) of 32-bit word (node >> 5) set = the node may be a RESULT (it is still traversed), applied on
+ * level 0 only as searchOneLayer does (:427-431); accept_stride_words = 0 shares one bitset between all queries of the batch,
+ * otherwise query i uses accept_bits + i * accept_stride_words. threshold: minimum approximate score of a result (the
+ * TwoPhaseTracker early-termination heuristic of ScoreTracker.java is NOT run: a threshold search here visits at least what
+ * the reference visits). rerank_floor: NodeQueue.rerank's rerankFloor (NodeQueue.java:168-230). NULL = {NULL, 0, 0, 0}.
+ * A filter that rejects most nodes needs a long candidate list; beyond 8192 live candidates the call fails with JV_ERR_OVERFLOW. */
+typedef struct {
+    const uint32_t *accept_bits;
+    int64_t accept_stride_words;
+    float threshold;
+    float rerank_floor;
+} jv_search_options;
+JV_API int jv_graph_search_batch_ex(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric,
+                                    const float *queries, int nq, int topK, int rerankK, const jv_search_options *opts,
+                                    int32_t *nodes_out, float *scores_out, jv_search_stats *stats);
 /* same with queries / outputs already in HBM (no host copies in the call) */
 JV_API int jv_graph_search_batch_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric,
                                         const float *queries_device, int nq, int topK, int rerankK,
                                         int32_t *nodes_out_device, float *scores_out_device, jv_search_stats *stats);
+
+/* _ex form with everything in HBM; opts->accept_bits is a DEVICE pointer here */
+JV_API int jv_graph_search_batch_device_ex(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric,
+                                           const float *queries_device, int nq, int topK, int rerankK,
+                                           const jv_search_options *opts_device_bits, int32_t *nodes_out_device,
+                                           float *scores_out_device, jv_search_stats *stats);
 
 /* GraphIndexBuilder.build over an f32 data set with exact scoring (BuildScoreProvider.randomAccessScoreProvider):
  * batched inserts, device-side beam search + Vamana robust prune + back-links. */

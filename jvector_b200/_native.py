@@ -26,6 +26,10 @@ class SearchStats(C.Structure):
                 ("retried", C.c_int64), ("device_ms", C.c_double)]
 
 
+class SearchOptions(C.Structure):
+    _fields_ = [("accept_bits", C.c_void_p), ("accept_stride_words", C.c_int64), ("threshold", C.c_float), ("rerank_floor", C.c_float)]
+
+
 class BuildParams(C.Structure):
     _fields_ = [("degree", C.c_int), ("beam_width", C.c_int), ("overflow", C.c_float), ("alpha", C.c_float),
                 ("add_hierarchy", C.c_int), ("seed", C.c_uint64), ("max_batch", C.c_int)]
@@ -71,6 +75,8 @@ SYMBOLS = [
     ("jv_graph_download", _I, [_P, _I, i32p, i32p, i32p]),
     ("jv_graph_search_batch", _I, [_P, _P, _P, _I, f32p, _I, _I, _I, i32p, f32p, C.POINTER(SearchStats)]),
     ("jv_graph_search_batch_device", _I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, C.POINTER(SearchStats)]),
+    ("jv_graph_search_batch_ex", _I, [_P, _P, _P, _I, f32p, _I, _I, _I, C.POINTER(SearchOptions), i32p, f32p, C.POINTER(SearchStats)]),
+    ("jv_graph_search_batch_device_ex", _I, [_P, _P, _P, _I, _P, _I, _I, _I, C.POINTER(SearchOptions), _P, _P, C.POINTER(SearchStats)]),
     ("jv_graph_build", _I, [_P, _I, C.POINTER(BuildParams), C.POINTER(_P), C.POINTER(C.c_double)]),
     ("jv_graph_build_stats", _I, [i64p, i64p, i64p]),
     ("jv_device_malloc", _I, [C.POINTER(_P), _Z]), ("jv_device_free", _I, [_P]), ("jv_memcpy_h2d", _I, [_P, _P, _Z]),

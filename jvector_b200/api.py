@@ -281,17 +281,38 @@ class GraphSearcher:
     def __init__(self, graph):
         self.graph = graph
 
-    def search(self, approx, queries, vsf, topK, rerankK=None, reranker=None):
+    def search(self, approx, queries, vsf, topK, rerankK=None, reranker=None, threshold=0.0, rerankFloor=0.0, acceptOrds=None):
+        """acceptOrds: None (Bits.ALL), a bool array [n] shared by the batch, or [nq][n] one per query
+        (GraphSearcher.search(sp, topK, rerankK, threshold, rerankFloor, acceptOrds))."""
         lib = nat.init()
         queries = c32(queries)
+        if queries.shape[1] != approx.dimension():
+            raise ValueError("query dimension %d != data set dimension %d" % (queries.shape[1], approx.dimension()))
         rerankK = rerankK or topK
         nq = queries.shape[0]
         nodes = np.empty((nq, topK), dtype=np.int32)
         scores = np.empty((nq, topK), dtype=np.float32)
         st = nat.SearchStats()
-        check(lib.jv_graph_search_batch(self.graph._h, approx._h, reranker._h if reranker is not None else None, int(vsf), fp(queries), nq,
-                                        topK, rerankK, ip(nodes), fp(scores), C.byref(st)))
+        opts = None
+        if acceptOrds is not None or threshold > 0 or rerankFloor > 0:
+            opts = nat.SearchOptions(None, 0, float(threshold), float(rerankFloor))
+            if acceptOrds is not None:
+                bits = pack_accept_bits(acceptOrds)
+                opts.accept_bits = bits.ctypes.data
+                opts.accept_stride_words = bits.shape[1] if bits.ndim == 2 else 0
+        check(lib.jv_graph_search_batch_ex(self.graph._h, approx._h, reranker._h if reranker is not None else None, int(vsf), fp(queries), nq,
+                                           topK, rerankK, C.byref(opts) if opts is not None else None, ip(nodes), fp(scores), C.byref(st)))
         return SearchResult(nodes, scores, st)
+
+
+def pack_accept_bits(mask):
+    """bool [n] or [nq][n] -> uint32 words, bit (node & 31) of word (node >> 5) (the layout jv_search_options.accept_bits takes)"""
+    m = np.asarray(mask, dtype=bool)
+    n = m.shape[-1]
+    pad = (-n) % 32
+    if pad:
+        m = np.concatenate([m, np.zeros(m.shape[:-1] + (pad,), bool)], axis=-1)
+    return np.ascontiguousarray(np.packbits(m, axis=-1, bitorder="little").view(np.uint32))
 
 
 class GraphIndexBuilder:

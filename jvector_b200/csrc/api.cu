@@ -47,8 +47,9 @@ int cuda_fail(cudaError_t e, const char *what)
 // per-thread stream + growable staging buffers (callers are ForkJoinPool workers: no global locks on the score path)
 struct ThreadCtx {
     cudaStream_t stream = nullptr;
-    void *dbuf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t dcap[6] = {0, 0, 0, 0, 0, 0};
+    static constexpr int SLOTS = 8;
+    void *dbuf[SLOTS] = {};
+    size_t dcap[SLOTS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int init()
     {
@@ -706,7 +707,7 @@ int jv_graph_download(jv_graph g, int level, int32_t *node_ids_out, int32_t *adj
 }
 
 static int search_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric, const float *queries_dev, int nq, int topK, int rerankK,
-                         int32_t *nodes_dev, float *scores_dev, jv_search_stats *stats)
+                         const SearchFilter *filter, int32_t *nodes_dev, float *scores_dev, jv_search_stats *stats)
 {
     if (!g || !approx || !queries_dev || !nodes_dev || !scores_dev || nq <= 0) return fail(JV_ERR_INVALID, "graph_search: bad arguments");
     if (topK < 1 || rerankK < topK) return fail(JV_ERR_INVALID, "graph_search: need 1 <= topK <= rerankK");
@@ -721,10 +722,12 @@ static int search_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int
     cudaStream_t s = t_ctx.stream;
     const DataDesc *rr = reranker ? &reranker->d : nullptr;
     SearchPlan plan;
-    // JV_VISITED_CAP: first visited-table size (testing / tuning knob; queries that outgrow it are re-run below with 4x)
+    // JV_VISITED_CAP / JV_LIST_CAP: first visited-table / candidate-list sizes (testing and tuning knobs; queries that outgrow
+    // either are re-run below with 4x)
     const char *cap_env = getenv("JV_VISITED_CAP");
-    const int cap_hint = cap_env ? atoi(cap_env) : 0;
-    CK(plan_search(approx->d, rr, g->g, topK, rerankK, nq, cap_hint > 0 ? cap_hint : 0, g_sm_count, &plan), "plan_search");
+    const char *lcap_env = getenv("JV_LIST_CAP");
+    const int cap_hint = cap_env ? atoi(cap_env) : 0, lcap_hint = lcap_env ? atoi(lcap_env) : 0;
+    CK(plan_search(approx->d, rr, g->g, topK, rerankK, nq, cap_hint > 0 ? cap_hint : 0, lcap_hint > 0 ? lcap_hint : 0, g_sm_count, &plan), "plan_search");
     const size_t aux = sizeof(SearchCounters) + 64 + (size_t)nq + (size_t)nq * 4 + 64;
     if ((rc = t_ctx.ensure(5, search_scratch_bytes(plan))) || (rc = t_ctx.ensure(3, aux))) return rc;
     char *a = (char *)t_ctx.dbuf[3];
@@ -734,7 +737,7 @@ static int search_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int
     int32_t *dindex = (int32_t *)(a + sizeof(SearchCounters) + 64 + (((size_t)nq + 63) & ~(size_t)63));
     CK(cudaMemsetAsync(dcnt, 0, sizeof(SearchCounters), s), "memset counters");
     CK(cudaEventRecord(t_ctx.ev0, s), "event");
-    CK(launch_search(g->g, approx->d, rr, metric, queries_dev, nq, topK, rerankK, plan, t_ctx.dbuf[5], dwork, nodes_dev, scores_dev, dcnt, dover, nullptr, 0, s),
+    CK(launch_search(g->g, approx->d, rr, metric, queries_dev, nq, topK, rerankK, plan, t_ctx.dbuf[5], dwork, nodes_dev, scores_dev, dcnt, dover, nullptr, 0, filter, s),
        "launch_search");
     CK(cudaEventRecord(t_ctx.ev1, s), "event");
     SearchCounters hc;
@@ -743,26 +746,36 @@ static int search_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int
     float ms = 0.f;
     cudaEventElapsedTime(&ms, t_ctx.ev0, t_ctx.ev1);
     long long retried = 0;
-    int cap = plan.visited_cap;
-    // queries whose visited table filled up are re-run with a 4x larger table (the result does not depend on the table size)
-    for (int attempt = 0; hc.overflowed > 0 && attempt < 4; attempt++) {
+    int cap = plan.visited_cap, lcap = plan.list_cap;
+    // queries whose visited table filled up (code 1) or whose candidate list could not hold a tie tail (code 2) are re-run with a
+    // 4x larger table / list: the result does not depend on either size, only whether the run completes does
+    for (int attempt = 0; hc.overflowed > 0 && attempt < 6; attempt++) {
         std::vector<uint8_t> hover(nq);
         CK(cudaMemcpy(hover.data(), dover, (size_t)nq, cudaMemcpyDeviceToHost), "D2H overflow flags");
         std::vector<int32_t> idx;
+        bool need_table = false, need_list = false;
         for (int i = 0; i < nq; i++)
-            if (hover[i]) idx.push_back(i);
+            if (hover[i]) {
+                idx.push_back(i);
+                if (hover[i] == 1) need_table = true;
+                else need_list = true;
+            }
         if (idx.empty()) break;
         retried += (long long)idx.size();
-        cap *= 4;
+        if (need_table) cap *= 4;
+        if (need_list) {
+            if (lcap >= MAX_LIST_CAP) return fail(JV_ERR_OVERFLOW, "graph_search: more equal-score (or filtered-out) candidates than the longest candidate list holds");
+            lcap = std::min(MAX_LIST_CAP, lcap * 4);
+        }
         SearchPlan p2;
-        CK(plan_search(approx->d, rr, g->g, topK, rerankK, (int)idx.size(), cap, g_sm_count, &p2), "plan_search(retry)");
+        CK(plan_search(approx->d, rr, g->g, topK, rerankK, (int)idx.size(), cap, lcap, g_sm_count, &p2), "plan_search(retry)");
         if ((rc = t_ctx.ensure(5, search_scratch_bytes(p2)))) return rc;
         CK(cudaMemcpyAsync(dindex, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, s), "H2D retry index");
         unsigned long long zero = 0;
         CK(cudaMemcpyAsync(&dcnt->overflowed, &zero, sizeof(zero), cudaMemcpyHostToDevice, s), "reset overflow");
         CK(cudaEventRecord(t_ctx.ev0, s), "event");
         CK(launch_search(g->g, approx->d, rr, metric, queries_dev, (int)idx.size(), topK, rerankK, p2, t_ctx.dbuf[5], dwork, nodes_dev, scores_dev, dcnt, dover,
-                         dindex, 0, s),
+                         dindex, 0, filter, s),
            "launch_search(retry)");
         CK(cudaEventRecord(t_ctx.ev1, s), "event");
         CK(cudaMemcpyAsync(&hc, dcnt, sizeof(hc), cudaMemcpyDeviceToHost, s), "D2H counters");
@@ -771,7 +784,7 @@ static int search_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int
         cudaEventElapsedTime(&ms2, t_ctx.ev0, t_ctx.ev1);
         ms += ms2;
     }
-    if (hc.overflowed > 0) return fail(JV_ERR_OVERFLOW, "graph_search: visited table overflow after retries");
+    if (hc.overflowed > 0) return fail(JV_ERR_OVERFLOW, "graph_search: visited table / candidate list overflow after retries");
     if (stats) {
         stats->visited = (int64_t)hc.visited;
         stats->expanded = (int64_t)hc.expanded;
@@ -783,29 +796,77 @@ static int search_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int
     return JV_OK;
 }
 
+// jv_search_options -> device-side SearchFilter (the bitset is uploaded when it is a host pointer)
+static int make_filter(const jv_search_options *opts, jv_graph g, int nq, bool bits_on_device, SearchFilter *f, bool *use)
+{
+    *use = false;
+    memset(f, 0, sizeof(*f));
+    if (!opts) return JV_OK;
+    if (opts->threshold < 0.f || opts->rerank_floor < 0.f || opts->accept_stride_words < 0) return fail(JV_ERR_INVALID, "graph_search: negative threshold / rerankFloor / stride");
+    f->threshold = opts->threshold;
+    f->rerank_floor = opts->rerank_floor;
+    f->accept_stride_words = opts->accept_stride_words;
+    if (opts->accept_bits) {
+        const size_t words = ((size_t)g->g.n + 31) / 32;
+        if (opts->accept_stride_words != 0 && (size_t)opts->accept_stride_words < words) return fail(JV_ERR_INVALID, "graph_search: accept_stride_words shorter than one bitset");
+        if (bits_on_device) f->accept_bits = opts->accept_bits;
+        else {
+            const size_t total = opts->accept_stride_words ? (size_t)opts->accept_stride_words * (size_t)(nq - 1) + words : words;
+            int rc = t_ctx.ensure(6, total * 4);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(t_ctx.dbuf[6], opts->accept_bits, total * 4, cudaMemcpyHostToDevice, t_ctx.stream), "H2D accept bits");
+            f->accept_bits = (const uint32_t *)t_ctx.dbuf[6];
+        }
+    }
+    *use = f->accept_bits != nullptr || f->threshold > 0.f || f->rerank_floor > 0.f;
+    return JV_OK;
+}
+
+int jv_graph_search_batch_device_ex(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric, const float *queries_device, int nq, int topK,
+                                    int rerankK, const jv_search_options *opts_device_bits, int32_t *nodes_out_device, float *scores_out_device,
+                                    jv_search_stats *stats)
+{
+    NEED_INIT();
+    if (!g || nq <= 0) return fail(JV_ERR_INVALID, "graph_search: bad arguments");
+    int rc;
+    if ((rc = t_ctx.init())) return rc;
+    SearchFilter f;
+    bool use;
+    if ((rc = make_filter(opts_device_bits, g, nq, true, &f, &use))) return rc;
+    return search_device(g, approx, reranker, metric, queries_device, nq, topK, rerankK, use ? &f : nullptr, nodes_out_device, scores_out_device, stats);
+}
+
 int jv_graph_search_batch_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric, const float *queries_device, int nq, int topK,
                                  int rerankK, int32_t *nodes_out_device, float *scores_out_device, jv_search_stats *stats)
 {
-    NEED_INIT();
-    return search_device(g, approx, reranker, metric, queries_device, nq, topK, rerankK, nodes_out_device, scores_out_device, stats);
+    return jv_graph_search_batch_device_ex(g, approx, reranker, metric, queries_device, nq, topK, rerankK, nullptr, nodes_out_device, scores_out_device, stats);
 }
 
-int jv_graph_search_batch(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric, const float *queries, int nq, int topK, int rerankK,
-                          int32_t *nodes_out, float *scores_out, jv_search_stats *stats)
+int jv_graph_search_batch_ex(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric, const float *queries, int nq, int topK, int rerankK,
+                             const jv_search_options *opts, int32_t *nodes_out, float *scores_out, jv_search_stats *stats)
 {
     NEED_INIT();
-    if (!approx || !queries || !nodes_out || !scores_out || nq <= 0 || topK < 1) return fail(JV_ERR_INVALID, "graph_search: bad arguments");
+    if (!g || !approx || !queries || !nodes_out || !scores_out || nq <= 0 || topK < 1) return fail(JV_ERR_INVALID, "graph_search: bad arguments");
     int rc;
     const size_t qb = (size_t)nq * approx->d.dim * 4, ob = (size_t)nq * topK * 4;
     if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(0, qb)) || (rc = t_ctx.ensure(1, ob)) || (rc = t_ctx.ensure(2, ob))) return rc;
     cudaStream_t s = t_ctx.stream;
+    SearchFilter f;
+    bool use;
+    if ((rc = make_filter(opts, g, nq, false, &f, &use))) return rc;
     CK(cudaMemcpyAsync(t_ctx.dbuf[0], queries, qb, cudaMemcpyHostToDevice, s), "H2D queries");
-    rc = search_device(g, approx, reranker, metric, (const float *)t_ctx.dbuf[0], nq, topK, rerankK, (int32_t *)t_ctx.dbuf[1], (float *)t_ctx.dbuf[2], stats);
+    rc = search_device(g, approx, reranker, metric, (const float *)t_ctx.dbuf[0], nq, topK, rerankK, use ? &f : nullptr, (int32_t *)t_ctx.dbuf[1], (float *)t_ctx.dbuf[2], stats);
     if (rc) return rc;
     CK(cudaMemcpyAsync(nodes_out, t_ctx.dbuf[1], ob, cudaMemcpyDeviceToHost, s), "D2H nodes");
     CK(cudaMemcpyAsync(scores_out, t_ctx.dbuf[2], ob, cudaMemcpyDeviceToHost, s), "D2H scores");
     CK(cudaStreamSynchronize(s), "sync");
     return JV_OK;
+}
+
+int jv_graph_search_batch(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric, const float *queries, int nq, int topK, int rerankK,
+                          int32_t *nodes_out, float *scores_out, jv_search_stats *stats)
+{
+    return jv_graph_search_batch_ex(g, approx, reranker, metric, queries, nq, topK, rerankK, nullptr, nodes_out, scores_out, stats);
 }
 
 int jv_graph_build(jv_dataset f32, int metric, const jv_build_params *params, jv_graph *out, double *device_ms)

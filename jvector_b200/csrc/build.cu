@@ -545,7 +545,7 @@ cudaError_t build_graph_flat(const DataDesc &d, int metric, const BuildParams &b
             if (batch > n - inserted) batch = n - inserted;
             // (1) beam search of the current graph for every node of the batch
             SearchPlan plan;
-            JV_TRY(plan_search(d, nullptr, g, beam, beam, batch, 0, sm_count, &plan));
+            JV_TRY(plan_search(d, nullptr, g, beam, beam, batch, 0, 0, sm_count, &plan));
             const size_t need = search_scratch_bytes(plan);
             if (need > scratch_bytes) {
                 if (scratch) cudaFree(scratch);
@@ -554,7 +554,7 @@ cudaError_t build_graph_flat(const DataDesc &d, int metric, const BuildParams &b
                 scratch_bytes = need;
             }
             JV_TRY(launch_search(g, d, nullptr, metric, d.rows + (size_t)inserted * d.stride, batch, beam, beam, plan, scratch, work_counter,
-                                 res_nodes, res_scores, counters, overflow, nullptr, d.stride, s));
+                                 res_nodes, res_scores, counters, overflow, nullptr, d.stride, nullptr, s));
             // (2) robust prune of each beam -> the new node's list
             PruneParams P;
             P.d = d; P.metric = metric; P.degree = degree; P.row_cap = row_cap; P.alpha = bp.alpha; P.adj = adj; P.deg = deg;

@@ -59,22 +59,32 @@ cudaError_t launch_nvq_encode(const float *rows_dev, long long n, int row_stride
                               const float *mean_dev, int learn, float *params_dev, uint8_t *bytes_dev, int byte_stride, cudaStream_t s);
 
 // ---- search.cu ----
+constexpr int MAX_LIST_CAP = 8192;  // longest candidate list (entries) the search kernel keeps in shared memory
 struct SearchPlan {
     int threads;
     size_t smem_bytes;
     int ctas;
-    int list_cap;     // rerankK rounded
+    int list_cap;     // entries the candidate list retains: rerankK + room for a tie tail
+    int list_alloc;   // entries per list buffer (>= list_cap, >= sort_pow2)
+    int sort_pow2;    // next power of two >= rerankK
     int visited_cap;  // power of two
     int blob_in_global;  // PQ LUT kept in an L2-resident global slice per CTA instead of shared memory
     int blob_floats;
 };
+// acceptOrds / threshold / rerankFloor of GraphSearcher.search (base:graph/GraphSearcher.java:166-181,427-431, NodeQueue.java:168-230)
+struct SearchFilter {
+    const uint32_t *accept_bits;    // device; bit (node & 31) of word (node >> 5) set = acceptable; nullptr = Bits.ALL
+    long long accept_stride_words;  // words between the bitsets of two queries; 0 = one bitset shared by the whole batch
+    float threshold;                // minimum approximate score of a result; 0 = none
+    float rerank_floor;             // NodeQueue.rerank's rerankFloor; 0 = none
+};
 cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const GraphDesc &g, int topK, int rerankK, int nq,
-                        int visited_cap_hint, int sm_count, SearchPlan *plan);
+                        int visited_cap_hint, int list_cap_hint, int sm_count, SearchPlan *plan);
 size_t search_scratch_bytes(const SearchPlan &p);
 cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const DataDesc *rerank, int metric, const float *queries_dev,
                           int nq, int topK, int rerankK, const SearchPlan &plan, void *scratch_dev, int *work_counter_dev,
                           int32_t *nodes_out_dev, float *scores_out_dev, SearchCounters *counters_dev, uint8_t *overflow_flags_dev,
-                          const int32_t *query_index_dev, int query_stride, cudaStream_t s);
+                          const int32_t *query_index_dev, int query_stride, const SearchFilter *filter, cudaStream_t s);
 
 // ---- build.cu ----
 struct BuildParams {

@@ -32,7 +32,9 @@ struct SearchParams {
     const float *queries;
     int query_stride;
     int nq, topK, rerankK;
-    int list_pow2;  // list buffers hold this many keys (>= rerankK, power of two)
+    int list_cap;    // entries the candidate list retains (>= rerankK; the slack holds the tie tail)
+    int list_alloc;  // entries per list buffer (>= list_cap and >= sort_pow2)
+    int sort_pow2;   // next power of two >= rerankK (bitonic sort of the result heap)
     int visited_cap;
     int visited_shift;
     int32_t *visited_tables;
@@ -44,6 +46,11 @@ struct SearchParams {
     const int32_t *query_index;
     int blobA_floats, blobR_floats;
     float *blob_global;  // PQ "LUT in L2" mode: per-CTA slices of global scratch hold the prepared query instead of shared memory
+    // acceptOrds / threshold / rerankFloor of GraphSearcher.search(sp, topK, rerankK, threshold, rerankFloor, acceptOrds)
+    const uint32_t *accept_bits;  // bit (node & 31) of word (node >> 5); nullptr = Bits.ALL
+    long long accept_stride;      // words between two queries' bitsets (0 = one bitset shared by the batch)
+    float threshold, rerank_floor;
+    int filtered;                 // accept_bits != nullptr || threshold > 0
     unsigned long long *dbg;  // JV_SEARCH_PROFILE builds only: per-phase cycle totals
 };
 
@@ -88,6 +95,37 @@ __device__ __forceinline__ void bitonic_sort_desc_block(long long *keys, int n_p
     }
 }
 
+// The reference's result queue is a BoundedLongHeap (min-heap of keys, 1-based array): its ARRAY ORDER decides which of two
+// equal exact scores survives NodeQueue.rerank, so the device keeps the same array with the same sift procedures
+// (base:util/AbstractLongHeap.java:158-187 upHeap / downHeap, base:util/BoundedLongHeap.java:60-70,100-104 push / updateTop).
+__device__ __forceinline__ void heap_up(long long *h, int pos)
+{
+    int i = pos;
+    const long long v = h[i];
+    int j = i >> 1;
+    while (j > 0 && v < h[j]) {
+        h[i] = h[j];
+        i = j;
+        j >>= 1;
+    }
+    h[i] = v;
+}
+__device__ __forceinline__ void heap_down(long long *h, int size, int pos)
+{
+    int i = pos;
+    const long long v = h[i];
+    int j = i << 1, k = j + 1;
+    if (k <= size && h[k] < h[j]) j = k;
+    while (j <= size && h[j] < v) {
+        h[i] = h[j];
+        i = j;
+        j = i << 1;
+        k = j + 1;
+        if (k <= size && h[k] < h[j]) j = k;
+    }
+    h[i] = v;
+}
+
 #ifndef JV_SEARCH_THREADS
 #define JV_SEARCH_THREADS 256
 #endif
@@ -98,6 +136,7 @@ __device__ __forceinline__ void bitonic_sort_desc_block(long long *keys, int n_p
 #define JV_SEARCH_MINB_PQ 6  // tools/sweep_pq_minb.sh: 5 -> 777k q/s, 6 -> 817k, 8 -> 592k (c3, LUT in L2)
 #endif
 constexpr int SEARCH_THREADS = JV_SEARCH_THREADS;
+constexpr int HEAP_TID = SEARCH_THREADS - 32;  // the thread that maintains the result heap (lane 0 of the last warp)
 
 // optional phase timers (tools/: build with JV_NVCC_EXTRA=-DJV_SEARCH_PROFILE); compiled out of the product build
 #ifdef JV_SEARCH_PROFILE
@@ -108,6 +147,21 @@ constexpr int SEARCH_THREADS = JV_SEARCH_THREADS;
 #define JV_ACC(slot, a, b)
 #endif
 
+// flags of a list entry
+constexpr uint8_t F_EXPANDED = 1;  // popped from the candidate queue at this level
+constexpr uint8_t F_ACCEPTED = 2;  // acceptOrds.get(node) && score >= threshold (what addTopCandidate requires at level 0)
+
+// State per query (see the file header). The traversal is EXACTLY the reference's, ties included:
+//   candidates  = the unexpanded entries of ONE list sorted by the reference key (pop order = the max-heap's pop order);
+//   results     = `heap`, the reference's BoundedLongHeap of the best rerankK (1 on upper levels) popped nodes, same array order;
+//   stopSearch  = results full && score(best candidate) < score(worst result)  (GraphSearcher.java:355-361, strict);
+//   addTopCandidate = push while not full, replace the worst when strictly better, otherwise (tie with the worst) expand the
+//                 node without adding it (GraphSearcher.java:520-530);
+//   a list entry may be dropped when at least rerankK accepted entries score STRICTLY higher (it can never be popped before
+//   stopSearch fires); the list keeps `list_cap` >= rerankK entries so a tie tail survives, and a query whose tail does not fit
+//   is re-run by the host with a larger list (overflow code 2), never answered approximately;
+//   upper levels: a node refused by addTopCandidate is neither a result nor evicted, so it is removed from the list at once
+//   (setEntryPointsFromPreviousLayer re-queues results + evicted only, GraphSearcher.java:316-323).
 template <int KIND, int METRIC>
 __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_MINB_PQ : JV_SEARCH_MINB)) graph_search_kernel(SearchParams P)
 {
@@ -117,18 +171,20 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
     float *blobA = P.blob_global ? P.blob_global + (size_t)blockIdx.x * P.blobA_floats : reinterpret_cast<float *>(smem_raw);
     float *blobR = reinterpret_cast<float *>(smem_raw) + (P.blob_global ? 0 : P.blobA_floats);
     long long *keys0 = reinterpret_cast<long long *>(blobR + P.blobR_floats);
-    long long *keys1 = keys0 + P.list_pow2;
-    long long *cand_keys = keys1 + P.list_pow2;
-    int32_t *cand_ids = reinterpret_cast<int32_t *>(cand_keys + MAX_DEGREE);
-    uint8_t *flags0 = reinterpret_cast<uint8_t *>(cand_ids + MAX_DEGREE);
-    uint8_t *flags1 = flags0 + P.list_pow2;
+    long long *keys1 = keys0 + P.list_alloc;
+    long long *cand_keys = keys1 + P.list_alloc;
+    long long *heap = cand_keys + MAX_DEGREE;  // 1-based, rerankK entries
+    int32_t *cand_ids = reinterpret_cast<int32_t *>(heap + ((P.rerankK + 2) & ~1));
+    uint8_t *cand_acc = reinterpret_cast<uint8_t *>(cand_ids + MAX_DEGREE);
+    uint8_t *flags0 = cand_acc + MAX_DEGREE;
+    uint8_t *flags1 = flags0 + P.list_alloc;
     __shared__ float red[36];
-    __shared__ int s_q, s_n;
+    __shared__ int s_q, s_n, s_hsize, s_drop, s_cnt;
     __shared__ int s_posv[2];
 
     const int tid = threadIdx.x;
     const int group = tid / G, lane = tid % G;
-    const int L = P.rerankK;
+    const int L = P.rerankK, LC = P.list_cap;
     const unsigned vmask = (unsigned)P.visited_cap - 1u;
     int32_t *table = P.visited_tables + (size_t)blockIdx.x * P.visited_cap;
     const int degree = P.g.degree;
@@ -140,6 +196,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
         if (wq >= P.nq) break;
         const int qi = P.query_index ? P.query_index[wq] : wq;
         const float *q = P.queries + (size_t)qi * P.query_stride;
+        const uint32_t *acc = P.accept_bits ? P.accept_bits + (size_t)qi * P.accept_stride : nullptr;
 #ifdef JV_SEARCH_PROFILE
         unsigned long long dbg_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
@@ -161,30 +218,40 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
         if (group == 0) {
             const float sc = score_row<KIND, METRIC>(P.approx, blobA, P.g.entry_node, lane);
             if (lane == 0) {
-                cur[0] = topk_key(sc, P.g.entry_node);
-                visited_insert(table, vmask, P.visited_shift, P.g.entry_node);
+                const int32_t en = P.g.entry_node;
+                cur[0] = topk_key(sc, en);
+                fcur[0] = ((!acc || ((acc[en >> 5] >> (en & 31)) & 1u)) && sc >= P.threshold) ? F_ACCEPTED : 0;
+                visited_insert(table, vmask, P.visited_shift, en);
             }
         }
         int size = 1;
         int table_cnt = 1;
         unsigned visited = 0, expanded = 0, expanded_base = 0;
-        bool failed = false;
+        int failed = 0;  // 1: visited table full, 2: candidate list too short for a tie tail
         __syncthreads();
 
         for (int lvl = P.g.entry_level; lvl >= 0 && !failed; --lvl) {
             const int K = lvl > 0 ? 1 : L;
-            // a new level: every seen node is a candidate again (setEntryPointsFromPreviousLayer), so the first unexpanded
-            // entry is entry 0. s_posv[sel] = first unexpanded position inside the window, maintained by the merge.
-            for (int i = tid; i < size; i += SEARCH_THREADS) fcur[i] = 0;
+            // a new level: results + evicted are candidates again (setEntryPointsFromPreviousLayer), the result heap is empty
+            for (int i = tid; i < size; i += SEARCH_THREADS) fcur[i] &= F_ACCEPTED;
             int sel = 0;
-            if (tid == 0) { s_posv[0] = 0; s_posv[1] = INT_MAX; s_n = 0; }
+            if (tid == 0) { s_posv[0] = 0; s_posv[1] = INT_MAX; s_n = 0; s_hsize = 0; s_drop = INT_MIN; s_cnt = 0; }
             __syncthreads();
             for (;;) {
-                const int p = s_posv[sel];
-                if (p == INT_MAX) break;  // stopSearch: every node of the best-K window is expanded
+                const int p = s_posv[sel];  // first unexpanded entry = the top of the candidate queue
+                if (p == INT_MAX) break;    // candidates.size() == 0
                 JV_T(t_i0);
-                const int node = key_node(cur[p]);
-                if (tid == 0) { fcur[p] = 1; s_posv[sel ^ 1] = INT_MAX; }
+                const long long ckey = cur[p];
+                const int hs = s_hsize;
+                const float csc = key_score(ckey);
+                const float wsc = hs > 0 ? key_score(heap[1]) : 0.f;
+                if (hs >= K && csc < wsc) break;  // stopSearch (strict <: a tie with the worst result is still expanded)
+                const int node = key_node(ckey);
+                // addTopCandidate: 1 push, 2 replace the worst, 3 tie with the worst: not added, 0 not acceptable (level 0 only)
+                int action = 0;
+                if (lvl > 0 || (fcur[p] & F_ACCEPTED)) action = hs < K ? 1 : (csc > wsc ? 2 : 3);
+                const int dead = (lvl > 0 && action == 3) ? p : -1;
+                if (tid == 0) { fcur[p] |= F_EXPANDED; s_posv[sel ^ 1] = INT_MAX; }
                 expanded++;
                 if (lvl == 0) expanded_base++;
                 const int32_t *nb;
@@ -207,7 +274,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
                     const int w = tid >> 5;
                     if (w >= 1 && w <= 3) {
                         const int pp = p + w;
-                        if (pp < size && !fcur[pp]) {
+                        if (pp < size && !(fcur[pp] & F_EXPANDED)) {
                             const int32_t *nb2 = P.g.adj0 + (size_t)key_node(cur[pp]) * degree;
                             for (int t = tid & 31; t < degree; t += 32) {
                                 const int32_t f = __ldg(nb2 + t);
@@ -227,9 +294,21 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
                 __syncthreads();
                 JV_T(t_i1);
                 JV_ACC(1, t_i0, t_i1);
+                // every thread has read the heap top by now: apply addTopCandidate to the result heap
+                if (tid == HEAP_TID) {
+                    if (action == 1) {
+                        heap[hs + 1] = ckey;
+                        heap_up(heap, hs + 1);
+                        s_hsize = hs + 1;
+                    } else if (action == 2) {
+                        heap[1] = ckey;
+                        heap_down(heap, hs, 1);
+                    }
+                }
+                if (tid == 0) { s_drop = INT_MIN; s_cnt = 0; }
                 const int n = s_n;
                 table_cnt += n;
-                if (table_cnt * 2 > P.visited_cap) { failed = true; break; }
+                if (table_cnt * 2 > P.visited_cap) { failed = 1; break; }
                 if (KIND == KIND_F32) {
                     // two rows per warp at a time: twice the loads in flight, query fragment read once
                     for (int i = group; i < n; i += 2 * NG) {
@@ -241,13 +320,20 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
                         if (lane == 0) {
                             cand_keys[i] = topk_key(sa, fa);
                             if (two) cand_keys[i + NG] = topk_key(sb, fb);
+                            if (P.filtered) {
+                                cand_acc[i] = ((!acc || ((acc[fa >> 5] >> (fa & 31)) & 1u)) && sa >= P.threshold) ? F_ACCEPTED : 0;
+                                if (two) cand_acc[i + NG] = ((!acc || ((acc[fb >> 5] >> (fb & 31)) & 1u)) && sb >= P.threshold) ? F_ACCEPTED : 0;
+                            }
                         }
                     }
                 } else {
                     for (int i = group; i < n; i += NG) {
                         const int32_t f = cand_ids[i];
                         const float sc = score_row<KIND, METRIC>(P.approx, blobA, f, lane);
-                        if (lane == 0) cand_keys[i] = topk_key(sc, f);
+                        if (lane == 0) {
+                            cand_keys[i] = topk_key(sc, f);
+                            if (P.filtered) cand_acc[i] = ((!acc || ((acc[f >> 5] >> (f & 31)) & 1u)) && sc >= P.threshold) ? F_ACCEPTED : 0;
+                        }
                     }
                 }
                 __syncthreads();
@@ -255,41 +341,45 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
                 JV_ACC(2, t_i1, t_i2);
                 visited += n;
                 // rank-merge (old list is sorted; candidates are few): every element computes its slot directly and the
-                // first unexpanded slot of the next window falls out of the same pass
-                const int newsize = min(L, size + n);
-                const int lim = min(newsize, K);
-                int mypos = INT_MAX;
+                // first unexpanded slot of the next list falls out of the same pass. The entry at `dead` (refused on an
+                // upper level) leaves the list.
+                const int live = size - (dead >= 0 ? 1 : 0);
+                const int newsize = min(LC, live + n);
+                const long long dead_key = dead >= 0 ? cur[dead] : KEY_MIN;
+                int mypos = INT_MAX, mydrop = INT_MIN;
                 // one work item per thread: items [0, size) are old entries, [size, size + n) the new candidates, so the
                 // two kinds run on different warps instead of back to back on warp 0
                 for (int it = tid; it < size + n; it += SEARCH_THREADS) {
                     if (it < size) {
+                        if (it == dead) continue;
                         const long long k = cur[it];
                         int c = 0;
 #pragma unroll 8
                         for (int j = 0; j < n; j++) c += (cand_keys[j] > k);
-                        const int np = it + c;
-                        if (np < L) {
-                            const uint8_t fl = fcur[it];
+                        const int np = it + c - ((dead >= 0 && it > dead) ? 1 : 0);
+                        const uint8_t fl = fcur[it];
+                        if (np < LC) {
                             nxt[np] = k;
                             fnxt[np] = fl;
-                            if (!fl && np < lim) mypos = min(mypos, np);
-                        }
+                            if (!(fl & F_EXPANDED)) mypos = min(mypos, np);
+                        } else if (!(fl & F_EXPANDED) || lvl > 0) mydrop = max(mydrop, float_to_sortable(key_score(k)));
                     } else {
                         const long long k = cand_keys[it - size];
-                        int c = count_greater_desc(cur, size, k);
+                        int c = count_greater_desc(cur, size, k) - ((dead >= 0 && dead_key > k) ? 1 : 0);
 #pragma unroll 8
                         for (int jj = 0; jj < n; jj++) c += (cand_keys[jj] > k);
-                        if (c < L) {
+                        if (c < LC) {
                             nxt[c] = k;
-                            fnxt[c] = 0;
-                            if (c < lim) mypos = min(mypos, c);
+                            fnxt[c] = P.filtered ? cand_acc[it - size] : F_ACCEPTED;
+                            mypos = min(mypos, c);
                             // a new candidate that lands at the very front is the likeliest next expansion: start pulling
                             // its adjacency row towards L2 now (128 B; reads only)
                             if (c < 2 && lvl == 0) prefetch_l2(P.g.adj0 + (size_t)key_node(k) * degree);
-                        }
+                        } else mydrop = max(mydrop, float_to_sortable(key_score(k)));
                     }
                 }
                 if (mypos != INT_MAX) atomicMin(&s_posv[sel ^ 1], mypos);
+                if (mydrop != INT_MIN) atomicMax(&s_drop, mydrop);
                 if (tid == 0) s_n = 0;
                 __syncthreads();
                 JV_T(t_i3);
@@ -297,6 +387,22 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
 #ifdef JV_SEARCH_PROFILE
                 if (tid == 0) { dbg_local[5] += 1; dbg_local[6] += (unsigned long long)n; }
 #endif
+                // something fell off the end of the list: that is exact only if at least rerankK accepted entries score strictly
+                // higher than everything dropped (then none of it can be popped before stopSearch fires)
+                const int dm = s_drop;
+                if (dm != INT_MIN) {
+                    bool ok;
+                    if (!P.filtered) ok = float_to_sortable(key_score(nxt[L - 1])) > dm;  // newsize == LC >= L here
+                    else {
+                        int c = 0;
+                        for (int i = tid; i < newsize; i += SEARCH_THREADS)
+                            c += ((fnxt[i] & F_ACCEPTED) && float_to_sortable(key_score(nxt[i])) > dm) ? 1 : 0;
+                        if (c) atomicAdd(&s_cnt, c);
+                        __syncthreads();
+                        ok = s_cnt >= L;
+                    }
+                    if (!ok) { failed = 2; break; }
+                }
                 { long long *t = cur; cur = nxt; nxt = t; }
                 { uint8_t *t = fcur; fcur = fnxt; fnxt = t; }
                 size = newsize;
@@ -311,54 +417,114 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
         unsigned reranked = 0;
         if (failed) {
             for (int i = tid; i < P.topK; i += SEARCH_THREADS) { no[i] = -1; so[i] = 0.f; }
-            if (tid == 0) { P.overflow[qi] = 1; atomicAdd(&P.counters->overflowed, 1ull); }
+            if (tid == 0) { P.overflow[qi] = (uint8_t)failed; atomicAdd(&P.counters->overflowed, 1ull); }
         } else {
             if (tid == 0) P.overflow[qi] = 0;
+            const int hs = s_hsize;  // the results: heap[1 .. hs]
             if (P.has_rerank) {
-                // NodeQueue.rerank (NodeQueue.java:168-230) with rerankFloor = 0: exact-score every survivor, keep topK
+                // NodeQueue.rerank (NodeQueue.java:168-230): rescore, in HEAP-ARRAY order, the results whose approximate score
+                // is >= rerankFloor (or the single best one if none is), keep the topK best exact scores; on an exact-score
+                // tie at the topK boundary the entry met first in array order stays.
                 constexpr int NGR = SEARCH_THREADS / 32;
                 const int wgroup = tid >> 5, wlane = tid & 31;
+                if (tid == 0) s_cnt = 0;
+                __syncthreads();
+                {
+                    int c = 0;
+                    for (int i = tid; i < hs; i += SEARCH_THREADS) {
+                        const bool above = key_score(heap[1 + i]) >= P.rerank_floor;
+                        fcur[i] = above ? 1 : 0;
+                        c += above ? 1 : 0;
+                    }
+                    if (c) atomicAdd(&s_cnt, c);
+                }
+                __syncthreads();
+                int nrr = s_cnt;
+                if (nrr == 0 && hs > 0) {
+                    // nothing above the floor: the best approximate score is reranked alone (first maximum in array order)
+                    if (tid == 0) {
+                        int bi = 0;
+                        float bs = key_score(heap[1]);
+                        for (int i = 1; i < hs; i++) {
+                            const float s = key_score(heap[1 + i]);
+                            if (s > bs) { bs = s; bi = i; }
+                        }
+                        fcur[bi] = 1;
+                    }
+                    nrr = 1;
+                    __syncthreads();
+                }
                 if (KIND == KIND_PQ || KIND == KIND_BQ) {
                     // the approximate walk left HBM idle: pull every survivor's exact row towards L2 before the rescoring loop
                     const int lines = P.rerank.kind == KIND_F32 ? (P.rerank.stride * 4 + 127) / 128 : (P.rerank.byte_stride + 127) / 128;
-                    for (int t = tid; t < size * lines; t += SEARCH_THREADS) {
+                    for (int t = tid; t < hs * lines; t += SEARCH_THREADS) {
                         const int i = t / lines, l = t - i * lines;
-                        const int32_t f = key_node(cur[i]);
+                        if (!fcur[i]) continue;
+                        const int32_t f = key_node(heap[1 + i]);
                         const char *a = P.rerank.kind == KIND_F32 ? reinterpret_cast<const char *>(P.rerank.rows + (size_t)f * P.rerank.stride)
                                                                   : reinterpret_cast<const char *>(P.rerank.bytes + (size_t)f * P.rerank.byte_stride);
                         prefetch_l2(a + (size_t)l * 128);
                     }
                 }
+                // exact keys in array order -> cur[0 .. hs) (KEY_MIN = not reranked)
                 if (P.rerank.kind == KIND_F32) {
-                    for (int i = wgroup; i < size; i += 2 * NGR) {
-                        const int32_t fa = key_node(cur[i]);
-                        const bool two = i + NGR < size;
-                        const int32_t fb = two ? key_node(cur[i + NGR]) : fa;
-                        float sa, sb;
-                        score_f32_pair<METRIC>(P.rerank, blobR, fa, fb, wlane, sa, sb);
+                    for (int i = wgroup; i < hs; i += 2 * NGR) {
+                        const int32_t fa = key_node(heap[1 + i]);
+                        const bool two = i + NGR < hs;
+                        const int32_t fb = two ? key_node(heap[1 + i + NGR]) : fa;
+                        const bool da = fcur[i] != 0, db = two && fcur[i + NGR] != 0;
+                        float sa = 0.f, sb = 0.f;
+                        if (da || db) score_f32_pair<METRIC>(P.rerank, blobR, da ? fa : fb, db ? fb : fa, wlane, sa, sb);
                         if (wlane == 0) {
-                            nxt[i] = topk_key(sa, fa);
-                            if (two) nxt[i + NGR] = topk_key(sb, fb);
+                            cur[i] = da ? topk_key(sa, fa) : KEY_MIN;
+                            if (two) cur[i + NGR] = db ? topk_key(sb, fb) : KEY_MIN;
                         }
                     }
                 } else {
-                    for (int i = wgroup; i < size; i += NGR) {
-                        const int32_t f = key_node(cur[i]);
-                        const float sc = score_row<KIND_NVQ, METRIC>(P.rerank, blobR, f, wlane);
-                        if (wlane == 0) nxt[i] = topk_key(sc, f);
+                    for (int i = wgroup; i < hs; i += NGR) {
+                        const int32_t f = key_node(heap[1 + i]);
+                        float sc = 0.f;
+                        const bool d = fcur[i] != 0;
+                        if (d) sc = score_row<KIND_NVQ, METRIC>(P.rerank, blobR, f, wlane);
+                        if (wlane == 0) cur[i] = d ? topk_key(sc, f) : KEY_MIN;
                     }
                 }
-                for (int i = size + tid; i < P.list_pow2; i += SEARCH_THREADS) nxt[i] = KEY_MIN;
                 __syncthreads();
-                bitonic_sort_desc_block(nxt, P.list_pow2);
-                reranked = size;
-                for (int i = tid; i < P.topK; i += SEARCH_THREADS) {
-                    if (i < size) { no[i] = key_node(nxt[i]); so[i] = key_score(nxt[i]); }
-                    else { no[i] = -1; so[i] = 0.f; }
+                for (int i = tid; i < P.sort_pow2; i += SEARCH_THREADS) nxt[i] = i < hs ? cur[i] : KEY_MIN;
+                __syncthreads();
+                bitonic_sort_desc_block(nxt, P.sort_pow2);
+                reranked = (unsigned)nrr;
+                const bool boundary_tie = nrr > P.topK && key_score(nxt[P.topK - 1]) == key_score(nxt[P.topK]);
+                if (!boundary_tie) {
+                    for (int i = tid; i < P.topK; i += SEARCH_THREADS) {
+                        if (i < nrr) { no[i] = key_node(nxt[i]); so[i] = key_score(nxt[i]); }
+                        else { no[i] = -1; so[i] = 0.f; }
+                    }
+                } else if (tid == 0) {
+                    // replay the reference loop (NodeQueue.java:199-215) over the array order; `heap` is free to be reused
+                    long long *rh = heap;
+                    int rs = 0;
+                    for (int i = 0; i < hs; i++) {
+                        const long long v = cur[i];
+                        if (v == KEY_MIN) continue;
+                        if (rs < P.topK) { rh[++rs] = v; heap_up(rh, rs); }
+                        else if (key_score(v) > key_score(rh[1])) { rh[1] = v; heap_down(rh, rs, 1); }
+                    }
+                    for (int i = rs - 1; i >= 0; i--) {  // pop: worst first
+                        const long long v = rh[1];
+                        rh[1] = rh[rs--];
+                        if (rs > 0) heap_down(rh, rs, 1);
+                        no[i] = key_node(v);
+                        so[i] = key_score(v);
+                    }
                 }
             } else {
+                // no reranker: the best topK of the results by approximate key (GraphSearcher.java:478-486, :494-500)
+                for (int i = tid; i < P.sort_pow2; i += SEARCH_THREADS) nxt[i] = i < hs ? heap[1 + i] : KEY_MIN;
+                __syncthreads();
+                bitonic_sort_desc_block(nxt, P.sort_pow2);
                 for (int i = tid; i < P.topK; i += SEARCH_THREADS) {
-                    if (i < size) { no[i] = key_node(cur[i]); so[i] = key_score(cur[i]); }
+                    if (i < hs) { no[i] = key_node(nxt[i]); so[i] = key_score(nxt[i]); }
                     else { no[i] = -1; so[i] = 0.f; }
                 }
             }
@@ -389,14 +555,16 @@ static int next_pow2i(int v)
     return p;
 }
 
-static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, int list_pow2, bool blob_in_global)
+static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, int rerankK, int list_alloc, bool blob_in_global)
 {
     size_t b = 0;
     if (!blob_in_global) b += (size_t)blob_floats(approx) * 4;
     if (rerank) b += (size_t)blob_floats(*rerank) * 4;
-    b += (size_t)list_pow2 * 8 * 2;
-    b += (size_t)MAX_DEGREE * 8 + (size_t)MAX_DEGREE * 4;
-    b += (size_t)list_pow2 * 2;
+    b += (size_t)list_alloc * 8 * 2;                  // the two list buffers
+    b += (size_t)MAX_DEGREE * 8;                      // candidate keys of one hop
+    b += (size_t)((rerankK + 2) & ~1) * 8;            // result heap (1-based)
+    b += (size_t)MAX_DEGREE * 4 + (size_t)MAX_DEGREE; // candidate ids + accept flags
+    b += (size_t)list_alloc * 2;                      // entry flags of the two buffers
     return (b + 15) & ~(size_t)15;
 }
 
@@ -430,11 +598,21 @@ static cudaError_t occupancy_of(size_t smem, int *blocks_per_sm)
     } while (0)
 
 cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const GraphDesc &g, int topK, int rerankK, int nq,
-                        int visited_cap_hint, int sm_count, SearchPlan *plan)
+                        int visited_cap_hint, int list_cap_hint, int sm_count, SearchPlan *plan)
 {
     if (g.degree > MAX_DEGREE || rerankK < 1 || topK < 1 || topK > rerankK) return cudaErrorInvalidValue;
     plan->threads = SEARCH_THREADS;
-    plan->list_cap = next_pow2i(rerankK);
+    plan->sort_pow2 = next_pow2i(rerankK);
+    // The list keeps rerankK entries plus a tie tail (see the kernel header). Continuous scores tie rarely: the slack that
+    // rounds rerankK up to a multiple of 32 is enough; BQ scores take at most dim + 1 values, so whole groups tie at the
+    // boundary. A query whose tail does not fit reports overflow code 2 and is re-run with list_cap_hint = 4x.
+    int cap = list_cap_hint > 0 ? list_cap_hint : (approx.kind == KIND_BQ ? 2 * rerankK + 64 : rerankK + 28);
+    if (cap < rerankK) cap = rerankK;
+    cap = (cap + 3) & ~3;
+    if (cap > MAX_LIST_CAP) cap = MAX_LIST_CAP;
+    if (cap < rerankK) return cudaErrorInvalidValue;
+    plan->list_cap = cap;
+    plan->list_alloc = cap > plan->sort_pow2 ? cap : plan->sort_pow2;
     // PQ: a LUT of M*k fp32 (96 KB at M=96) in shared memory limits residency to 2 CTAs per SM, and the walk is a latency chain
     // (profiles/r1_search_phase_cycles.md). When five LUTs do not fit an SM's shared memory the LUT lives in an L2-resident
     // global slice per CTA instead: residency becomes register-limited (5 CTAs per SM) and the gathers are served by L2.
@@ -447,12 +625,16 @@ cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const Gr
         else plan->blob_in_global = (size_t)blob_floats(approx) * 4 * 5 > 200 * 1024 ? 1 : 0;
     }
     plan->blob_floats = blob_floats(approx);
-    plan->smem_bytes = search_smem_bytes(approx, rerank, plan->list_cap, plan->blob_in_global != 0);
+    plan->smem_bytes = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, plan->blob_in_global != 0);
+    if (plan->smem_bytes > 227 * 1024 && approx.kind == KIND_PQ && !plan->blob_in_global) {
+        plan->blob_in_global = 1;  // a long list next to a LUT: keep the list in shared memory, move the LUT to L2
+        plan->smem_bytes = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, true);
+    }
     if (plan->smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
-    int cap = visited_cap_hint > 0 ? visited_cap_hint : next_pow2i(4 * rerankK * (g.degree > 16 ? g.degree : 16));
-    if (cap < 2048) cap = 2048;
-    if (cap > (1 << 22)) cap = 1 << 22;
-    plan->visited_cap = next_pow2i(cap);
+    int vcap = visited_cap_hint > 0 ? visited_cap_hint : next_pow2i(4 * rerankK * (g.degree > 16 ? g.degree : 16));
+    if (vcap < 2048) vcap = 2048;
+    if (vcap > (1 << 22)) vcap = 1 << 22;
+    plan->visited_cap = next_pow2i(vcap);
     int bps = 0;
     cudaError_t e = cudaSuccess;
     const int metric_for_occ = JV_METRIC_DOT;
@@ -478,10 +660,15 @@ size_t search_scratch_bytes(const SearchPlan &p)
 cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const DataDesc *rerank, int metric, const float *queries_dev,
                           int nq, int topK, int rerankK, const SearchPlan &plan, void *scratch_dev, int *work_counter_dev,
                           int32_t *nodes_out_dev, float *scores_out_dev, SearchCounters *counters_dev, uint8_t *overflow_flags_dev,
-                          const int32_t *query_index_dev, int query_stride, cudaStream_t s)
+                          const int32_t *query_index_dev, int query_stride, const SearchFilter *filter, cudaStream_t s)
 {
     if (nq <= 0) return cudaSuccess;
     SearchParams P;
+    P.accept_bits = filter ? filter->accept_bits : nullptr;
+    P.accept_stride = filter ? filter->accept_stride_words : 0;
+    P.threshold = filter ? filter->threshold : 0.f;
+    P.rerank_floor = filter ? filter->rerank_floor : 0.f;
+    P.filtered = (P.accept_bits != nullptr || P.threshold > 0.f) ? 1 : 0;
     P.query_stride = query_stride > 0 ? query_stride : approx.dim;
     P.g = g;
     P.approx = approx;
@@ -492,7 +679,9 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
     P.nq = nq;
     P.topK = topK;
     P.rerankK = rerankK;
-    P.list_pow2 = plan.list_cap;
+    P.list_cap = plan.list_cap;
+    P.list_alloc = plan.list_alloc;
+    P.sort_pow2 = plan.sort_pow2;
     P.visited_cap = plan.visited_cap;
     int lg = 0;
     while ((1 << lg) < plan.visited_cap) lg++;

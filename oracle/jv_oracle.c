@@ -424,8 +424,55 @@ void jvo_nvq_cosine_8bit(const float *q, const uint8_t *b, int n, float alpha, f
     out2[1] = nm;
 }
 
+/* ---- the loss sums under an explicit summation order ------------------------------------------------------------------
+ * The reference defines nvqLoss / nvqUniformLoss only up to the order of the float additions: the scalar provider sums
+ * sequentially (base:vector/DefaultVectorUtilSupport.java:493-520), the Panama provider keeps SPECIES_PREFERRED lane
+ * accumulators (element i goes to lane i mod lanes) and then reduceLanes (jvector-twenty/.../PanamaVectorUtilSupport.java:
+ * 1270-1330), the native provider does the same with Highway lanes (native-c:src/jvector_simd_kernels.cpp:1199-1303).
+ * `lanes` selects a member of that family: 1 = sequential (the functions above); 32 = thirty-two strided accumulators folded
+ * by a xor butterfly (16, 8, 4, 2, 1), which is the order a 32-lane GPU warp produces. The growth-rate grid search compares
+ * these sums, so bit-exact parameters need the same order on both sides; all orders agree to ~1e-6 relative (tests). */
+static float lanes_fold(float *acc, int lanes)
+{
+    float tmp[64];
+    for (int o = lanes >> 1; o > 0; o >>= 1) {
+        for (int l = 0; l < lanes; l++) tmp[l] = acc[l] + acc[l ^ o];
+        memcpy(acc, tmp, sizeof(float) * (size_t)lanes);
+    }
+    return acc[0];
+}
+
+float jvo_nvq_loss_lanes(const float *v, int n, float alpha, float x0, float minv, float maxv, int nbits, int lanes)
+{
+    if (lanes <= 1) return jvo_nvq_loss(v, n, alpha, x0, minv, maxv, nbits);
+    float levels = (float)((1 << nbits) - 1);
+    nvq_consts c = nvq_setup(alpha, x0, minv, maxv, levels);
+    float inv = 1.0f / c.scale, acc[64] = {0};
+    for (int i = 0; i < n; i++) {
+        float r = (jvo_nvq_logistic(v[i], c.sa, c.sx0) - c.bias) * inv;
+        float rq = (float)(int)(r + 0.5f);
+        float d = v[i] - nvq_dq(&c, rq);
+        acc[i % lanes] = fmaf(d, d, acc[i % lanes]);
+    }
+    return lanes_fold(acc, lanes);
+}
+
+float jvo_nvq_uniform_loss_lanes(const float *v, int n, float minv, float maxv, int nbits, int lanes)
+{
+    if (lanes <= 1) return jvo_nvq_uniform_loss(v, n, minv, maxv, nbits);
+    float constant = (float)((1 << nbits) - 1), delta = maxv - minv, acc[64] = {0};
+    for (int i = 0; i < n; i++) {
+        float r = (v[i] - minv) * (constant / delta);
+        float rq = (float)(int)(r + 0.5f);
+        float rec = fmaf(rq, delta / constant, minv);
+        float d = v[i] - rec;
+        acc[i % lanes] = fmaf(d, d, acc[i % lanes]);
+    }
+    return lanes_fold(acc, lanes);
+}
+
 /* base:quantization/NVQuantization.java:524-578 (parameter search) */
-void jvo_nvq_encode_subvector(const float *v, int n, int learn, float *params_out, uint8_t *bytes_out)
+void jvo_nvq_encode_subvector_lanes(const float *v, int n, int learn, int lanes, float *params_out, uint8_t *bytes_out)
 {
     float minv = 3.402823466e+38f, maxv = -3.402823466e+38f;
     for (int i = 0; i < n; i++) {
@@ -434,15 +481,15 @@ void jvo_nvq_encode_subvector(const float *v, int n, int learn, float *params_ou
     }
     float growth = 1e-2f, mid = 0.f;
     if (learn) {
-        float baseline = jvo_nvq_uniform_loss(v, n, minv, maxv, 8);
+        float baseline = jvo_nvq_uniform_loss_lanes(v, n, minv, maxv, 8, lanes);
         float coarse = 1e-2f, best = 1.40129846e-45f; /* Float.MIN_VALUE */
         for (float gr = 1e-6f; gr < 20.f; gr += 1.f) {
-            float lv = baseline / jvo_nvq_loss(v, n, gr, 0.f, minv, maxv, 8);
+            float lv = baseline / jvo_nvq_loss_lanes(v, n, gr, 0.f, minv, maxv, 8, lanes);
             if (lv > best) { best = lv; coarse = gr; }
         }
         float fine = coarse;
         for (float gr = coarse - 1; gr < coarse + 1; gr += 0.1f) {
-            float lv = baseline / jvo_nvq_loss(v, n, gr, 0.f, minv, maxv, 8);
+            float lv = baseline / jvo_nvq_loss_lanes(v, n, gr, 0.f, minv, maxv, 8, lanes);
             if (lv > best) { best = lv; fine = gr; }
         }
         growth = fine;
@@ -451,16 +498,26 @@ void jvo_nvq_encode_subvector(const float *v, int n, int learn, float *params_ou
     params_out[0] = minv; params_out[1] = maxv; params_out[2] = growth; params_out[3] = mid;
 }
 
+void jvo_nvq_encode_subvector(const float *v, int n, int learn, float *params_out, uint8_t *bytes_out)
+{
+    jvo_nvq_encode_subvector_lanes(v, n, learn, 1, params_out, bytes_out);
+}
+
 /* base:quantization/NVQuantization.java:201-251 */
-void jvo_nvq_encode(const float *v, const float *mean, int dim, int nsub, int learn, float *params_out, uint8_t *bytes_out)
+void jvo_nvq_encode_lanes(const float *v, const float *mean, int dim, int nsub, int learn, int lanes, float *params_out, uint8_t *bytes_out)
 {
     int *sizes = (int *)malloc(sizeof(int) * nsub * 2), *offsets = sizes + nsub;
     float *c = (float *)malloc(sizeof(float) * dim);
     jvo_pq_layout(dim, nsub, sizes, offsets);
     for (int i = 0; i < dim; i++) c[i] = v[i] - mean[i];
-    for (int s = 0; s < nsub; s++) jvo_nvq_encode_subvector(c + offsets[s], sizes[s], learn, params_out + 4 * s, bytes_out + offsets[s]);
+    for (int s = 0; s < nsub; s++) jvo_nvq_encode_subvector_lanes(c + offsets[s], sizes[s], learn, lanes, params_out + 4 * s, bytes_out + offsets[s]);
     free(c);
     free(sizes);
+}
+
+void jvo_nvq_encode(const float *v, const float *mean, int dim, int nsub, int learn, float *params_out, uint8_t *bytes_out)
+{
+    jvo_nvq_encode_lanes(v, mean, dim, nsub, learn, 1, params_out, bytes_out);
 }
 
 /* base:quantization/NVQScorer.java:46-137 */
@@ -571,6 +628,146 @@ const char *jvo_ref_isa(void) { return REF.isa ? REF.isa() : "port"; }
  * (base:graph/similarity/DefaultSearchScoreProvider.java:71-80, base:quantization/PQDecoder.java,
  *  BQVectors.java:108-118, NVQScorer.java)
  * ========================================================================================== */
+/* ============================================================================================
+ * WARP-ORDER restatements. The float sums of the path are defined up to the order of the additions (the scalar
+ * provider sums sequentially, Panama keeps 2 vector accumulators, the native library 4 Highway accumulators; the reference's
+ * tests accept 1e-4). A traversal, however, is only reproducible id for id when both sides produce the SAME bits, so the
+ * oracle can also evaluate every score in the one order the sm_100a kernels use (jvector_b200/csrc/scorers.cuh): elements
+ * dealt to 32 (fp32 rows, NVQ bytes) or 8 (PQ code rows) lane accumulators, fused multiply-adds, lanes folded by a xor
+ * butterfly; block-wide sums (query norms) over 256 strided accumulators folded warp by warp. Same arithmetic, same formulas
+ * (cited at each function), one fixed member of the family of orders the reference itself ships.
+ * jvo_scorer_set_order(s, 1) switches a scorer to it; order 0 (default) is the sequential / reference-kernel arithmetic.
+ * ========================================================================================== */
+static float block256_sum(const float *acc /* 256 */)
+{
+    float red[32];
+    for (int w = 0; w < 32; w++) red[w] = 0.f;
+    for (int w = 0; w < 8; w++) {
+        float lanes[32];
+        memcpy(lanes, acc + 32 * w, sizeof(lanes));
+        red[w] = lanes_fold(lanes, 32);
+    }
+    return lanes_fold(red, 32);
+}
+
+/* prepare_blob's ||q||^2-style sums: element i goes to accumulator i mod 256 */
+static float block256_dot(const float *a, const float *b, int n)
+{
+    float acc[256] = {0};
+    for (int i = 0; i < n; i++) acc[i & 255] = fmaf(a[i], b[i], acc[i & 255]);
+    return block256_sum(acc);
+}
+
+/* score_f32_vec / score_f32_pair: float4 j of the row goes to lane j mod 32; four accumulators per lane (x, y, z, w) */
+static float warp_raw_f32(int metric, const float *q, const float *row, int dim, float qnorm2)
+{
+    float s[32][4] = {{0}}, b0[32] = {0}, b1[32] = {0}, lanes[32];
+    for (int i = 0; i < dim; i++) {
+        const int l = (i >> 2) & 31, c = i & 3;
+        if (metric == JVO_EUCLIDEAN) {
+            float d = q[i] - row[i];
+            s[l][c] = fmaf(d, d, s[l][c]);
+        } else {
+            s[l][c] = fmaf(q[i], row[i], s[l][c]);
+            if (metric == JVO_COSINE) {
+                if (c & 1) b1[l] = fmaf(row[i], row[i], b1[l]);
+                else b0[l] = fmaf(row[i], row[i], b0[l]);
+            }
+        }
+    }
+    for (int l = 0; l < 32; l++) lanes[l] = (s[l][0] + s[l][1]) + (s[l][2] + s[l][3]);
+    float r = lanes_fold(lanes, 32);
+    if (metric == JVO_COSINE) {
+        for (int l = 0; l < 32; l++) lanes[l] = b0[l] + b1[l];
+        r = r / sqrtf(qnorm2 * lanes_fold(lanes, 32));
+    }
+    return r;
+}
+
+float jvo_compare_f32_warp(int metric, const float *q, const float *row, int dim)
+{
+    return jvo_score_from_raw(metric, warp_raw_f32(metric, q, row, dim, metric == JVO_COSINE ? block256_dot(q, q, dim) : 0.f));
+}
+
+/* prepare_blob (PQ branch) and pq_self_mag_kernel: every table entry is one sequential fused chain over the sub-vector */
+static void warp_pq_tables(const float *codebooks, const int *sizes, const int *offsets, int M, int k, const float *centroid,
+                           const float *q, int dim, int metric, float *lut, float *mag, float *bMag)
+{
+    float *c = (float *)malloc(sizeof(float) * dim);
+    for (int i = 0; i < dim; i++) c[i] = centroid ? q[i] - centroid[i] : q[i];
+    for (int m = 0; m < M; m++) {
+        const float *cb = cb_of(codebooks, offsets, k, m);
+        for (int j = 0; j < k; j++) {
+            const float *cen = cb + (size_t)j * sizes[m];
+            float t = 0.f, g = 0.f;
+            for (int e = 0; e < sizes[m]; e++) {
+                if (metric == JVO_EUCLIDEAN) {
+                    float d = cen[e] - c[offsets[m] + e];
+                    t = fmaf(d, d, t);
+                } else t = fmaf(cen[e], c[offsets[m] + e], t);
+                g = fmaf(cen[e], cen[e], g);
+            }
+            lut[m * k + j] = t;
+            if (mag) mag[m * k + j] = g;
+        }
+    }
+    *bMag = block256_dot(c, c, dim);
+    free(c);
+}
+
+/* score_pq: 32-bit word j of the code row (4 codes) goes to lane j mod 8, its 4 entries added in code order; a tail of
+ * M mod 4 codes goes one code per lane */
+static float warp_pq_score(int metric, const float *lut, const float *mag, float bMag, int k, const uint8_t *codes, int M)
+{
+    float s[8] = {0}, a[8] = {0};
+    const int M4 = M >> 2;
+    for (int j = 0; j < M4; j++)
+        for (int e = 0; e < 4; e++) {
+            const int m = 4 * j + e, idx = m * k + codes[m];
+            s[j & 7] = s[j & 7] + lut[idx];
+            if (metric == JVO_COSINE) a[j & 7] = a[j & 7] + mag[idx];
+        }
+    for (int m = 4 * M4; m < M; m++) {
+        const int g = (m - 4 * M4) & 7, idx = m * k + codes[m];
+        s[g] = s[g] + lut[idx];
+        if (metric == JVO_COSINE) a[g] = a[g] + mag[idx];
+    }
+    float r = lanes_fold(s, 8);
+    if (metric == JVO_COSINE) r = r / sqrtf(lanes_fold(a, 8) * bMag);
+    return jvo_score_from_raw(metric, r);
+}
+
+/* score_nvq: one accumulator per lane across all sub-vectors; a sub-vector whose offset and size are multiples of 4 is dealt
+ * four bytes at a time (word j to lane j mod 32), otherwise byte i to lane i mod 32 */
+static float warp_nvq_score(int metric, const float *qs /* shifted for L2 */, const float *mean, int nsub, const int *sizes,
+                            const int *offsets, const float *params, const uint8_t *bytes, float qbias, float qnorm)
+{
+    float s[32] = {0}, nm[32] = {0};
+    for (int sv = 0; sv < nsub; sv++) {
+        const float *pp = params + 4 * sv;
+        nvq_consts c = nvq_setup(pp[2], pp[3], pp[0], pp[1], 255.0f);
+        const int off = offsets[sv], sz = sizes[sv], vec = ((off | sz) & 3) == 0;
+        for (int i = 0; i < sz; i++) {
+            const int l = vec ? ((i >> 2) & 31) : (i & 31);
+            const float dq = nvq_dq(&c, (float)bytes[off + i]), q = qs[off + i];
+            if (metric == JVO_DOT_PRODUCT) s[l] = fmaf(q, dq, s[l]);
+            else if (metric == JVO_EUCLIDEAN) {
+                float d = q - dq;
+                s[l] = fmaf(d, d, s[l]);
+            } else {
+                float e = dq + mean[off + i];
+                s[l] = fmaf(q, e, s[l]);
+                nm[l] = fmaf(e, e, nm[l]);
+            }
+        }
+    }
+    float r = lanes_fold(s, 32);
+    if (metric == JVO_DOT_PRODUCT) return ((1.0f + r) + qbias) / 2.0f;
+    if (metric == JVO_EUCLIDEAN) return 1.0f / (1.0f + r);
+    float cosine = (r / qnorm) / sqrtf(lanes_fold(nm, 32));
+    return (1.0f + cosine) / 2.0f;
+}
+
 struct jvo_scorer {
     int kind; /* 0 f32, 1 pq, 2 bq, 3 nvq */
     int metric, dim;
@@ -594,7 +791,32 @@ struct jvo_scorer {
     const float *mean;
     float *mean_sh; /* shuffled copy of mean sub-vectors (cosine, ref path) */
     float qbias, qnorm;
+    /* warp order (jvo_scorer_set_order) */
+    int order;
+    const float *codebooks, *centroid;
+    float *q_raw;               /* the query as given */
+    float *wlut, *wmag, wbMag;  /* PQ tables in warp order */
+    float *wq, wqbias, wqnorm;  /* NVQ prepared query in warp order */
 };
+
+void jvo_scorer_set_order(jvo_scorer *s, int order)
+{
+    s->order = order;
+    if (!order) return;
+    if (s->kind == 1 && !s->wlut) {
+        s->wlut = (float *)malloc(sizeof(float) * s->M * s->k);
+        s->wmag = (float *)malloc(sizeof(float) * s->M * s->k);
+        warp_pq_tables(s->codebooks, s->sizes, s->offsets, s->M, s->k, s->centroid, s->q_raw, s->dim,
+                       s->metric == JVO_EUCLIDEAN ? JVO_EUCLIDEAN : JVO_DOT_PRODUCT, s->wlut, s->wmag, &s->wbMag);
+    }
+    if (s->kind == 3 && !s->wq) {
+        /* prepare_blob (NVQ branch): DOT keeps q and adds <q, mean>; L2 shifts q by the mean; COSINE keeps q and needs ||q|| */
+        s->wq = (float *)malloc(sizeof(float) * s->dim);
+        for (int i = 0; i < s->dim; i++) s->wq[i] = s->metric == JVO_EUCLIDEAN ? s->q_raw[i] - s->mean[i] : s->q_raw[i];
+        s->wqbias = block256_dot(s->q_raw, s->mean, s->dim);
+        s->wqnorm = sqrtf(block256_dot(s->q_raw, s->q_raw, s->dim));
+    }
+}
 
 jvo_scorer *jvo_scorer_f32(int metric, const float *base, int64_t n, int dim, const float *q)
 {
@@ -602,6 +824,7 @@ jvo_scorer *jvo_scorer_f32(int metric, const float *base, int64_t n, int dim, co
     s->kind = 0; s->metric = metric; s->dim = dim; s->n = n; s->base = base;
     s->q = (float *)malloc(sizeof(float) * dim);
     memcpy(s->q, q, sizeof(float) * dim);
+    s->wqnorm = block256_dot(q, q, dim);
     return s;
 }
 
@@ -610,6 +833,9 @@ jvo_scorer *jvo_scorer_pq(int metric, const float *codebooks, int M, int k, int 
 {
     jvo_scorer *s = (jvo_scorer *)calloc(1, sizeof(*s));
     s->kind = 1; s->metric = metric; s->dim = dim; s->n = n; s->M = M; s->k = k; s->codes = codes;
+    s->codebooks = codebooks; s->centroid = centroid;
+    s->q_raw = (float *)malloc(sizeof(float) * dim);
+    memcpy(s->q_raw, q, sizeof(float) * dim);
     s->sizes = (int *)malloc(sizeof(int) * 2 * M);
     s->offsets = s->sizes + M;
     jvo_pq_layout(dim, M, s->sizes, s->offsets);
@@ -659,6 +885,8 @@ jvo_scorer *jvo_scorer_nvq(int metric, const float *mean, int dim, int nsub, con
     s->sizes = (int *)malloc(sizeof(int) * 2 * nsub);
     s->offsets = s->sizes + nsub;
     jvo_pq_layout(dim, nsub, s->sizes, s->offsets);
+    s->q_raw = (float *)malloc(sizeof(float) * dim);
+    memcpy(s->q_raw, q, sizeof(float) * dim);
     s->q = (float *)malloc(sizeof(float) * dim);
     for (int i = 0; i < dim; i++) s->q[i] = metric == JVO_EUCLIDEAN ? q[i] - mean[i] : q[i];
     s->qbias = jvo_dot_f32(q, mean, dim);
@@ -676,6 +904,15 @@ jvo_scorer *jvo_scorer_nvq(int metric, const float *mean, int dim, int nsub, con
 
 float jvo_scorer_score(jvo_scorer *s, int32_t node)
 {
+    if (s->order) {
+        switch (s->kind) {
+        case 0: return jvo_score_from_raw(s->metric, warp_raw_f32(s->metric, s->q, s->base + (size_t)node * s->dim, s->dim, s->wqnorm));
+        case 1: return warp_pq_score(s->metric, s->wlut, s->wmag, s->wbMag, s->k, s->codes + (size_t)node * s->M, s->M);
+        case 2: break; /* integers: one order */
+        default: return warp_nvq_score(s->metric, s->wq, s->mean, s->nsub, s->sizes, s->offsets, s->params + (size_t)node * 4 * s->nsub,
+                                       s->bytes + (size_t)node * s->dim, s->wqbias, s->wqnorm);
+        }
+    }
     switch (s->kind) {
     case 0: {
         const float *row = s->base + (size_t)node * s->dim;
@@ -742,6 +979,7 @@ void jvo_scorer_free(jvo_scorer *s)
 {
     if (!s) return;
     free(s->q); free(s->lut); free(s->mag); free(s->qbits); free(s->sizes); free(s->mean_sh);
+    free(s->q_raw); free(s->wlut); free(s->wmag); free(s->wq);
     free(s);
 }
 
@@ -860,7 +1098,12 @@ static void ev_add(searcher *S, int64_t key)
     S->evicted[S->nev++] = key;
 }
 
-static void search_one_layer(const jvo_graph *g, searcher *S, jvo_scorer *sf, int rerankK, int level)
+static int accept_get(const uint32_t *bits, int32_t node) { return !bits || ((bits[node >> 5] >> (node & 31)) & 1u); }
+
+/* searchOneLayer with acceptOrdsThisLayer + threshold (GraphSearcher.java:406-457). The TwoPhaseTracker that a threshold > 0
+ * installs (ScoreTracker.java:70-125) is NOT restated: its sliding window survives reset() between queries, so its decisions
+ * depend on the searcher's previous queries; threshold here is the admission rule of :427-431 only. */
+static void search_one_layer(const jvo_graph *g, searcher *S, jvo_scorer *sf, int rerankK, int level, float threshold, const uint32_t *accept)
 {
     S->results.bound = rerankK;
     while (S->candidates.size > 0) {
@@ -869,9 +1112,11 @@ static void search_one_layer(const jvo_graph *g, searcher *S, jvo_scorer *sf, in
         if (S->results.size >= rerankK && topScore < jvo_key_score(S->results.a[1])) break;
         kh_pop(&S->candidates);
         int32_t node = jvo_key_node(top);
-        /* addTopCandidate */
-        if (S->results.size < rerankK) kh_push(&S->results, top);
-        else if (topScore > jvo_key_score(S->results.a[1])) { ev_add(S, S->results.a[1]); kh_push(&S->results, top); }
+        if (accept_get(accept, node) && topScore >= threshold) {
+            /* addTopCandidate (GraphSearcher.java:520-530) */
+            if (S->results.size < rerankK) kh_push(&S->results, top);
+            else if (topScore > jvo_key_score(S->results.a[1])) { ev_add(S, S->results.a[1]); kh_push(&S->results, top); }
+        }
         if (level == 0) S->st.expanded_base++;
         S->st.expanded++;
         const int32_t *nb = graph_neighbors(g, level, node);
@@ -887,8 +1132,10 @@ static void search_one_layer(const jvo_graph *g, searcher *S, jvo_scorer *sf, in
     }
 }
 
-int jvo_graph_search(const jvo_graph *g, jvo_scorer *approx, jvo_scorer *reranker, int topK, int rerankK,
-                     int32_t *nodes_out, float *scores_out, jvo_search_stats *stats)
+/* GraphSearcher.search(scoreProvider, topK, rerankK, threshold, rerankFloor, acceptOrds) (GraphSearcher.java:166-181,263-282);
+ * accept_bits: bit (node & 31) of word (node >> 5), NULL = Bits.ALL. Upper layers use Bits.ALL and threshold 0 (:273-278). */
+int jvo_graph_search_ex(const jvo_graph *g, jvo_scorer *approx, jvo_scorer *reranker, int topK, int rerankK, float threshold,
+                        float rerankFloor, const uint32_t *accept_bits, int32_t *nodes_out, float *scores_out, jvo_search_stats *stats)
 {
     searcher S;
     memset(&S, 0, sizeof(S));
@@ -900,14 +1147,14 @@ int jvo_graph_search(const jvo_graph *g, jvo_scorer *approx, jvo_scorer *reranke
     is_add(&S.visited, g->entry_node);
     kh_push(&S.candidates, jvo_topk_key(es, g->entry_node));
     for (int lvl = g->entry_level; lvl > 0; lvl--) {
-        search_one_layer(g, &S, approx, 1, lvl);
+        search_one_layer(g, &S, approx, 1, lvl, 0.0f, NULL);
         /* setEntryPointsFromPreviousLayer */
         for (int i = 1; i <= S.results.size; i++) kh_push(&S.candidates, S.results.a[i]);
         for (int i = 0; i < S.nev; i++) kh_push(&S.candidates, S.evicted[i]);
         S.nev = 0;
         S.results.size = 0;
     }
-    search_one_layer(g, &S, approx, rerankK, 0);
+    search_one_layer(g, &S, approx, rerankK, 0, threshold, accept_bits);
     int count;
     if (!reranker) {
         while (S.results.size > topK) kh_pop(&S.results);
@@ -918,16 +1165,28 @@ int jvo_graph_search(const jvo_graph *g, jvo_scorer *approx, jvo_scorer *reranke
             scores_out[i] = jvo_key_score(key);
         }
     } else {
-        /* NodeQueue.rerank with rerankFloor = 0: rescore every survivor in heap-array order, keep topK */
+        /* NodeQueue.rerank (NodeQueue.java:168-230): heap-array order; only approximate scores >= rerankFloor are rescored,
+         * or the single best one when none is; strict > keeps the first of two equal exact scores */
         kheap rr;
         kh_init(&rr, topK, topK, 0);
-        for (int i = 1; i <= S.results.size; i++) {
+        int n = S.results.size, above = 0, bestIndex = -1;
+        float bestScore = -INFINITY;
+        char *take = (char *)calloc((size_t)n + 1, 1);
+        for (int i = 1; i <= n; i++) {
+            float sc = jvo_key_score(S.results.a[i]);
+            if (sc > bestScore) { bestScore = sc; bestIndex = i; }
+            if (sc >= rerankFloor) { take[i] = 1; above++; }
+        }
+        if (above == 0 && bestIndex >= 1) take[bestIndex] = 1;
+        for (int i = 1; i <= n; i++) {
+            if (!take[i]) continue;
             int32_t node = jvo_key_node(S.results.a[i]);
             float ex = jvo_scorer_score(reranker, node);
             S.st.reranked++;
             if (rr.size < topK) kh_push(&rr, jvo_topk_key(ex, node));
             else if (ex > jvo_key_score(rr.a[1])) kh_push(&rr, jvo_topk_key(ex, node));
         }
+        free(take);
         count = rr.size;
         for (int i = count - 1; i >= 0; i--) {
             int64_t key = kh_pop(&rr);
@@ -939,6 +1198,12 @@ int jvo_graph_search(const jvo_graph *g, jvo_scorer *approx, jvo_scorer *reranke
     if (stats) *stats = S.st;
     free(S.candidates.a); free(S.results.a); free(S.evicted); free(S.visited.t);
     return count;
+}
+
+int jvo_graph_search(const jvo_graph *g, jvo_scorer *approx, jvo_scorer *reranker, int topK, int rerankK,
+                     int32_t *nodes_out, float *scores_out, jvo_search_stats *stats)
+{
+    return jvo_graph_search_ex(g, approx, reranker, topK, rerankK, 0.0f, 0.0f, NULL, nodes_out, scores_out, stats);
 }
 
 /* ---- multi-threaded batch driver (queries block-partitioned, one searcher per thread:
@@ -956,6 +1221,7 @@ static void *batch_worker(void *arg)
         const float *q = j->queries + (size_t)qi * ds->dim;
         jvo_scorer *ex = jvo_scorer_f32(ds->metric, ds->base, ds->n, ds->dim, q);
         jvo_scorer *ap = ds->kind == 1 ? jvo_scorer_pq(ds->metric, ds->codebooks, ds->M, ds->k, ds->dim, ds->centroid, ds->codes, ds->n, q) : NULL;
+        if (ds->order) { jvo_scorer_set_order(ex, ds->order); if (ap) jvo_scorer_set_order(ap, ds->order); }
         jvo_search_stats st;
         int32_t *no = j->nodes + (size_t)qi * j->topK;
         float *so = j->scores + (size_t)qi * j->topK;

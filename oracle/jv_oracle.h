@@ -77,6 +77,12 @@ void jvo_nvq_cosine_8bit(const float *q, const uint8_t *b, int n, float alpha, f
 void jvo_nvq_encode_subvector(const float *v, int n, int learn, float *params_out, uint8_t *bytes_out);
 /* encode a whole vector: subtract mean, split into nsub sub-vectors (layout as jvo_pq_layout) */
 void jvo_nvq_encode(const float *v, const float *mean, int dim, int nsub, int learn, float *params_out, uint8_t *bytes_out);
+/* the same sums and parameter search under an explicit summation order (see jv_oracle.c): lanes = 1 sequential,
+ * lanes = 32 strided accumulators + xor butterfly (a GPU warp's order) */
+float jvo_nvq_loss_lanes(const float *v, int n, float alpha, float x0, float minv, float maxv, int nbits, int lanes);
+float jvo_nvq_uniform_loss_lanes(const float *v, int n, float minv, float maxv, int nbits, int lanes);
+void jvo_nvq_encode_subvector_lanes(const float *v, int n, int learn, int lanes, float *params_out, uint8_t *bytes_out);
+void jvo_nvq_encode_lanes(const float *v, const float *mean, int dim, int nsub, int learn, int lanes, float *params_out, uint8_t *bytes_out);
 float jvo_nvq_score(int metric, const float *q, const float *mean, int dim, int nsub,
                     const float *params, const uint8_t *bytes);
 
@@ -115,10 +121,22 @@ typedef struct {
     int32_t reranked;
 } jvo_search_stats;
 
+/* order 0 (default): sequential sums, or the reference's kernels after jvo_use_ref; order 1: the summation order of the
+ * sm_100a kernels (32 / 8 lane accumulators + xor butterfly, see "WARP-ORDER restatements" in jv_oracle.c), which makes a
+ * traversal reproducible id for id. Same formulas either way. */
+void jvo_scorer_set_order(jvo_scorer *s, int order);
+float jvo_compare_f32_warp(int metric, const float *q, const float *row, int dim);
+
 /* one query; approx scorer walks the graph, optional reranker re-scores the rerankK survivors.
  * Writes up to topK (node, score) pairs ordered best first; returns the count. */
 int jvo_graph_search(const jvo_graph *g, jvo_scorer *approx, jvo_scorer *reranker, int topK, int rerankK,
                      int32_t *nodes_out, float *scores_out, jvo_search_stats *stats);
+
+/* GraphSearcher.search(scoreProvider, topK, rerankK, threshold, rerankFloor, acceptOrds) (GraphSearcher.java:166-181):
+ * accept_bits: bit (node & 31) of word (node >> 5), NULL = Bits.ALL. threshold: admission rule of :427-431 only (the
+ * TwoPhaseTracker early stop is not restated, see jv_oracle.c). */
+int jvo_graph_search_ex(const jvo_graph *g, jvo_scorer *approx, jvo_scorer *reranker, int topK, int rerankK, float threshold,
+                        float rerankFloor, const uint32_t *accept_bits, int32_t *nodes_out, float *scores_out, jvo_search_stats *stats);
 
 /* batched, multi-threaded driver over f32 / pq(+f32 rerank) data for the CPU baseline.
  * kind: 0 = exact f32 only, 1 = PQ first pass + f32 rerank */
@@ -126,6 +144,7 @@ typedef struct {
     int kind, metric, dim;
     const float *base; int64_t n;
     const float *codebooks; int M, k; const float *centroid; const uint8_t *codes;
+    int order; /* 0: sequential / reference kernels; 1: warp order (jvo_scorer_set_order) */
 } jvo_dataset;
 double jvo_graph_search_batch(const jvo_graph *g, const jvo_dataset *ds, const float *queries, int nq,
                               int topK, int rerankK, int threads, int32_t *nodes_out, float *scores_out,

@@ -53,7 +53,7 @@ class Stats(C.Structure):
 
 class Dataset(C.Structure):
     _fields_ = [("kind", C.c_int), ("metric", C.c_int), ("dim", C.c_int), ("base", f32p), ("n", C.c_int64),
-                ("codebooks", f32p), ("M", C.c_int), ("k", C.c_int), ("centroid", f32p), ("codes", u8p)]
+                ("codebooks", f32p), ("M", C.c_int), ("k", C.c_int), ("centroid", f32p), ("codes", u8p), ("order", C.c_int)]
 
 
 _lib = None
@@ -115,6 +115,10 @@ def load():
     sig("jvo_nvq_cosine_8bit", None, f32p, u8p, I, F, F, F, F, f32p, f32p)
     sig("jvo_nvq_encode_subvector", None, f32p, I, I, f32p, u8p)
     sig("jvo_nvq_encode", None, f32p, f32p, I, I, I, f32p, u8p)
+    sig("jvo_nvq_loss_lanes", F, f32p, I, F, F, F, F, I, I)
+    sig("jvo_nvq_uniform_loss_lanes", F, f32p, I, F, F, I, I)
+    sig("jvo_nvq_encode_subvector_lanes", None, f32p, I, I, I, f32p, u8p)
+    sig("jvo_nvq_encode_lanes", None, f32p, f32p, I, I, I, I, f32p, u8p)
     sig("jvo_nvq_score", F, I, f32p, f32p, I, I, f32p, u8p)
     sig("jvo_use_ref", I, C.c_char_p)
     sig("jvo_ref_isa", C.c_char_p)
@@ -123,8 +127,11 @@ def load():
     sig("jvo_scorer_bq", P, u64p, C.c_int64, I, f32p)
     sig("jvo_scorer_nvq", P, I, f32p, I, I, f32p, u8p, C.c_int64, f32p)
     sig("jvo_scorer_score", F, P, C.c_int32)
+    sig("jvo_scorer_set_order", None, P, I)
+    sig("jvo_compare_f32_warp", F, I, f32p, f32p, I)
     sig("jvo_scorer_free", None, P)
     sig("jvo_graph_search", I, C.POINTER(Graph), P, P, I, I, i32p, f32p, C.POINTER(Stats))
+    sig("jvo_graph_search_ex", I, C.POINTER(Graph), P, P, I, I, F, F, C.POINTER(C.c_uint32), i32p, f32p, C.POINTER(Stats))
     sig("jvo_graph_search_batch", C.c_double, C.POINTER(Graph), C.POINTER(Dataset), f32p, I, I, I, I, i32p, f32p, i64p)
     sig("jvo_nvq_encode_batch", C.c_double, f32p, C.c_int64, I, I, f32p, I, I, f32p, u8p)
     sig("jvo_bq_bruteforce_batch", C.c_double, u64p, C.c_int64, I, u64p, I, I, I, i64p)

@@ -233,6 +233,30 @@ def test_nvq_vs_ref(oracle, ref, n):
     assert abs(ul - rul) <= 1e-5 * abs(rul) + 1e-12
 
 
+@pytest.mark.parametrize("n", [5, 31, 32, 33, 64, 384, 1000])
+def test_nvq_loss_lane_orders_vs_ref(oracle, ref, n):
+    # the loss sums are defined up to summation order (scalar provider: sequential; Panama / native: lane accumulators); the
+    # 32-lane order the device uses stays inside the reference's own agreement band and the search it drives picks the same
+    # growth rate as the sequential order except on near-ties
+    rng = np.random.default_rng(300 + n)
+    v = (rng.standard_normal(n) * 0.05).astype(np.float32)
+    minv, maxv = float(v.min()), float(v.max())
+    for alpha in (1e-6, 1e-2, 3.000001, 7.3, 19.000001):
+        rlo = ref.nvq_loss(fp(v), n, alpha, 0.0, minv, maxv, 8)
+        for lanes in (1, 8, 16, 32):
+            lo = oracle.jvo_nvq_loss_lanes(fp(v), n, alpha, 0.0, minv, maxv, 8, lanes)
+            assert abs(lo - rlo) <= 1e-5 * abs(rlo) + 1e-12, (lanes, alpha)
+    rul = ref.nvq_uniform_loss(fp(v), n, minv, maxv, 8)
+    for lanes in (1, 8, 16, 32):
+        assert abs(oracle.jvo_nvq_uniform_loss_lanes(fp(v), n, minv, maxv, 8, lanes) - rul) <= 1e-5 * abs(rul) + 1e-12
+    assert oracle.jvo_nvq_loss_lanes(fp(v), n, 2.5, 0.0, minv, maxv, 8, 1) == oracle.jvo_nvq_loss(fp(v), n, 2.5, 0.0, minv, maxv, 8)
+    p1, p32 = np.empty(4, np.float32), np.empty(4, np.float32)
+    b1, b32 = np.empty(n, np.uint8), np.empty(n, np.uint8)
+    oracle.jvo_nvq_encode_subvector_lanes(fp(v), n, 1, 1, fp(p1), bp(b1))
+    oracle.jvo_nvq_encode_subvector_lanes(fp(v), n, 1, 32, fp(p32), bp(b32))
+    assert np.array_equal(p1[[0, 1, 3]], p32[[0, 1, 3]]) and abs(p1[2] - p32[2]) <= 0.11  # at most one grid step apart
+
+
 def test_nvq_dequant_elementwise_exact(oracle, ref):
     # per-element dequantisation is bit-reproducible: n = 1 calls of the reference kernel isolate one element
     rng = np.random.default_rng(9)
@@ -390,3 +414,34 @@ def test_builder_known_answer_fallback_and_3d(oracle):
         oracle.jvo_graph_build_f32(o.EUCLIDEAN, fp(np.ascontiguousarray(v[:n])), n, 3, 2, 10, 1.0, 1.0, ip(adj))
         for node, nbrs in want.items():
             assert sorted(int(x) for x in adj[node] if x >= 0) == nbrs, ("3d", n, node, adj[node].tolist())
+
+
+def test_warp_order_scorers_agree_with_sequential_order(oracle):
+    # order 1 (the kernels' summation order) is the same arithmetic as order 0: every score within 1e-5 relative, BQ identical
+    rng = np.random.default_rng(91)
+    for dim, M, nsub in ((64, 16, 2), (100, 7, 3), (768, 96, 2), (33, 33, 1)):
+        n = 120
+        data = o.random_unit_vectors(rng, n, dim)
+        q = o.random_unit_vectors(rng, 1, dim)[0]
+        cb, sizes, offsets = o.train_pq_numpy(rng, data, M, 256, iters=1)
+        cen = data.mean(0).astype(np.float32)
+        codes = o.encode_pq(oracle, cb, sizes, offsets, M, 256, cen, data)
+        params = np.empty((n, nsub, 4), np.float32)
+        bys = np.empty((n, dim), np.uint8)
+        for i in range(n):
+            oracle.jvo_nvq_encode(fp(data[i]), fp(cen), dim, nsub, 1, fp(params[i]), bp(bys[i]))
+        words = np.zeros((n, (dim + 63) // 64), np.uint64)
+        for i in range(n):
+            oracle.jvo_bq_encode(fp(data[i]), dim, wp(words[i]))
+        for metric in (o.EUCLIDEAN, o.DOT_PRODUCT, o.COSINE):
+            for mk in (lambda: oracle.jvo_scorer_f32(metric, fp(data), n, dim, fp(q)),
+                       lambda: oracle.jvo_scorer_pq(metric, fp(cb), M, 256, dim, fp(cen), bp(codes), n, fp(q)),
+                       lambda: oracle.jvo_scorer_nvq(metric, fp(cen), dim, nsub, fp(params), bp(bys), n, fp(q)),
+                       lambda: oracle.jvo_scorer_bq(wp(words), n, dim, fp(q))):
+                sf = mk()
+                a = np.array([oracle.jvo_scorer_score(sf, i) for i in range(n)], np.float32)
+                oracle.jvo_scorer_set_order(sf, 1)
+                b = np.array([oracle.jvo_scorer_score(sf, i) for i in range(n)], np.float32)
+                oracle.jvo_scorer_free(sf)
+                assert np.abs(a - b).max() <= 1e-5 * max(1e-2, float(np.abs(a).max())), (dim, metric)
+        assert oracle.jvo_compare_f32_warp(o.DOT_PRODUCT, fp(q), fp(data[3]), dim) == pytest.approx(oracle.jvo_compare_f32(o.DOT_PRODUCT, fp(q), fp(data[3]), dim), rel=1e-5)
