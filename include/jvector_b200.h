@@ -88,7 +88,15 @@ typedef struct jv_dataset_s *jv_dataset; /* vectors / codes resident in HBM */
 typedef struct jv_query_s *jv_query;     /* one query prepared against one data set (LUT / bits / shifted copy) */
 typedef struct jv_graph_s *jv_graph;     /* adjacency resident in HBM */
 
-JV_API int jv_gpu_init(int device);      /* bind the calling process to CUDA device `device`; idempotent */
+/* Bind CUDA device `device` and make it the device on which the CALLING THREAD creates data sets and graphs. Idempotent. Every
+ * handle remembers its device, so binding another device later never invalidates existing handles. */
+JV_API int jv_gpu_init(int device);
+/* One process driving several GPUs (the reference host is one JVM: base:vector/VectorizationProvider.java:79-177): bind every
+ * device of the mask (bit d = CUDA device d) and enable peer access between them (NVLink / NVSwitch). SURVEY §8(b). */
+JV_API int jv_gpu_init_mask(uint32_t device_mask);
+JV_API uint32_t jv_gpu_bound_mask(void);
+/* the device on which the calling thread's next register / create calls place their data (a bound device) */
+JV_API int jv_gpu_set_device(int device);
 JV_API int jv_gpu_device_count(void);
 JV_API const char *jv_last_error(void);
 JV_API const char *jv_version(void);
@@ -108,6 +116,10 @@ JV_API int jv_dataset_register_bq(const uint64_t *words, int64_t n, int dim, jv_
  * (NVQuantization.java:489-498), mean = globalMean */
 JV_API int jv_dataset_register_nvq(const uint8_t *bytes, const float *params, int64_t n, int dim, int nsub,
                                    const float *mean, jv_dataset *out);
+/* rows already in HBM on the calling thread's device (e.g. produced by another kernel): BORROWED, not copied — the caller keeps
+ * them alive until jv_dataset_free. 16-byte aligned, row_stride = dim rounded up to 4 floats, padding floats zero. */
+JV_API int jv_dataset_adopt_f32_device(const float *rows_device, int64_t n, int dim, int row_stride, jv_dataset *out);
+JV_API int jv_dataset_device(jv_dataset ds);
 JV_API int jv_dataset_free(jv_dataset ds);
 JV_API int64_t jv_dataset_size(jv_dataset ds);
 JV_API int jv_dataset_dim(jv_dataset ds);
@@ -136,6 +148,28 @@ JV_API int jv_topk_bruteforce_device(jv_dataset ds, int metric, const float *que
                                      int64_t *keys_out_device);
 /* the merge after the all-gather: keys_in [nq][parts * k] (any order) -> keys_out [nq][k] best first */
 JV_API int jv_topk_merge_device(const int64_t *keys_in_device, int nq, int parts, int k, int64_t *keys_out_device);
+
+/* Stream-ordered forms for callers that own a CUDA stream (the multi-process bench puts the local top-k, the NCCL all-gather and
+ * the merge on ONE stream with no host synchronisation in between). BQ data sets only (the tensor-core contraction of
+ * csrc/bq_imma.cu); *status_device receives the number of queries left unresolved (0 normally; non-zero = call the synchronous
+ * form, which falls back to the key-threshold kernels). cuda_stream: a cudaStream_t. */
+JV_API int jv_topk_bruteforce_device_async(jv_dataset ds, int metric, const float *queries_device, int nq, int k, int64_t id_base,
+                                           int64_t *keys_out_device, int32_t *status_device, void *cuda_stream);
+/* keys_in: SHARD-MAJOR [parts][nq][k], exactly what an all-gather of the per-rank [nq][k] arrays produces */
+JV_API int jv_topk_merge_device_async(const int64_t *keys_in_device, int nq, int parts, int k, int64_t *keys_out_device, void *cuda_stream);
+
+/* ---- several GPUs driven by ONE process (SURVEY §8b last row, §8e) ----
+ * jv_multi: a base RANGE-SHARDED by contiguous node id over the devices bound by jv_gpu_init_mask (shard i holds rows
+ * [first_row_i, first_row_i + rows_i)). jv_multi_topk_bruteforce: every shard scores all queries on its own stream (one worker
+ * thread per device inside the call), the per-shard top-k keys (global node ids) go to the first device by NVLink peer copies
+ * and are merged there by the reference key — the same exchange the multi-process path does with an NCCL all-gather. */
+typedef struct jv_multi_s *jv_multi;
+JV_API int jv_multi_register_bq(const uint64_t *words, int64_t n, int dim, jv_multi *out);
+JV_API int jv_multi_register_f32(const float *rows, int64_t n, int dim, jv_multi *out);
+JV_API int jv_multi_free(jv_multi m);
+JV_API int jv_multi_shard_count(jv_multi m);
+JV_API int jv_multi_shard_info(jv_multi m, int shard, int *device, int64_t *first_row, int64_t *rows);
+JV_API int jv_multi_topk_bruteforce(jv_multi m, int metric, const float *queries, int nq, int k, int64_t *keys_out);
 
 /* ---- bulk encoders (next to the scoring path: ProductQuantization.encodeAll, BinaryQuantization.encodeAll,
  *      NVQuantization.encodeAll) ---- */
@@ -200,6 +234,13 @@ JV_API int jv_graph_search_batch_device_ex(jv_graph g, jv_dataset approx, jv_dat
                                            const float *queries_device, int nq, int topK, int rerankK,
                                            const jv_search_options *opts_device_bits, int32_t *nodes_out_device,
                                            float *scores_out_device, jv_search_stats *stats);
+
+/* Replicas: graph + data sets registered once per device (jv_gpu_set_device(d), then the ordinary create / register calls); the
+ * batch is split into contiguous slices, one per replica, searched concurrently (no data-path exchange). stats sums the counters,
+ * device_ms is the slowest replica. */
+JV_API int jv_multi_graph_search_batch(int replicas, const jv_graph *graphs, const jv_dataset *approx, const jv_dataset *rerankers,
+                                       int metric, const float *queries, int nq, int topK, int rerankK, const jv_search_options *opts,
+                                       int32_t *nodes_out, float *scores_out, jv_search_stats *stats);
 
 /* GraphIndexBuilder.build over an f32 data set with exact scoring (BuildScoreProvider.randomAccessScoreProvider):
  * batched inserts, device-side beam search + Vamana robust prune + back-links. */

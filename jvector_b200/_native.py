@@ -54,18 +54,26 @@ SYMBOLS = [
     ("nvq_cosine_8bit_packed", _L, [f32p, u8p, _Z, _F, _F, _F, _F, f32p]), ("nvq_shuffle_query_in_place_8bit", None, [f32p, _Z]),
     ("jvector_simd_get_active_isa", C.c_char_p, []), ("jvector_simd_get_max_isa_env", C.c_char_p, []),
     # batched GPU ABI
-    ("jv_gpu_init", _I, [_I]), ("jv_gpu_device_count", _I, []), ("jv_last_error", C.c_char_p, []), ("jv_version", C.c_char_p, []),
+    ("jv_gpu_init", _I, [_I]), ("jv_gpu_init_mask", _I, [C.c_uint32]), ("jv_gpu_bound_mask", C.c_uint32, []), ("jv_gpu_set_device", _I, [_I]),
+    ("jv_gpu_device_count", _I, []), ("jv_last_error", C.c_char_p, []), ("jv_version", C.c_char_p, []),
     ("jv_gpu_sm_count", _I, []),
     ("jv_dataset_register_f32", _I, [f32p, _L, _I, C.POINTER(_P)]),
     ("jv_dataset_register_pq", _I, [u8p, _L, _I, _I, _I, f32p, f32p, C.POINTER(_P)]),
     ("jv_dataset_register_bq", _I, [u64p, _L, _I, C.POINTER(_P)]),
     ("jv_dataset_register_nvq", _I, [u8p, f32p, _L, _I, _I, f32p, C.POINTER(_P)]),
+    ("jv_dataset_adopt_f32_device", _I, [_P, _L, _I, _I, C.POINTER(_P)]), ("jv_dataset_device", _I, [_P]),
     ("jv_dataset_free", _I, [_P]), ("jv_dataset_size", _L, [_P]), ("jv_dataset_dim", _I, [_P]), ("jv_dataset_device_bytes", _L, [_P]),
     ("jv_query_begin", _I, [_P, f32p, _I, C.POINTER(_P)]), ("jv_score_batch", _I, [_P, i32p, _I, f32p]), ("jv_query_end", _I, [_P]),
     ("jv_query_get_lut", _I, [_P, f32p]),
     ("jv_score_multi", _I, [_P, _I, f32p, _I, i32p, i32p, f32p]), ("jv_score_pairs", _I, [_P, _I, i32p, i32p, _I, f32p]),
     ("jv_topk_bruteforce", _I, [_P, _I, f32p, _I, _I, i64p]),
     ("jv_topk_bruteforce_device", _I, [_P, _I, _P, _I, _I, _L, _P]), ("jv_topk_merge_device", _I, [_P, _I, _I, _I, _P]),
+    ("jv_topk_bruteforce_device_async", _I, [_P, _I, _P, _I, _I, _L, _P, _P, _P]), ("jv_topk_merge_device_async", _I, [_P, _I, _I, _I, _P, _P]),
+    ("jv_multi_register_bq", _I, [u64p, _L, _I, C.POINTER(_P)]), ("jv_multi_register_f32", _I, [f32p, _L, _I, C.POINTER(_P)]),
+    ("jv_multi_free", _I, [_P]), ("jv_multi_shard_count", _I, [_P]), ("jv_multi_shard_info", _I, [_P, _I, C.POINTER(_I), i64p, i64p]),
+    ("jv_multi_topk_bruteforce", _I, [_P, _I, f32p, _I, _I, i64p]),
+    ("jv_multi_graph_search_batch", _I, [_I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _I, f32p, _I, _I, _I, C.POINTER(SearchOptions), i32p, f32p,
+                                         C.POINTER(SearchStats)]),
     ("jv_bq_encode_batch", _I, [f32p, _L, _I, u64p]), ("jv_pq_encode_batch", _I, [f32p, _L, _I, _I, _I, f32p, f32p, u8p]),
     ("jv_nvq_encode_batch", _I, [f32p, _L, _I, _I, f32p, _I, f32p, u8p]),
     ("jv_bq_encode_dataset", _I, [_P, u64p]), ("jv_pq_encode_dataset", _I, [_P, _I, _I, f32p, f32p, u8p]),

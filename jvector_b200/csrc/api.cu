@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -19,8 +20,15 @@ namespace {
 
 thread_local std::string t_err;
 std::mutex g_mu;
-int g_device = -1;
-int g_sm_count = 0;
+constexpr int MAX_DEVICES = 16;
+// One process may drive several GPUs (the reference host is one JVM, all parallelism is threads: base:vector/
+// VectorizationProvider.java:79-177, base:graph/GraphIndexBuilder.java:440-444): every handle remembers the device it lives on,
+// every caller thread owns one context (stream + staging buffers) per device.
+unsigned g_mask = 0;                 // devices bound by jv_gpu_init / jv_gpu_init_mask
+int g_default_device = -1;           // first device bound
+int g_sm_counts[MAX_DEVICES] = {0};
+thread_local int t_device = -1;      // device new data sets / graphs of this thread are created on (jv_gpu_set_device); -1 = default
+thread_local int t_active = 0;       // device of the call in progress
 
 int fail(int code, const std::string &msg)
 {
@@ -37,23 +45,39 @@ int cuda_fail(cudaError_t e, const char *what)
         cudaError_t e_ = (x);                            \
         if (e_ != cudaSuccess) return cuda_fail(e_, what); \
     } while (0)
+// enter a call that creates something: the thread's target device
 #define NEED_INIT()                                                                            \
     do {                                                                                       \
-        if (g_device < 0) return fail(JV_ERR_NO_DEVICE, "jv_gpu_init() has not succeeded");    \
-        cudaError_t e0_ = cudaSetDevice(g_device);                                             \
+        const int d0_ = t_device >= 0 ? t_device : g_default_device;                           \
+        if (d0_ < 0) return fail(JV_ERR_NO_DEVICE, "jv_gpu_init() has not succeeded");         \
+        t_active = d0_;                                                                        \
+        cudaError_t e0_ = cudaSetDevice(d0_);                                                  \
         if (e0_ != cudaSuccess) return cuda_fail(e0_, "cudaSetDevice");                        \
     } while (0)
+// enter a call on an existing handle: the handle's device
+#define ON_DEVICE_OF(h)                                                                        \
+    do {                                                                                       \
+        if (g_default_device < 0) return fail(JV_ERR_NO_DEVICE, "jv_gpu_init() has not succeeded"); \
+        if (!(h)) return fail(JV_ERR_INVALID, "null handle");                                  \
+        t_active = (h)->device;                                                                \
+        cudaError_t e0_ = cudaSetDevice(t_active);                                             \
+        if (e0_ != cudaSuccess) return cuda_fail(e0_, "cudaSetDevice");                        \
+    } while (0)
+#define g_sm_count (g_sm_counts[t_active])
 
-// per-thread stream + growable staging buffers (callers are ForkJoinPool workers: no global locks on the score path)
+// per-thread, per-device stream + growable staging buffers (callers are ForkJoinPool workers: no global locks on the score
+// path); released when the thread exits
 struct ThreadCtx {
-    cudaStream_t stream = nullptr;
     static constexpr int SLOTS = 8;
+    int device = -1;
+    cudaStream_t stream = nullptr;
     void *dbuf[SLOTS] = {};
     size_t dcap[SLOTS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int init()
     {
         if (stream) return JV_OK;
+        device = t_active;
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
         CK(cudaEventCreate(&ev0), "cudaEventCreate");
         CK(cudaEventCreate(&ev1), "cudaEventCreate");
@@ -70,8 +94,25 @@ struct ThreadCtx {
         dcap[slot] = want;
         return JV_OK;
     }
+    ~ThreadCtx()
+    {
+        if (!stream) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) return;  // runtime already torn down at process exit: nothing left to free
+        if (cudaSetDevice(device) != cudaSuccess) return;
+        cudaStreamSynchronize(stream);
+        for (int i = 0; i < SLOTS; i++)
+            if (dbuf[i]) cudaFree(dbuf[i]);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        cudaStreamDestroy(stream);
+        stream = nullptr;
+        if (cur >= 0) cudaSetDevice(cur);
+    }
 };
-thread_local ThreadCtx t_ctx;
+thread_local ThreadCtx t_ctxs[MAX_DEVICES];
+thread_local ThreadCtx *t_ctx_override = nullptr;  // worker threads of the multi-device entry points run on the shard's own context
+#define t_ctx (*(t_ctx_override ? t_ctx_override : &t_ctxs[t_active]))
 thread_local BuildStats t_build_stats = {0, 0, 0, 0};
 
 int round4(int v) { return (v + 3) & ~3; }
@@ -92,6 +133,8 @@ void pq_layout(int dim, int M, std::vector<int> &sizes, std::vector<int> &offset
 }  // namespace
 
 struct jv_dataset_s {
+    int device = 0;
+    bool borrowed_rows = false;  // jv_dataset_adopt_f32_device: rows belong to the caller
     DataDesc d;
     std::vector<void *> allocs;
     size_t bytes = 0;
@@ -109,12 +152,15 @@ struct jv_dataset_s {
 };
 
 struct jv_query_s {
+    int device = 0;
     jv_dataset ds;
     int metric;
     float *blob = nullptr;
+    int pooled = 0;  // blob belongs to a jv_query_batch
 };
 
 struct jv_graph_s {
+    int device = 0;
     GraphDesc g;
     int32_t *adj0 = nullptr;
     int32_t *upper_row = nullptr;
@@ -128,6 +174,52 @@ struct jv_graph_s {
     }
 };
 
+struct jv_multi_s {
+    int kind = 0, dim = 0;
+    int64_t n = 0;
+    std::vector<int> devices;
+    std::vector<int64_t> lo;        // shard i holds rows [lo[i], lo[i + 1])
+    std::vector<jv_dataset> shards;
+    std::vector<ThreadCtx *> ctx;   // one persistent context per shard (worker threads come and go)
+};
+
+static void shard_ranges(int64_t n, int parts, std::vector<int64_t> &lo)
+{
+    lo.resize(parts + 1);
+    const int64_t base = n / parts, rem = n % parts;
+    for (int i = 0; i <= parts; i++) lo[i] = i * base + std::min<int64_t>(i, rem);
+}
+
+static int multi_devices(std::vector<int> &devs)
+{
+    devs.clear();
+    for (int d = 0; d < MAX_DEVICES; d++)
+        if (g_mask & (1u << d)) devs.push_back(d);
+    if (devs.empty()) return fail(JV_ERR_NO_DEVICE, "jv_gpu_init_mask() has not succeeded");
+    return JV_OK;
+}
+
+template <typename F>
+static int multi_register(jv_multi m, F reg)
+{
+    int rc = multi_devices(m->devices);
+    if (rc) return rc;
+    const int parts = (int)std::min<int64_t>((int64_t)m->devices.size(), m->n);
+    m->devices.resize(parts);
+    shard_ranges(m->n, parts, m->lo);
+    const int saved = t_device;
+    for (int i = 0; i < parts; i++) {
+        t_device = m->devices[i];
+        jv_dataset ds = nullptr;
+        rc = reg(i, m->lo[i], m->lo[i + 1] - m->lo[i], &ds);
+        if (rc) break;
+        m->shards.push_back(ds);
+        m->ctx.push_back(new ThreadCtx());
+    }
+    t_device = saved;
+    return rc;
+}
+
 extern "C" {
 
 int jv_gpu_device_count(void)
@@ -137,25 +229,68 @@ int jv_gpu_device_count(void)
     return n;
 }
 
-int jv_gpu_init(int device)
+static int bind_device(int device)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) return fail(JV_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
-    if (device < 0 || device >= n) return fail(JV_ERR_INVALID, "device index out of range");
+    if (device < 0 || device >= n || device >= MAX_DEVICES) return fail(JV_ERR_INVALID, "device index out of range");
     cudaDeviceProp p;
     CK(cudaGetDeviceProperties(&p, device), "cudaGetDeviceProperties");
     if (p.major != 10) return fail(JV_ERR_NO_DEVICE, "device is not sm_100 (this library carries sm_100a code only)");
     CK(cudaSetDevice(device), "cudaSetDevice");
-    g_device = device;
-    g_sm_count = p.multiProcessorCount;
+    g_sm_counts[device] = p.multiProcessorCount;
+    g_mask |= 1u << device;
+    if (g_default_device < 0) g_default_device = device;
     return JV_OK;
 }
 
+int jv_gpu_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = bind_device(device);
+    if (rc) return rc;
+    t_device = device;  // the calling thread creates its data sets here; handles remember their device, so a later
+    return JV_OK;       // jv_gpu_init(other) never invalidates them
+}
+
+int jv_gpu_init_mask(uint32_t device_mask)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (device_mask == 0) return fail(JV_ERR_INVALID, "gpu_init_mask: empty mask");
+    for (int d = 0; d < MAX_DEVICES; d++)
+        if (device_mask & (1u << d)) {
+            int rc = bind_device(d);
+            if (rc) return rc;
+        }
+    // peer access between every pair (NVLink / NVSwitch): the multi-device entry points copy shard results device to device
+    for (int a = 0; a < MAX_DEVICES; a++)
+        for (int b = 0; b < MAX_DEVICES; b++)
+            if (a != b && (g_mask & (1u << a)) && (g_mask & (1u << b))) {
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
+                    cudaSetDevice(a);
+                    cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+                    cudaGetLastError();
+                }
+            }
+    cudaSetDevice(g_default_device);
+    return JV_OK;
+}
+
+int jv_gpu_set_device(int device)
+{
+    if (device < 0 || device >= MAX_DEVICES || !(g_mask & (1u << device))) return fail(JV_ERR_INVALID, "gpu_set_device: device was not bound by jv_gpu_init / jv_gpu_init_mask");
+    t_device = device;
+    return JV_OK;
+}
+
+uint32_t jv_gpu_bound_mask(void) { return g_mask; }
+
 const char *jv_last_error(void) { return t_err.c_str(); }
 const char *jv_version(void) { return "jvector-b200 0.1 (sm_100a)"; }
-int jv_gpu_sm_count(void) { return g_sm_count; }
+int jv_gpu_sm_count(void) { return g_default_device >= 0 ? g_sm_counts[t_device >= 0 ? t_device : g_default_device] : 0; }
 int64_t jv_kernel_launch_count(void) { return (int64_t)g_launches.load(); }
 
 // ------------------------------------------------------------------------------------------------ data sets
@@ -164,6 +299,7 @@ int jv_dataset_register_f32(const float *rows, int64_t n, int dim, jv_dataset *o
     NEED_INIT();
     if (!rows || !out || n <= 0 || dim <= 0 || n > 0x7fffffffLL) return fail(JV_ERR_INVALID, "register_f32: bad arguments");
     jv_dataset ds = new jv_dataset_s();
+    ds->device = t_active;
     memset(&ds->d, 0, sizeof(DataDesc));
     ds->d.kind = KIND_F32;
     ds->d.dim = dim;
@@ -191,6 +327,7 @@ int jv_dataset_register_pq(const uint8_t *codes, int64_t n, int dim, int M, int 
     if (!codes || !codebooks || !out || n <= 0 || dim <= 0 || M <= 0 || M > dim || k <= 0 || k > 256 || n > 0x7fffffffLL)
         return fail(JV_ERR_INVALID, "register_pq: bad arguments");
     jv_dataset ds = new jv_dataset_s();
+    ds->device = t_active;
     memset(&ds->d, 0, sizeof(DataDesc));
     DataDesc &d = ds->d;
     d.kind = KIND_PQ; d.dim = dim; d.n = n; d.M = M; d.k = k; d.code_stride = round4(M);
@@ -230,6 +367,7 @@ int jv_dataset_register_bq(const uint64_t *words, int64_t n, int dim, jv_dataset
     NEED_INIT();
     if (!words || !out || n <= 0 || dim <= 0 || n > 0x7fffffffLL) return fail(JV_ERR_INVALID, "register_bq: bad arguments");
     jv_dataset ds = new jv_dataset_s();
+    ds->device = t_active;
     memset(&ds->d, 0, sizeof(DataDesc));
     ds->d.kind = KIND_BQ; ds->d.dim = dim; ds->d.n = n; ds->d.W = (dim + 63) / 64;
     unsigned long long *dw = nullptr;
@@ -248,6 +386,7 @@ int jv_dataset_register_nvq(const uint8_t *bytes, const float *params, int64_t n
     if (!bytes || !params || !mean || !out || n <= 0 || dim <= 0 || nsub <= 0 || nsub > dim || n > 0x7fffffffLL)
         return fail(JV_ERR_INVALID, "register_nvq: bad arguments");
     jv_dataset ds = new jv_dataset_s();
+    ds->device = t_active;
     memset(&ds->d, 0, sizeof(DataDesc));
     DataDesc &d = ds->d;
     d.kind = KIND_NVQ; d.dim = dim; d.n = n; d.nsub = nsub; d.stride = round4(dim); d.byte_stride = round4(dim);
@@ -280,10 +419,31 @@ int jv_dataset_register_nvq(const uint8_t *bytes, const float *params, int64_t n
     return JV_OK;
 }
 
+int jv_dataset_adopt_f32_device(const float *rows_device, int64_t n, int dim, int row_stride, jv_dataset *out)
+{
+    NEED_INIT();
+    if (!rows_device || !out || n <= 0 || dim <= 0 || n > 0x7fffffffLL || row_stride < dim || (row_stride & 3) || ((uintptr_t)rows_device & 15))
+        return fail(JV_ERR_INVALID, "adopt_f32_device: need 16-byte aligned rows and a row stride that is a multiple of 4 floats >= dim");
+    if (row_stride != round4(dim)) return fail(JV_ERR_INVALID, "adopt_f32_device: row_stride must equal dim rounded up to 4 (padding floats must be zero)");
+    jv_dataset ds = new jv_dataset_s();
+    ds->device = t_active;
+    ds->borrowed_rows = true;
+    memset(&ds->d, 0, sizeof(DataDesc));
+    ds->d.kind = KIND_F32;
+    ds->d.dim = dim;
+    ds->d.n = n;
+    ds->d.stride = row_stride;
+    ds->d.rows = rows_device;
+    *out = ds;
+    return JV_OK;
+}
+
+int jv_dataset_device(jv_dataset ds) { return ds ? ds->device : -1; }
+
 int jv_dataset_free(jv_dataset ds)
 {
     if (!ds) return JV_OK;
-    if (g_device >= 0) cudaSetDevice(g_device);
+    cudaSetDevice(ds->device);
     cudaDeviceSynchronize();
     delete ds;
     return JV_OK;
@@ -302,13 +462,14 @@ static int check_metric(const DataDesc &d, int metric)
 
 int jv_query_begin(jv_dataset ds, const float *q, int metric, jv_query *out)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(ds);
     if (!ds || !q || !out) return fail(JV_ERR_INVALID, "query_begin: null argument");
     int rc = check_metric(ds->d, metric);
     if (rc) return rc;
     if ((rc = t_ctx.init())) return rc;
     jv_query h = new jv_query_s();
     h->ds = ds;
+    h->device = ds->device;
     h->metric = metric;
     cudaError_t e = cudaMalloc((void **)&h->blob, (size_t)blob_floats(ds->d) * 4);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(query)"); }
@@ -324,7 +485,7 @@ int jv_query_begin(jv_dataset ds, const float *q, int metric, jv_query *out)
 
 int jv_score_batch(jv_query q, const int32_t *ids, int n, float *scores_out)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(q);
     if (!q || (n > 0 && (!ids || !scores_out)) || n < 0) return fail(JV_ERR_INVALID, "score_batch: bad arguments");
     if (n == 0) return JV_OK;
     int rc;
@@ -339,7 +500,7 @@ int jv_score_batch(jv_query q, const int32_t *ids, int n, float *scores_out)
 
 int jv_query_get_lut(jv_query q, float *lut_out)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(q);
     if (!q || !lut_out || q->ds->d.kind != KIND_PQ) return fail(JV_ERR_INVALID, "get_lut: not a PQ query");
     CK(cudaMemcpy(lut_out, q->blob, (size_t)q->ds->d.M * q->ds->d.k * 4, cudaMemcpyDeviceToHost), "D2H lut");
     return JV_OK;
@@ -348,15 +509,15 @@ int jv_query_get_lut(jv_query q, float *lut_out)
 int jv_query_end(jv_query q)
 {
     if (!q) return JV_OK;
-    if (g_device >= 0) cudaSetDevice(g_device);
-    cudaFree(q->blob);
+    cudaSetDevice(q->device);
+    if (!q->pooled) cudaFree(q->blob);
     delete q;
     return JV_OK;
 }
 
 int jv_score_multi(jv_dataset ds, int metric, const float *queries, int nq, const int32_t *ids, const int32_t *offsets, float *scores_out)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(ds);
     if (!ds || !queries || !ids || !offsets || !scores_out || nq <= 0) return fail(JV_ERR_INVALID, "score_multi: bad arguments");
     if (nq > 65535) return fail(JV_ERR_INVALID, "score_multi: at most 65535 queries per call");
     int rc = check_metric(ds->d, metric);
@@ -387,10 +548,12 @@ int jv_score_multi(jv_dataset ds, int metric, const float *queries, int nq, cons
 
 int jv_score_pairs(jv_dataset ds, int metric, const int32_t *a, const int32_t *b, int n, float *scores_out)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(ds);
     if (!ds || n < 0 || (n > 0 && (!a || !b || !scores_out))) return fail(JV_ERR_INVALID, "score_pairs: bad arguments");
     if (ds->d.kind == KIND_NVQ) return fail(JV_ERR_UNSUPPORTED, "score_pairs: NVQ has no node-vs-node scorer in the reference");
     if (n == 0) return JV_OK;
+    for (int i = 0; i < n; i++)
+        if (a[i] < 0 || a[i] >= ds->d.n || b[i] < 0 || b[i] >= ds->d.n) return fail(JV_ERR_INVALID, "score_pairs: node id out of range");
     int rc = check_metric(ds->d, metric);
     if (rc) return rc;
     if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(1, (size_t)n * 8)) || (rc = t_ctx.ensure(2, (size_t)n * 4))) return rc;
@@ -404,8 +567,9 @@ int jv_score_pairs(jv_dataset ds, int metric, const int32_t *a, const int32_t *b
     return JV_OK;
 }
 
-// exhaustive top-k with queries and keys in HBM; id_base is added to every node id (range-sharded base)
-static int topk_device(jv_dataset ds, int metric, const float *queries_dev, int nq, int k, int64_t id_base, long long *keys_dev)
+// generic exhaustive top-k (any storage kind): sample -> key threshold -> filtered pass -> per-query selection, with a host
+// decision between passes (kernels_batch.cu). Queries and keys in HBM; id_base is added to every node id.
+static int topk_device_generic(jv_dataset ds, int metric, const float *queries_dev, int nq, int k, int64_t id_base, long long *keys_dev)
 {
     cudaStream_t s = t_ctx.stream;
     int rc;
@@ -449,9 +613,46 @@ static int topk_device(jv_dataset ds, int metric, const float *queries_dev, int 
     return JV_OK;
 }
 
+constexpr int IMMA_QUERY_CHUNK = 4096;  // queries per bq_imma launch sequence (bounds the capture buffers: 64 KB per query)
+
+// BQ: the tensor-core contraction (bq_imma.cu), enqueued on `s` without any host synchronisation. status_dev receives the number of
+// queries the integer-threshold path left unresolved (0 in the normal case).
+static int topk_bq_imma_enqueue(jv_dataset ds, const float *queries_dev, int nq, int k, int64_t id_base, long long *keys_dev, int *status_dev, cudaStream_t s)
+{
+    int rc;
+    const int chunk = std::min(nq, IMMA_QUERY_CHUNK);
+    if ((rc = t_ctx.ensure(7, bq_imma_scratch_bytes(ds->d.n, chunk, ds->d.W) + 64))) return rc;
+    int *tmp = (int *)((char *)t_ctx.dbuf[7] + bq_imma_scratch_bytes(ds->d.n, chunk, ds->d.W));
+    for (int q0 = 0; q0 < nq; q0 += chunk) {
+        const int cq = std::min(chunk, nq - q0);
+        // one status word per call: chunks after the first accumulate through a scratch word
+        int *st = q0 == 0 ? status_dev : tmp;
+        CK(launch_bq_topk_imma(ds->d, queries_dev + (size_t)q0 * ds->d.dim, cq, k, (long long)id_base, t_ctx.dbuf[7], keys_dev + (size_t)q0 * k, st, s), "bq_topk_imma");
+        if (q0 > 0) CK(launch_add_int(status_dev, tmp, s), "status");
+    }
+    return JV_OK;
+}
+
+static int topk_device(jv_dataset ds, int metric, const float *queries_dev, int nq, int k, int64_t id_base, long long *keys_dev)
+{
+    const char *force = getenv("JV_BQ_BRUTEFORCE");  // "popc": keep the round-1 popcount kernels (A/B timing, fallback tests)
+    if (bq_imma_supported(ds->d, k) && !(force && force[0] == 'p')) {
+        int rc;
+        if ((rc = t_ctx.ensure(3, 64))) return rc;
+        int *dflag = (int *)t_ctx.dbuf[3];
+        if ((rc = topk_bq_imma_enqueue(ds, queries_dev, nq, k, id_base, keys_dev, dflag, t_ctx.stream))) return rc;
+        int unresolved = 0;
+        CK(cudaMemcpyAsync(&unresolved, dflag, sizeof(int), cudaMemcpyDeviceToHost, t_ctx.stream), "D2H status");
+        CK(cudaStreamSynchronize(t_ctx.stream), "sync");
+        if (unresolved == 0) return JV_OK;
+        // a Hamming bin wider than the capture buffer (very low dimension, or adversarial duplicates): the key-threshold path decides
+    }
+    return topk_device_generic(ds, metric, queries_dev, nq, k, id_base, keys_dev);
+}
+
 int jv_topk_bruteforce(jv_dataset ds, int metric, const float *queries, int nq, int k, int64_t *keys_out)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(ds);
     if (!ds || !queries || !keys_out || nq <= 0 || k <= 0) return fail(JV_ERR_INVALID, "topk_bruteforce: bad arguments");
     if (k > 2048) return fail(JV_ERR_INVALID, "topk_bruteforce: k <= 2048");
     int rc = check_metric(ds->d, metric);
@@ -467,7 +668,7 @@ int jv_topk_bruteforce(jv_dataset ds, int metric, const float *queries, int nq, 
 
 int jv_topk_bruteforce_device(jv_dataset ds, int metric, const float *queries_device, int nq, int k, int64_t id_base, int64_t *keys_out_device)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(ds);
     if (!ds || !queries_device || !keys_out_device || nq <= 0 || k <= 0 || k > 2048 || id_base < 0) return fail(JV_ERR_INVALID, "topk_bruteforce_device: bad arguments");
     int rc = check_metric(ds->d, metric);
     if (rc) return rc;
@@ -483,6 +684,26 @@ int jv_topk_merge_device(const int64_t *keys_in_device, int nq, int parts, int k
     if ((rc = t_ctx.init())) return rc;
     CK(launch_topk_merge((const long long *)keys_in_device, nq, parts, k, (long long *)keys_out_device, t_ctx.stream), "topk_merge");
     CK(cudaStreamSynchronize(t_ctx.stream), "sync");
+    return JV_OK;
+}
+
+int jv_topk_bruteforce_device_async(jv_dataset ds, int metric, const float *queries_device, int nq, int k, int64_t id_base, int64_t *keys_out_device,
+                                    int32_t *status_device, void *cuda_stream)
+{
+    ON_DEVICE_OF(ds);
+    if (!queries_device || !keys_out_device || !status_device || nq <= 0 || k <= 0 || id_base < 0) return fail(JV_ERR_INVALID, "topk_bruteforce_device_async: bad arguments");
+    (void)metric;
+    if (!bq_imma_supported(ds->d, k)) return fail(JV_ERR_UNSUPPORTED, "topk_bruteforce_device_async: BQ data sets (even word count, n >= 4096) only; use jv_topk_bruteforce_device");
+    int rc;
+    if ((rc = t_ctx.init())) return rc;
+    return topk_bq_imma_enqueue(ds, queries_device, nq, k, id_base, (long long *)keys_out_device, status_device, (cudaStream_t)cuda_stream);
+}
+
+int jv_topk_merge_device_async(const int64_t *keys_in_device, int nq, int parts, int k, int64_t *keys_out_device, void *cuda_stream)
+{
+    NEED_INIT();
+    if (!keys_in_device || !keys_out_device || nq <= 0 || parts <= 0 || k <= 0 || (long long)parts * k > 16384) return fail(JV_ERR_INVALID, "topk_merge: bad arguments");
+    CK(launch_topk_merge_strided((const long long *)keys_in_device, nq, parts, k, (long long *)keys_out_device, (cudaStream_t)cuda_stream), "topk_merge");
     return JV_OK;
 }
 
@@ -513,7 +734,7 @@ int jv_bq_encode_batch(const float *rows, int64_t n, int dim, uint64_t *words_ou
 
 int jv_bq_encode_dataset(jv_dataset f32, uint64_t *words_out)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(f32);
     if (!f32 || f32->d.kind != KIND_F32 || !words_out) return fail(JV_ERR_INVALID, "bq_encode_dataset: needs an fp32 data set");
     return bq_encode_impl(nullptr, f32->d.rows, f32->d.stride, f32->d.n, f32->d.dim, words_out);
 }
@@ -558,7 +779,7 @@ int jv_pq_encode_batch(const float *rows, int64_t n, int dim, int M, int k, cons
 
 int jv_pq_encode_dataset(jv_dataset f32, int M, int k, const float *codebooks, const float *centroid, uint8_t *codes_out)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(f32);
     if (!f32 || f32->d.kind != KIND_F32 || !codebooks || !codes_out || M <= 0 || M > f32->d.dim || k <= 0 || k > 256)
         return fail(JV_ERR_INVALID, "pq_encode_dataset: bad arguments");
     return pq_encode_impl(nullptr, f32->d.rows, f32->d.stride, f32->d.n, f32->d.dim, M, k, codebooks, centroid, codes_out);
@@ -602,7 +823,7 @@ int jv_nvq_encode_batch(const float *rows, int64_t n, int dim, int nsub, const f
 
 int jv_nvq_encode_dataset(jv_dataset f32, int nsub, const float *mean, int learn, float *params_out, uint8_t *bytes_out)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(f32);
     if (!f32 || f32->d.kind != KIND_F32 || !mean || !params_out || !bytes_out || nsub <= 0 || nsub > f32->d.dim)
         return fail(JV_ERR_INVALID, "nvq_encode_dataset: bad arguments");
     return nvq_encode_impl(nullptr, f32->d.rows, f32->d.stride, f32->d.n, f32->d.dim, nsub, mean, learn, params_out, bytes_out);
@@ -614,7 +835,11 @@ int jv_graph_create(int32_t n, int degree, const int32_t *adj0, int32_t entry_no
     NEED_INIT();
     if (!adj0 || !out || n <= 0 || degree <= 0 || degree > MAX_DEGREE || entry_node < 0 || entry_node >= n)
         return fail(JV_ERR_INVALID, "graph_create: bad arguments");
+    // one pass over data that is copied anyway: a neighbour id outside [-1, n) would be an illegal address inside the search kernel
+    for (size_t i = 0, tot = (size_t)n * degree; i < tot; i++)
+        if (adj0[i] < -1 || adj0[i] >= n) return fail(JV_ERR_INVALID, "graph_create: neighbour id out of range");
     jv_graph g = new jv_graph_s();
+    g->device = t_active;
     memset(&g->g, 0, sizeof(GraphDesc));
     cudaError_t e = cudaMalloc((void **)&g->adj0, (size_t)n * degree * 4);
     if (e == cudaSuccess) e = cudaMemcpy(g->adj0, adj0, (size_t)n * degree * 4, cudaMemcpyHostToDevice);
@@ -656,8 +881,10 @@ static int graph_rebuild_upper(jv_graph g)
 
 int jv_graph_add_level(jv_graph g, int32_t count, const int32_t *node_ids, const int32_t *adj)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(g);
     if (!g || count <= 0 || !node_ids || !adj) return fail(JV_ERR_INVALID, "graph_add_level: bad arguments");
+    for (size_t i = 0, tot = (size_t)count * g->g.degree; i < tot; i++)
+        if (adj[i] < -1 || adj[i] >= g->g.n) return fail(JV_ERR_INVALID, "graph_add_level: neighbour id out of range");
     bool has_entry = false;
     for (int i = 0; i < count; i++) {
         if (node_ids[i] < 0 || node_ids[i] >= g->g.n) return fail(JV_ERR_INVALID, "graph_add_level: node id out of range");
@@ -672,7 +899,7 @@ int jv_graph_add_level(jv_graph g, int32_t count, const int32_t *node_ids, const
 int jv_graph_free(jv_graph g)
 {
     if (!g) return JV_OK;
-    if (g_device >= 0) cudaSetDevice(g_device);
+    cudaSetDevice(g->device);
     cudaDeviceSynchronize();
     delete g;
     return JV_OK;
@@ -690,7 +917,7 @@ int jv_graph_info(jv_graph g, int32_t *n, int *degree, int *levels, int32_t *ent
 
 int jv_graph_download(jv_graph g, int level, int32_t *node_ids_out, int32_t *adj_out, int32_t *count_out)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(g);
     if (!g || level < 0 || level >= g->g.levels) return fail(JV_ERR_INVALID, "graph_download: bad level");
     if (level == 0) {
         if (count_out) *count_out = g->g.n;
@@ -713,6 +940,7 @@ static int search_device(jv_graph g, jv_dataset approx, jv_dataset reranker, int
     if (topK < 1 || rerankK < topK) return fail(JV_ERR_INVALID, "graph_search: need 1 <= topK <= rerankK");
     if (rerankK > 4096) return fail(JV_ERR_INVALID, "graph_search: rerankK <= 4096");
     if (approx->d.n != g->g.n) return fail(JV_ERR_INVALID, "graph_search: data set and graph sizes differ");
+    if (approx->device != g->device || (reranker && reranker->device != g->device)) return fail(JV_ERR_INVALID, "graph_search: graph and data sets live on different devices");
     if (reranker && (reranker->d.n != g->g.n || reranker->d.dim != approx->d.dim)) return fail(JV_ERR_INVALID, "graph_search: reranker shape mismatch");
     if (reranker && reranker->d.kind != KIND_F32 && reranker->d.kind != KIND_NVQ)
         return fail(JV_ERR_UNSUPPORTED, "graph_search: the reranker must be fp32 or NVQ (OnDiskGraphIndex.java:705-713)");
@@ -826,7 +1054,7 @@ int jv_graph_search_batch_device_ex(jv_graph g, jv_dataset approx, jv_dataset re
                                     int rerankK, const jv_search_options *opts_device_bits, int32_t *nodes_out_device, float *scores_out_device,
                                     jv_search_stats *stats)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(g);
     if (!g || nq <= 0) return fail(JV_ERR_INVALID, "graph_search: bad arguments");
     int rc;
     if ((rc = t_ctx.init())) return rc;
@@ -845,7 +1073,7 @@ int jv_graph_search_batch_device(jv_graph g, jv_dataset approx, jv_dataset reran
 int jv_graph_search_batch_ex(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric, const float *queries, int nq, int topK, int rerankK,
                              const jv_search_options *opts, int32_t *nodes_out, float *scores_out, jv_search_stats *stats)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(g);
     if (!g || !approx || !queries || !nodes_out || !scores_out || nq <= 0 || topK < 1) return fail(JV_ERR_INVALID, "graph_search: bad arguments");
     int rc;
     const size_t qb = (size_t)nq * approx->d.dim * 4, ob = (size_t)nq * topK * 4;
@@ -871,7 +1099,7 @@ int jv_graph_search_batch(jv_graph g, jv_dataset approx, jv_dataset reranker, in
 
 int jv_graph_build(jv_dataset f32, int metric, const jv_build_params *params, jv_graph *out, double *device_ms)
 {
-    NEED_INIT();
+    ON_DEVICE_OF(f32);
     if (!f32 || !params || !out || f32->d.kind != KIND_F32) return fail(JV_ERR_INVALID, "graph_build: needs an fp32 data set");
     int rc = check_metric(f32->d, metric);
     if (rc) return rc;
@@ -883,6 +1111,7 @@ int jv_graph_build(jv_dataset f32, int metric, const jv_build_params *params, jv
     BuildParams bp;
     bp.degree = degree; bp.beam = params->beam_width; bp.overflow = params->overflow; bp.alpha = params->alpha; bp.max_batch = params->max_batch;
     jv_graph g = new jv_graph_s();
+    g->device = f32->device;
     memset(&g->g, 0, sizeof(GraphDesc));
     cudaError_t e = cudaMalloc((void **)&g->adj0, (size_t)n * degree * 4);
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaMalloc(adjacency)"); }
@@ -965,6 +1194,178 @@ int jv_graph_build_stats(int64_t *scored_vectors, int64_t *batches, int64_t *dro
     if (scored_vectors) *scored_vectors = t_build_stats.searched;
     if (batches) *batches = t_build_stats.batches;
     if (dropped_backlinks) *dropped_backlinks = t_build_stats.dropped_backlinks;
+    return JV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ several GPUs, one process
+// The reference host is ONE JVM whose parallelism is threads (base:vector/VectorizationProvider.java:79-177,
+// base:graph/GraphIndexBuilder.java:440-444), so the sharding of SURVEY §8e has to be reachable from one process: the base
+// range-sharded by contiguous node id over the bound devices, every shard scoring all queries on its own stream, the per-shard
+// top-k keys (global ids) copied to the first device over NVLink (peer copies) and merged there.
+int jv_multi_free(jv_multi m)
+{
+    if (!m) return JV_OK;
+    for (jv_dataset ds : m->shards) jv_dataset_free(ds);
+    for (size_t i = 0; i < m->ctx.size(); i++) {
+        t_active = m->devices[i];
+        cudaSetDevice(m->devices[i]);
+        delete m->ctx[i];
+    }
+    delete m;
+    return JV_OK;
+}
+
+int jv_multi_register_bq(const uint64_t *words, int64_t n, int dim, jv_multi *out)
+{
+    if (!words || !out || n <= 0 || dim <= 0 || n > 0x7fffffffLL) return fail(JV_ERR_INVALID, "multi_register_bq: bad arguments");
+    jv_multi m = new jv_multi_s();
+    m->kind = KIND_BQ; m->dim = dim; m->n = n;
+    const int W = (dim + 63) / 64;
+    int rc = multi_register(m, [&](int, int64_t lo, int64_t cnt, jv_dataset *ds) { return jv_dataset_register_bq(words + (size_t)lo * W, cnt, dim, ds); });
+    if (rc) { jv_multi_free(m); return rc; }
+    *out = m;
+    return JV_OK;
+}
+
+int jv_multi_register_f32(const float *rows, int64_t n, int dim, jv_multi *out)
+{
+    if (!rows || !out || n <= 0 || dim <= 0 || n > 0x7fffffffLL) return fail(JV_ERR_INVALID, "multi_register_f32: bad arguments");
+    jv_multi m = new jv_multi_s();
+    m->kind = KIND_F32; m->dim = dim; m->n = n;
+    int rc = multi_register(m, [&](int, int64_t lo, int64_t cnt, jv_dataset *ds) { return jv_dataset_register_f32(rows + (size_t)lo * dim, cnt, dim, ds); });
+    if (rc) { jv_multi_free(m); return rc; }
+    *out = m;
+    return JV_OK;
+}
+
+int jv_multi_shard_count(jv_multi m) { return m ? (int)m->shards.size() : 0; }
+
+int jv_multi_shard_info(jv_multi m, int shard, int *device, int64_t *first_row, int64_t *rows)
+{
+    if (!m || shard < 0 || shard >= (int)m->shards.size()) return fail(JV_ERR_INVALID, "multi_shard_info: bad shard");
+    if (device) *device = m->devices[shard];
+    if (first_row) *first_row = m->lo[shard];
+    if (rows) *rows = m->lo[shard + 1] - m->lo[shard];
+    return JV_OK;
+}
+
+int jv_multi_topk_bruteforce(jv_multi m, int metric, const float *queries, int nq, int k, int64_t *keys_out)
+{
+    if (!m || !queries || !keys_out || nq <= 0 || k <= 0 || k > 2048) return fail(JV_ERR_INVALID, "multi_topk_bruteforce: bad arguments");
+    const int parts = (int)m->shards.size();
+    if ((long long)parts * k > 16384) return fail(JV_ERR_INVALID, "multi_topk_bruteforce: shards * k <= 16384");
+    const size_t qb = (size_t)nq * m->dim * 4, kb = (size_t)nq * k * 8;
+    std::vector<int> rcs(parts, JV_OK);
+    std::vector<std::string> errs(parts);
+    // the gathered keys live on the first shard's device: [parts][nq][k]
+    ThreadCtx *c0 = m->ctx[0];
+    {
+        t_active = m->devices[0];
+        t_ctx_override = c0;
+        cudaSetDevice(m->devices[0]);
+        int rc = c0->init();
+        if (!rc) rc = c0->ensure(6, kb * parts + kb);
+        t_ctx_override = nullptr;
+        if (rc) return rc;
+    }
+    long long *gathered = (long long *)c0->dbuf[6];
+    auto work = [&](int i) {
+        t_active = m->devices[i];
+        t_ctx_override = m->ctx[i];
+        ThreadCtx &c = *m->ctx[i];
+        int rc = JV_OK;
+        do {
+            if (cudaSetDevice(m->devices[i]) != cudaSuccess) { rc = fail(JV_ERR_CUDA, "cudaSetDevice"); break; }
+            if ((rc = c.init()) || (rc = c.ensure(0, qb)) || (rc = c.ensure(5, kb))) break;
+            if (cudaMemcpyAsync(c.dbuf[0], queries, qb, cudaMemcpyHostToDevice, c.stream) != cudaSuccess) { rc = fail(JV_ERR_CUDA, "H2D queries"); break; }
+            if ((rc = topk_device(m->shards[i], metric, (const float *)c.dbuf[0], nq, k, m->lo[i], (long long *)c.dbuf[5]))) break;
+            // shard keys -> the first device (NVLink peer copy; a plain device copy for shard 0)
+            cudaError_t e = cudaMemcpyPeerAsync(gathered + (size_t)i * nq * k, m->devices[0], c.dbuf[5], m->devices[i], kb, c.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "peer copy of shard keys");
+        } while (0);
+        rcs[i] = rc;
+        if (rc) errs[i] = t_err;
+        t_ctx_override = nullptr;
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < parts; i++) th.emplace_back(work, i);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int i = 0; i < parts; i++)
+        if (rcs[i]) return fail(rcs[i], "shard " + std::to_string(i) + ": " + errs[i]);
+    // merge on the first device: [parts][nq][k] -> per query the k best of parts * k
+    t_active = m->devices[0];
+    t_ctx_override = c0;
+    int rc = JV_OK;
+    do {
+        if (cudaSetDevice(m->devices[0]) != cudaSuccess) { rc = fail(JV_ERR_CUDA, "cudaSetDevice"); break; }
+        long long *merged = gathered + (size_t)parts * nq * k;
+        cudaError_t e = parts == 1 ? cudaMemcpyAsync(merged, gathered, kb, cudaMemcpyDeviceToDevice, c0->stream)
+                                   : launch_topk_merge_strided(gathered, nq, parts, k, merged, c0->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(keys_out, merged, kb, cudaMemcpyDeviceToHost, c0->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c0->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "merge");
+    } while (0);
+    t_ctx_override = nullptr;
+    return rc;
+}
+
+// replicas: graph + data sets registered once per device (jv_gpu_set_device + the ordinary register calls); the query batch is
+// split into contiguous slices, one per replica, searched concurrently (no data-path exchange: SURVEY §8e "shard queries")
+int jv_multi_graph_search_batch(int replicas, const jv_graph *graphs, const jv_dataset *approx, const jv_dataset *rerankers, int metric,
+                                const float *queries, int nq, int topK, int rerankK, const jv_search_options *opts, int32_t *nodes_out,
+                                float *scores_out, jv_search_stats *stats)
+{
+    if (replicas <= 0 || !graphs || !approx || !queries || !nodes_out || !scores_out || nq <= 0) return fail(JV_ERR_INVALID, "multi_graph_search: bad arguments");
+    if (opts && opts->accept_bits && opts->accept_stride_words == 0 && replicas > 1) { /* a shared bitset is simply reused by every slice */ }
+    const int parts = std::min(replicas, nq);
+    const int dim = approx[0]->d.dim;
+    // worker threads come and go; their contexts (streams, visited-table scratch) must not: one persistent context per device,
+    // calls of this entry point are serialised
+    static ThreadCtx *worker_ctx[MAX_DEVICES] = {nullptr};
+    static std::mutex worker_mu;
+    std::lock_guard<std::mutex> lk(worker_mu);
+    for (int i = 0; i < parts; i++) {
+        if (!graphs[i] || !approx[i]) return fail(JV_ERR_INVALID, "multi_graph_search: null replica handle");
+        if (!worker_ctx[graphs[i]->device]) worker_ctx[graphs[i]->device] = new ThreadCtx();
+        for (int j = 0; j < i; j++)
+            if (graphs[j]->device == graphs[i]->device) return fail(JV_ERR_INVALID, "multi_graph_search: two replicas on one device");
+    }
+    std::vector<int> rcs(parts, JV_OK);
+    std::vector<std::string> errs(parts);
+    std::vector<jv_search_stats> st(parts);
+    std::vector<int64_t> lo;
+    shard_ranges(nq, parts, lo);
+    auto work = [&](int i) {
+        const int q0 = (int)lo[i], cq = (int)(lo[i + 1] - lo[i]);
+        jv_search_options o2;
+        const jv_search_options *op = opts;
+        if (opts && opts->accept_bits && opts->accept_stride_words) {
+            o2 = *opts;
+            o2.accept_bits = opts->accept_bits + (size_t)q0 * opts->accept_stride_words;
+            op = &o2;
+        }
+        t_ctx_override = worker_ctx[graphs[i]->device];
+        rcs[i] = jv_graph_search_batch_ex(graphs[i], approx[i], rerankers ? rerankers[i] : nullptr, metric, queries + (size_t)q0 * dim, cq, topK, rerankK, op,
+                                          nodes_out + (size_t)q0 * topK, scores_out + (size_t)q0 * topK, &st[i]);
+        if (rcs[i]) errs[i] = t_err;
+        t_ctx_override = nullptr;
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < parts; i++) th.emplace_back(work, i);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int i = 0; i < parts; i++)
+        if (rcs[i]) return fail(rcs[i], "replica " + std::to_string(i) + ": " + errs[i]);
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        for (int i = 0; i < parts; i++) {
+            stats->visited += st[i].visited; stats->expanded += st[i].expanded; stats->expanded_base += st[i].expanded_base;
+            stats->reranked += st[i].reranked; stats->retried += st[i].retried;
+            stats->device_ms = std::max(stats->device_ms, st[i].device_ms);  // the replicas run concurrently: the step takes the slowest one
+        }
+    }
     return JV_OK;
 }
 

@@ -47,16 +47,28 @@ struct TopkScratch {
 cudaError_t launch_topk_bruteforce(const DataDesc &d, int metric, const float *blobs_dev, int nq, int k, const TopkScratch &ts,
                                    long long *keys_out_dev, int *overflow_flag_dev, cudaStream_t s);
 
+cudaError_t launch_add_int(int *dst_dev, const int *src_dev, cudaStream_t s);
 // keys[i] -> same score, node id + id_base (KEY_MIN pads untouched)
 cudaError_t launch_key_rebase(long long *keys_dev, long long count, long long id_base, cudaStream_t s);
 // per query: the k best of parts*k keys (the NCCL-gathered per-shard top-k), descending
 cudaError_t launch_topk_merge(const long long *keys_in_dev, int nq, int parts, int k, long long *keys_out_dev, cudaStream_t s);
+// the same for keys laid out [parts][nq][k] (shard-major, what peer copies / all_gather produce)
+cudaError_t launch_topk_merge_strided(const long long *keys_in_dev, int nq, int parts, int k, long long *keys_out_dev, cudaStream_t s);
 
 cudaError_t launch_bq_encode(const float *rows_dev, long long n, int dim, int row_stride, unsigned long long *words_dev, cudaStream_t s);
 cudaError_t launch_pq_encode(const DataDesc &pq, const float *rows_dev, long long n, int row_stride, uint8_t *codes_dev, cudaStream_t s);
 cudaError_t launch_pq_self_magnitudes(const DataDesc &pq, float *mag_dev, cudaStream_t s);
 cudaError_t launch_nvq_encode(const float *rows_dev, long long n, int row_stride, int nsub, const int *sizes_dev, const int *offsets_dev,
                               const float *mean_dev, int learn, float *params_dev, uint8_t *bytes_dev, int byte_stride, cudaStream_t s);
+
+// ---- bq_imma.cu: BQ Hamming top-k as an exact u8 contraction on the tensor cores (IMMA.16832) ----
+constexpr int BQ_IMMA_CAP = 8192;  // captured keys per query in the filter pass
+bool bq_imma_supported(const DataDesc &d, int k);
+size_t bq_imma_scratch_bytes(long long n, int nq, int W);
+// fully asynchronous on `s`: keys_out_dev [nq][k] best first with GLOBAL ids (row + id_base); *unresolved_dev = number of queries
+// the integer-threshold path could not resolve (a Hamming bin wider than the buffer) — the caller falls back for those batches
+cudaError_t launch_bq_topk_imma(const DataDesc &d, const float *queries_dev, int nq, int k, long long id_base, void *scratch_dev,
+                                long long *keys_out_dev, int *unresolved_dev, cudaStream_t s);
 
 // ---- search.cu ----
 constexpr int MAX_LIST_CAP = 8192;  // longest candidate list (entries) the search kernel keeps in shared memory

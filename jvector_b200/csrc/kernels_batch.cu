@@ -543,6 +543,14 @@ cudaError_t launch_topk_bruteforce(const DataDesc &d, int metric, const float *b
     return cudaGetLastError();  // overflow_flag_dev still holds the number of unresolved queries
 }
 
+__global__ void add_int_kernel(int *dst, const int *src) { *dst += *src; }
+cudaError_t launch_add_int(int *dst_dev, const int *src_dev, cudaStream_t s)
+{
+    add_int_kernel<<<1, 1, 0, s>>>(dst_dev, src_dev);
+    g_launches++;
+    return cudaGetLastError();
+}
+
 // the low word of a key is ~node: adding id_base to the node subtracts it from the key (no borrow: node + base < 2^31)
 __global__ void __launch_bounds__(256) key_rebase_kernel(long long *keys, long long count, long long id_base)
 {
@@ -567,6 +575,31 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const long long *__rest
     __syncthreads();
     bitonic_sort_desc(skeys, total_pow2);
     for (int i = threadIdx.x; i < k; i += blockDim.x) out[(size_t)q * k + i] = i < total ? skeys[i] : KEY_MIN;
+}
+
+// same merge over the layout the peer copies produce: in [parts][nq][k]
+__global__ void __launch_bounds__(256) topk_merge_strided_kernel(const long long *__restrict__ in, int nq, int parts, int k, int total_pow2, long long *__restrict__ out)
+{
+    extern __shared__ long long skeys[];
+    const int q = blockIdx.x, total = parts * k;
+    for (int i = threadIdx.x; i < total_pow2; i += blockDim.x) {
+        const int p = i / k, j = i - p * k;
+        skeys[i] = i < total ? in[((size_t)p * nq + q) * k + j] : KEY_MIN;
+    }
+    __syncthreads();
+    bitonic_sort_desc(skeys, total_pow2);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) out[(size_t)q * k + i] = i < total ? skeys[i] : KEY_MIN;
+}
+
+cudaError_t launch_topk_merge_strided(const long long *keys_in_dev, int nq, int parts, int k, long long *keys_out_dev, cudaStream_t s)
+{
+    const int total = parts * k, p2 = next_pow2(total);
+    cudaError_t e;
+    if ((size_t)p2 * 8 > 48 * 1024)
+        if ((e = cudaFuncSetAttribute(topk_merge_strided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p2 * 8)) != cudaSuccess) return e;
+    topk_merge_strided_kernel<<<nq, 256, (size_t)p2 * 8, s>>>(keys_in_dev, nq, parts, k, p2, keys_out_dev);
+    g_launches++;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_topk_merge(const long long *keys_in_dev, int nq, int parts, int k, long long *keys_out_dev, cudaStream_t s)

@@ -75,28 +75,51 @@ class ShardedBruteForce:
 
 
 def gpu_sharded_bruteforce(dist, vectors, vsf, id_base):
-    """ShardedBruteForce over a device-resident shard (`vectors` holds rows [id_base, id_base + n))."""
+    """ShardedBruteForce over a device-resident shard (`vectors` holds rows [id_base, id_base + n)).
+
+    BQ shards take the stream-ordered C entry points: local top-k (tensor-core contraction), the all-gather and the merge are
+    enqueued on torch's current stream with no host synchronisation; `status()` (call it after the timed region) returns the
+    number of queries the device left unresolved since the last check. Other kinds use the synchronous entry points."""
     import ctypes as C
 
     import torch
 
     from . import _native as nat
     lib = nat.init()
+    status = torch.zeros(2, dtype=torch.int32, device="cuda")  # [0] this step, [1] running total
+    use_async = [True]
 
     def local_topk(queries, k):
         q = queries if isinstance(queries, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).cuda()
         q = q.contiguous()
         keys = torch.empty((q.shape[0], k), dtype=torch.int64, device=q.device)
+        if use_async[0]:
+            st = torch.cuda.current_stream().cuda_stream
+            rc = lib.jv_topk_bruteforce_device_async(vectors._h, int(vsf), C.c_void_p(q.data_ptr()), q.shape[0], k, int(id_base), C.c_void_p(keys.data_ptr()),
+                                                     C.c_void_p(status.data_ptr()), C.c_void_p(st))
+            if rc == 0:
+                status[1] += status[0]
+                return keys
+            if rc != -5:  # JV_ERR_UNSUPPORTED: not a BQ shard the contraction kernel takes
+                nat.check(rc)
+            use_async[0] = False
         torch.cuda.synchronize()
         nat.check(lib.jv_topk_bruteforce_device(vectors._h, int(vsf), C.c_void_p(q.data_ptr()), q.shape[0], k, int(id_base), C.c_void_p(keys.data_ptr())))
         return keys
 
     def merge(gathered, k):
-        world, nq, kk = gathered.shape
-        flat = gathered.permute(1, 0, 2).contiguous()  # [nq][world*k]
+        world, nq, kk = gathered.shape  # shard-major, as all_gather_into_tensor leaves it
+        g = gathered.contiguous()
         out = torch.empty((nq, k), dtype=torch.int64, device=gathered.device)
+        if kk == k:
+            st = torch.cuda.current_stream().cuda_stream
+            nat.check(lib.jv_topk_merge_device_async(C.c_void_p(g.data_ptr()), nq, world, kk, C.c_void_p(out.data_ptr()), C.c_void_p(st)))
+            return out
+        flat = g.permute(1, 0, 2).contiguous()
         torch.cuda.synchronize()
         nat.check(lib.jv_topk_merge_device(C.c_void_p(flat.data_ptr()), nq, world, kk, C.c_void_p(out.data_ptr())))
         return out
 
-    return ShardedBruteForce(dist, local_topk, merge)
+    sb = ShardedBruteForce(dist, local_topk, merge)
+    sb.status = lambda: int(status[1].item())
+    return sb

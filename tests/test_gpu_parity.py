@@ -184,6 +184,137 @@ def test_bq_exact(jv, oracle, dim):
     bqv.close()
 
 
+def _bq_world(jv, oracle, rng, n, dim, nq, dup=0):
+    data = rng.standard_normal((n, dim)).astype(np.float32)
+    if dup:
+        data[n - dup:] = data[:dup]  # duplicated rows: identical distances for every query, order decided by node id alone
+    words = jv.bq_encode_all(data)
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    queries[0] = data[3]
+    W = words.shape[1]
+    qw = np.zeros((nq, W), np.uint64)
+    for i in range(nq):
+        oracle.jvo_bq_encode(fp(queries[i]), dim, wp(qw[i]))
+    return words, queries, qw
+
+
+@pytest.mark.parametrize("dim,n,nq,k", [(1536, 20000, 130, 100), (256, 9000, 7, 10), (128, 60000, 40, 100), (2048, 5000, 3, 1), (1000, 4100, 129, 33)])
+def test_bq_bruteforce_tensor_core_contraction_exact(jv, oracle, dim, n, nq, k):
+    # csrc/bq_imma.cu (n >= 4096, even word count): Hamming top-k as a u8 contraction on IMMA + integer thresholds. Integer work:
+    # every key must equal the scalar popcount restatement, ties to the smaller node id. dim 128 over 60 000 rows makes Hamming
+    # bins of thousands of rows (the capture buffer overflows and the redo / fallback paths run); the duplicated tail makes exact
+    # key ties; nq 129 / 130 crosses a query tile.
+    rng = np.random.default_rng(dim + n)
+    words, queries, qw = _bq_world(jv, oracle, rng, n, dim, nq, dup=64)
+    bqv = jv.BQVectors(words, dim)
+    _, _, keys = jv.topk_bruteforce(bqv, o.COSINE, queries, k)
+    want = np.empty((nq, k), np.int64)
+    oracle.jvo_bq_bruteforce_batch(wp(words), n, dim, wp(qw), nq, k, 8, lp(want))
+    bad = np.flatnonzero((keys != want).any(axis=1))
+    assert len(bad) == 0, (len(bad), bad[:5], keys[bad[:1]], want[bad[:1]])
+    # the popcount kernels of round 1 stay reachable (JV_BQ_BRUTEFORCE=popc) and must agree as well
+    import os
+    os.environ["JV_BQ_BRUTEFORCE"] = "popc"
+    try:
+        _, _, keys2 = jv.topk_bruteforce(bqv, o.COSINE, queries[:5], k)
+    finally:
+        del os.environ["JV_BQ_BRUTEFORCE"]
+    assert np.array_equal(keys2, want[:5])
+    bqv.close()
+
+
+def test_bq_bruteforce_giant_tie_bin_falls_back_exactly(jv, oracle):
+    # 11 000 copies of one row: for the query equal to that row, Hamming bin 0 alone is wider than the capture buffer, the
+    # integer-threshold path reports the query unresolved and the key-threshold kernels must produce the exact answer
+    rng = np.random.default_rng(77)
+    n, dim, nq, k = 30000, 256, 6, 50
+    data = rng.standard_normal((n, dim)).astype(np.float32)
+    data[5000:16000] = data[3]
+    words = jv.bq_encode_all(data)
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    queries[0] = data[3]
+    qw = np.zeros((nq, words.shape[1]), np.uint64)
+    for i in range(nq):
+        oracle.jvo_bq_encode(fp(queries[i]), dim, wp(qw[i]))
+    bqv = jv.BQVectors(words, dim)
+    _, _, keys = jv.topk_bruteforce(bqv, o.COSINE, queries, k)
+    want = np.empty((nq, k), np.int64)
+    oracle.jvo_bq_bruteforce_batch(wp(words), n, dim, wp(qw), nq, k, 8, lp(want))
+    assert np.array_equal(keys, want)
+    bqv.close()
+
+
+def test_bq_bruteforce_stream_ordered_shards(jv, oracle):
+    # the multi-process path's building blocks on ONE device: two range shards -> stream-ordered local top-k (global ids) ->
+    # shard-major gather -> stream-ordered merge, no host synchronisation in between; must equal the unsharded oracle, bit for bit
+    import torch
+
+    from jvector_b200 import parallel as par
+    rng = np.random.default_rng(19)
+    n, dim, nq, k = 16000, 512, 50, 20
+    words, queries, qw = _bq_world(jv, oracle, rng, n, dim, nq, dup=16)
+    halves = [jv.BQVectors(words[:7000], dim), jv.BQVectors(words[7000:], dim)]
+    qd = torch.from_numpy(queries).cuda()
+    sbs = [par.gpu_sharded_bruteforce(None, halves[0], o.COSINE, 0), par.gpu_sharded_bruteforce(None, halves[1], o.COSINE, 7000)]
+    parts = [sb.local_topk(qd, k) for sb in sbs]
+    merged = sbs[0].merge(torch.stack(parts), k)
+    torch.cuda.synchronize()
+    assert sbs[0].status() == 0 and sbs[1].status() == 0
+    want = np.empty((nq, k), np.int64)
+    oracle.jvo_bq_bruteforce_batch(wp(words), n, dim, wp(qw), nq, k, 8, lp(want))
+    assert np.array_equal(merged.cpu().numpy(), want)
+    for v in halves:
+        v.close()
+
+
+def test_multi_device_in_one_process(jv, oracle):
+    # one process driving several GPUs through the C ABI alone (what a single JVM needs): range-sharded brute force with peer
+    # copies + device merge, and replica graph search with the batch split across devices. With one visible device the same
+    # entry points run as their 1-shard / 1-replica degenerate.
+    import ctypes as C
+
+    from jvector_b200 import _native as nat
+    lib = nat.load()
+    ndev = min(lib.jv_gpu_device_count(), 8)
+    nat.check(lib.jv_gpu_init_mask((1 << ndev) - 1))
+    rng = np.random.default_rng(29)
+    n, dim, nq, k = 30000, 1536, 33, 50
+    words, queries, qw = _bq_world(jv, oracle, rng, n, dim, nq, dup=8)
+    m = C.c_void_p()
+    nat.check(lib.jv_multi_register_bq(wp(words), n, dim, C.byref(m)))
+    assert lib.jv_multi_shard_count(m) == ndev
+    keys = np.empty((nq, k), np.int64)
+    nat.check(lib.jv_multi_topk_bruteforce(m, o.COSINE, fp(queries), nq, k, lp(keys)))
+    want = np.empty((nq, k), np.int64)
+    oracle.jvo_bq_bruteforce_batch(wp(words), n, dim, wp(qw), nq, k, 8, lp(want))
+    assert np.array_equal(keys, want)
+    nat.check(lib.jv_multi_free(m))
+    # replica graph search
+    gn, gdim = 3000, 48
+    data = o.random_unit_vectors(rng, gn, gdim)
+    adj = np.empty((gn, 12), np.int32)
+    entry = oracle.jvo_graph_build_f32(o.DOT_PRODUCT, fp(data), gn, gdim, 12, 60, 1.2, 1.2, ip(adj))
+    gq = o.random_unit_vectors(rng, 41, gdim)
+    graphs, vecs = [], []
+    for d in range(ndev):
+        nat.check(lib.jv_gpu_set_device(d))
+        vecs.append(jv.F32Vectors(data))
+        graphs.append(jv.GraphIndex(adj, entry))
+        assert lib.jv_dataset_device(vecs[-1]._h) == d
+    nat.check(lib.jv_gpu_set_device(0))
+    GA = (C.c_void_p * ndev)(*[g._h for g in graphs])
+    VA = (C.c_void_p * ndev)(*[v._h for v in vecs])
+    nodes = np.empty((41, 10), np.int32)
+    scores = np.empty((41, 10), np.float32)
+    st = nat.SearchStats()
+    nat.check(lib.jv_multi_graph_search_batch(ndev, GA, VA, None, o.DOT_PRODUCT, fp(gq), 41, 10, 40, None, ip(nodes), fp(scores), C.byref(st)))
+    g = o.make_graph(adj, entry)
+    wn, ws, wv, wr = _oracle_search(oracle, g, lambda q: oracle.jvo_scorer_f32(o.DOT_PRODUCT, fp(data), gn, gdim, fp(q)), gq, 10, 40)
+    assert np.array_equal(nodes, wn) and np.array_equal(scores.view(np.int32), ws.view(np.int32)) and st.visited == wv
+    for x in graphs + vecs:
+        x.close()
+
+
 # ------------------------------------------------------------------------------------------------ NVQ
 @pytest.mark.parametrize("dim,nsub", [(64, 1), (65, 2), (256, 4), (768, 2), (100, 3)])
 def test_nvq_scores(jv, oracle, dim, nsub):
