@@ -189,6 +189,16 @@ JV_API int jv_graph_create(int32_t n, int degree, const int32_t *adj0, int32_t e
 /* add level 1, 2, ... in order; node_ids[count] are the members, adj [count][degree] their lists at that level.
  * The entry node must be a member of the last level added. */
 JV_API int jv_graph_add_level(jv_graph g, int32_t count, const int32_t *node_ids, const int32_t *adj);
+/* FusedPQ feature (base:graph/disk/feature/FusedPQ.java:99-101,122-141,215-241): pack, for every node, its level-0 neighbour ids
+ * and the neighbours' PQ codes into ONE record [degree int32 ids][degree code rows, zero padded] (built on the device from the
+ * resident adjacency and codes). A later search whose `approx` is this PQ data set then scores neighbours from the expanded
+ * node's record — FusedPQDecoder.similarityToNeighbor (base:quantization/FusedPQDecoder.java:84-114), the
+ * "useEdgeLoading && level == 0" branch of OnDiskGraphIndex.java:639-651 — one contiguous read per hop; upper levels and the
+ * entry node use the plain code rows (the hierarchy's cached source features, FusedPQDecoder.java:96-105). Scores are those of
+ * the plain PQ walk. JV_FUSED_PQ=0 in the environment ignores the records (A/B timing). */
+JV_API int jv_graph_fuse_pq(jv_graph g, jv_dataset pq);
+/* records_out [n][*record_bytes] (query the size with records_out = NULL first) */
+JV_API int jv_graph_fused_download(jv_graph g, uint8_t *records_out, int *record_bytes);
 JV_API int jv_graph_free(jv_graph g);
 JV_API int jv_graph_info(jv_graph g, int32_t *n, int *degree, int *levels, int32_t *entry_node);
 JV_API int jv_graph_download(jv_graph g, int level, int32_t *node_ids_out, int32_t *adj_out, int32_t *count_out);

@@ -249,6 +249,18 @@ class GraphIndex:
         check(nat.load().jv_graph_download(self._h, level, ip(ids), ip(adj), C.byref(cnt)))
         return ids, adj
 
+    def fuse_pq(self, pq_vectors):
+        """FusedPQ feature: pack every node's neighbour codes next to its adjacency row (jv_graph_fuse_pq)."""
+        check(nat.load().jv_graph_fuse_pq(self._h, pq_vectors._h))
+        return self
+
+    def fused_records(self):
+        rb = C.c_int()
+        check(nat.load().jv_graph_fused_download(self._h, None, C.byref(rb)))
+        out = np.empty((self.info()["n"], rb.value), dtype=np.uint8)
+        check(nat.load().jv_graph_fused_download(self._h, bp(out), C.byref(rb)))
+        return out
+
     def close(self):
         if self._h:
             nat.load().jv_graph_free(self._h)

@@ -162,6 +162,7 @@ struct jv_query_s {
 struct jv_graph_s {
     int device = 0;
     GraphDesc g;
+    uint8_t *fused = nullptr;  // FusedPQ records
     int32_t *adj0 = nullptr;
     int32_t *upper_row = nullptr;
     int32_t *upper_adj = nullptr;
@@ -170,7 +171,7 @@ struct jv_graph_s {
     std::vector<std::vector<int32_t>> level_adj;
     ~jv_graph_s()
     {
-        cudaFree(adj0); cudaFree(upper_row); cudaFree(upper_adj); cudaFree(upper_off);
+        cudaFree(adj0); cudaFree(upper_row); cudaFree(upper_adj); cudaFree(upper_off); cudaFree(fused);
     }
 };
 
@@ -894,6 +895,36 @@ int jv_graph_add_level(jv_graph g, int32_t count, const int32_t *node_ids, const
     g->level_ids.emplace_back(node_ids, node_ids + count);
     g->level_adj.emplace_back(adj, adj + (size_t)count * g->g.degree);
     return graph_rebuild_upper(g);
+}
+
+int jv_graph_fuse_pq(jv_graph g, jv_dataset pq)
+{
+    ON_DEVICE_OF(g);
+    if (!pq || pq->d.kind != KIND_PQ) return fail(JV_ERR_INVALID, "graph_fuse_pq: needs a PQ data set");
+    if (pq->device != g->device || pq->d.n != g->g.n) return fail(JV_ERR_INVALID, "graph_fuse_pq: data set and graph differ in device or size");
+    int rc;
+    if ((rc = t_ctx.init())) return rc;
+    const int rec = (g->g.degree * (4 + pq->d.code_stride) + 15) & ~15;
+    cudaFree(g->fused);
+    g->fused = nullptr;
+    g->g.fused = nullptr;
+    CK(cudaMalloc((void **)&g->fused, (size_t)g->g.n * rec), "cudaMalloc(fused records)");
+    CK(launch_fuse_pq(g->g, pq->d, g->fused, rec, t_ctx.stream), "fuse_pq");
+    CK(cudaStreamSynchronize(t_ctx.stream), "fuse_pq");
+    g->g.fused = g->fused;
+    g->g.fused_codes_of = pq->d.codes;
+    g->g.fused_rec = rec;
+    g->g.fused_code_stride = pq->d.code_stride;
+    return JV_OK;
+}
+
+int jv_graph_fused_download(jv_graph g, uint8_t *records_out, int *record_bytes)
+{
+    ON_DEVICE_OF(g);
+    if (!g->fused) return fail(JV_ERR_INVALID, "graph_fused_download: jv_graph_fuse_pq has not been called");
+    if (record_bytes) *record_bytes = g->g.fused_rec;
+    if (records_out) CK(cudaMemcpy(records_out, g->fused, (size_t)g->g.n * g->g.fused_rec, cudaMemcpyDeviceToHost), "D2H fused records");
+    return JV_OK;
 }
 
 int jv_graph_free(jv_graph g)

@@ -534,7 +534,7 @@ cudaError_t build_graph_flat(const DataDesc &d, int metric, const BuildParams &b
     JV_TRY(cudaMalloc(&overflow, (size_t)max_batch));
 
     {
-        GraphDesc g;
+        GraphDesc g = {};
         g.n = n; g.degree = row_cap; g.levels = 1; g.entry_node = 0; g.entry_level = 0;
         g.adj0 = adj; g.upper_row = nullptr; g.upper_adj = nullptr; g.upper_off = nullptr;
         int inserted = 1;  // node 0 is the entry point with an empty list

@@ -21,6 +21,12 @@ struct GraphDesc {
     const int32_t *upper_row;  // [(levels-1)][n] row index or -1 (nullptr when levels == 1)
     const int32_t *upper_adj;  // rows of all upper levels, concatenated
     const long long *upper_off;  // [(levels-1)] first row of each level in upper_adj (device)
+    // FusedPQ feature (base:graph/disk/feature/FusedPQ.java): per node ONE record = [degree int32 neighbour ids][degree code rows
+    // of fused_code_stride bytes, zero padded], so a level-0 hop of a PQ walk is one contiguous read. nullptr = not fused.
+    const uint8_t *fused;
+    const uint8_t *fused_codes_of;  // the PQ code array the records were packed from (identity of the data set they belong to)
+    int fused_rec;                  // bytes per record (multiple of 16)
+    int fused_code_stride;
 };
 
 struct SearchCounters {  // device-side totals
@@ -69,6 +75,9 @@ size_t bq_imma_scratch_bytes(long long n, int nq, int W);
 // the integer-threshold path could not resolve (a Hamming bin wider than the buffer) — the caller falls back for those batches
 cudaError_t launch_bq_topk_imma(const DataDesc &d, const float *queries_dev, int nq, int k, long long id_base, void *scratch_dev,
                                 long long *keys_out_dev, int *unresolved_dev, cudaStream_t s);
+
+// FusedPQ.writeInline (FusedPQ.java:122-141) for every node: records[node] = ids + the neighbours' code rows in neighbour order
+cudaError_t launch_fuse_pq(const GraphDesc &g, const DataDesc &pq, uint8_t *records_dev, int rec_bytes, cudaStream_t s);
 
 // ---- search.cu ----
 constexpr int MAX_LIST_CAP = 8192;  // longest candidate list (entries) the search kernel keeps in shared memory

@@ -614,6 +614,38 @@ cudaError_t launch_topk_merge(const long long *keys_in_dev, int nq, int parts, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// FusedPQ.writeInline (base:graph/disk/feature/FusedPQ.java:122-141): one record per node = its level-0 neighbour ids followed by
+// the neighbours' PQ codes in neighbour order, zero padded to the full degree. One warp per (node, neighbour slot) code row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fuse_pq_kernel(const int32_t *__restrict__ adj0, int n, int degree, const uint8_t *__restrict__ codes, int code_stride,
+                                                      uint8_t *__restrict__ records, int rec_bytes)
+{
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= (long long)n * degree) return;
+    const int node = (int)(warp / degree), slot = (int)(warp - (long long)node * degree);
+    uint8_t *rec = records + (size_t)node * rec_bytes;
+    const int32_t f = adj0[(size_t)node * degree + slot];
+    if (lane == 0) reinterpret_cast<int32_t *>(rec)[slot] = f;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(rec + 4 * degree + (size_t)slot * code_stride);
+    const uint32_t *src = f >= 0 ? reinterpret_cast<const uint32_t *>(codes + (size_t)f * code_stride) : nullptr;
+    for (int i = lane; i < (code_stride >> 2); i += 32) dst[i] = src ? src[i] : 0u;
+    // bytes between the last code row and the 16-byte rounded record end
+    if (slot == degree - 1)
+        for (int o = 4 * degree + degree * code_stride + lane; o < rec_bytes; o += 32) rec[o] = 0;
+}
+
+cudaError_t launch_fuse_pq(const GraphDesc &g, const DataDesc &pq, uint8_t *records_dev, int rec_bytes, cudaStream_t s)
+{
+    const long long warps = (long long)g.n * g.degree;
+    const long long blocks = (warps * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    fuse_pq_kernel<<<(unsigned)blocks, 256, 0, s>>>(g.adj0, g.n, g.degree, pq.codes, pq.code_stride, records_dev, rec_bytes);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // bulk encoders
 // ------------------------------------------------------------------------------------------------
 // BinaryQuantization.encodeTo (BinaryQuantization.java:96-109): one warp per 32 dimensions via ballot

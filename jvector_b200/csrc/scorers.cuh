@@ -256,9 +256,8 @@ __device__ __forceinline__ void score_f32_pair(const DataDesc &d, const float *b
 // (DefaultVectorUtilSupport.java:303-309; native-c:...:662-724,821-879). 8 lanes per code row, 4 codes per 32-bit load.
 // ------------------------------------------------------------------------------------------------
 template <int METRIC>
-__device__ __forceinline__ float score_pq(const DataDesc &d, const float *lut, int node, int g)
+__device__ __forceinline__ float score_pq_codes(const DataDesc &d, const float *lut, const uint8_t *__restrict__ c, int g)
 {
-    const uint8_t *c = d.codes + (size_t)node * d.code_stride;
     const int k = d.k, M = d.M;
     float s = 0.f, a = 0.f;
     const int M4 = M >> 2;
@@ -285,6 +284,12 @@ __device__ __forceinline__ float score_pq(const DataDesc &d, const float *lut, i
         s = __fdiv_rn(s, __fsqrt_rn(__fmul_rn(a, lut[M * k])));  // native-c:...:879
     }
     return score_map(METRIC, s);
+}
+
+template <int METRIC>
+__device__ __forceinline__ float score_pq(const DataDesc &d, const float *lut, int node, int g)
+{
+    return score_pq_codes<METRIC>(d, lut, d.codes + (size_t)node * d.code_stride, g);
 }
 
 // ------------------------------------------------------------------------------------------------

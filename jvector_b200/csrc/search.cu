@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
     long long *heap = cand_keys + MAX_DEGREE;  // 1-based, rerankK entries
     int32_t *cand_ids = reinterpret_cast<int32_t *>(heap + ((P.rerankK + 2) & ~1));
     uint8_t *cand_acc = reinterpret_cast<uint8_t *>(cand_ids + MAX_DEGREE);
-    uint8_t *flags0 = cand_acc + MAX_DEGREE;
+    uint8_t *cand_slot = cand_acc + MAX_DEGREE;  // fused PQ: position of the candidate inside the expanded node's record
+    uint8_t *flags0 = cand_slot + MAX_DEGREE;
     uint8_t *flags1 = flags0 + P.list_alloc;
     __shared__ float red[36];
     __shared__ int s_q, s_n, s_hsize, s_drop, s_cnt;
@@ -260,11 +261,20 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
                     const int32_t row = P.g.upper_row[(size_t)(lvl - 1) * P.g.n + node];
                     nb = row >= 0 ? P.g.upper_adj + ((size_t)P.g.upper_off[lvl - 1] + row) * degree : nullptr;
                 }
+                // FusedPQ (OnDiskGraphIndex.java:639-651, "useEdgeLoading && level == 0"): ids and the neighbours' codes come from the
+                // expanded node's own record
+                const bool fused = KIND == KIND_PQ && lvl == 0 && P.g.fused != nullptr;
+                const uint8_t *rec = fused ? P.g.fused + (size_t)node * P.g.fused_rec : nullptr;
+                if (fused) nb = reinterpret_cast<const int32_t *>(rec);
                 // processNeighbors: score a neighbour only if visited.add() says it is new (OnHeapGraphIndex.java:478)
                 if (nb)
                     for (int t = tid; t < degree; t += SEARCH_THREADS) {
                         const int32_t f = __ldg(nb + t);
-                        if (f >= 0 && visited_insert(table, vmask, P.visited_shift, f)) cand_ids[atomicAdd(&s_n, 1)] = f;
+                        if (f >= 0 && visited_insert(table, vmask, P.visited_shift, f)) {
+                            const int slot = atomicAdd(&s_n, 1);
+                            cand_ids[slot] = f;
+                            if (KIND == KIND_PQ) cand_slot[slot] = (uint8_t)t;
+                        }
                     }
                 // Speculation by the otherwise idle warps (PQ / BQ only: their traversal is a latency chain and HBM is idle, while
                 // the fp32 / NVQ paths are bandwidth-bound and must not waste it): the entries right behind p are the likeliest to
@@ -274,7 +284,11 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
                     const int w = tid >> 5;
                     if (w >= 1 && w <= 3) {
                         const int pp = p + w;
-                        if (pp < size && !(fcur[pp] & F_EXPANDED)) {
+                        if (pp < size && !(fcur[pp] & F_EXPANDED) && KIND == KIND_PQ && P.g.fused) {
+                            // one record = ids + codes: pull its lines towards L2 (25 x 128 B at degree 32, M = 96)
+                            const char *r2 = reinterpret_cast<const char *>(P.g.fused + (size_t)key_node(cur[pp]) * P.g.fused_rec);
+                            for (int o = (tid & 31) * 128; o < P.g.fused_rec; o += 32 * 128) prefetch_l2(r2 + o);
+                        } else if (pp < size && !(fcur[pp] & F_EXPANDED)) {
                             const int32_t *nb2 = P.g.adj0 + (size_t)key_node(cur[pp]) * degree;
                             for (int t = tid & 31; t < degree; t += 32) {
                                 const int32_t f = __ldg(nb2 + t);
@@ -326,6 +340,17 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
                             }
                         }
                     }
+                } else if (KIND == KIND_PQ && fused) {
+                    // FusedPQDecoder.similarityToNeighbor (FusedPQDecoder.java:107-114): the code row sits inside the record just read
+                    const uint8_t *codes0 = rec + 4 * degree;
+                    for (int i = group; i < n; i += NG) {
+                        const int32_t f = cand_ids[i];
+                        const float sc = score_pq_codes<METRIC>(P.approx, blobA, codes0 + (size_t)cand_slot[i] * P.g.fused_code_stride, lane);
+                        if (lane == 0) {
+                            cand_keys[i] = topk_key(sc, f);
+                            if (P.filtered) cand_acc[i] = ((!acc || ((acc[f >> 5] >> (f & 31)) & 1u)) && sc >= P.threshold) ? F_ACCEPTED : 0;
+                        }
+                    }
                 } else {
                     for (int i = group; i < n; i += NG) {
                         const int32_t f = cand_ids[i];
@@ -374,7 +399,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
                             mypos = min(mypos, c);
                             // a new candidate that lands at the very front is the likeliest next expansion: start pulling
                             // its adjacency row towards L2 now (128 B; reads only)
-                            if (c < 2 && lvl == 0) prefetch_l2(P.g.adj0 + (size_t)key_node(k) * degree);
+                            if (c < 2 && lvl == 0) {
+                                if (KIND == KIND_PQ && P.g.fused) prefetch_l2(P.g.fused + (size_t)key_node(k) * P.g.fused_rec);
+                                else prefetch_l2(P.g.adj0 + (size_t)key_node(k) * degree);
+                            }
                         } else mydrop = max(mydrop, float_to_sortable(key_score(k)));
                     }
                 }
@@ -563,7 +591,7 @@ static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, 
     b += (size_t)list_alloc * 8 * 2;                  // the two list buffers
     b += (size_t)MAX_DEGREE * 8;                      // candidate keys of one hop
     b += (size_t)((rerankK + 2) & ~1) * 8;            // result heap (1-based)
-    b += (size_t)MAX_DEGREE * 4 + (size_t)MAX_DEGREE; // candidate ids + accept flags
+    b += (size_t)MAX_DEGREE * 4 + (size_t)MAX_DEGREE * 2; // candidate ids + accept flags + record slots
     b += (size_t)list_alloc * 2;                      // entry flags of the two buffers
     return (b + 15) & ~(size_t)15;
 }
@@ -671,6 +699,11 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
     P.filtered = (P.accept_bits != nullptr || P.threshold > 0.f) ? 1 : 0;
     P.query_stride = query_stride > 0 ? query_stride : approx.dim;
     P.g = g;
+    if (!(approx.kind == KIND_PQ && g.fused && g.fused_codes_of == approx.codes && g.fused_code_stride == approx.code_stride)) P.g.fused = nullptr;
+    {
+        const char *fe = getenv("JV_FUSED_PQ");
+        if (fe && fe[0] == '0') P.g.fused = nullptr;
+    }
     P.approx = approx;
     P.has_rerank = rerank ? 1 : 0;
     P.rerank = rerank ? *rerank : approx;

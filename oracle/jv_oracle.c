@@ -791,6 +791,9 @@ struct jvo_scorer {
     const float *mean;
     float *mean_sh; /* shuffled copy of mean sub-vectors (cosine, ref path) */
     float qbias, qnorm;
+    /* FusedPQ: packed[node] = the codes of node's level-0 neighbours, in neighbour order (jvo_fused_pq_pack) */
+    const uint8_t *packed;
+    int packed_degree;
     /* warp order (jvo_scorer_set_order) */
     int order;
     const float *codebooks, *centroid;
@@ -900,6 +903,39 @@ jvo_scorer *jvo_scorer_nvq(int metric, const float *mean, int dim, int nsub, con
         }
     }
     return s;
+}
+
+/* FusedPQ.writeInline (base:graph/disk/feature/FusedPQ.java:122-141): for every node, the PQ codes of its level-0 neighbours in
+ * neighbour order, zero codes up to maxDegree. packed_out [n][degree][M]. */
+void jvo_fused_pq_pack(const int32_t *adj0, int32_t n, int degree, const uint8_t *codes, int M, uint8_t *packed_out)
+{
+    for (int32_t v = 0; v < n; v++)
+        for (int i = 0; i < degree; i++) {
+            int32_t f = adj0[(size_t)v * degree + i];
+            uint8_t *dst = packed_out + ((size_t)v * degree + i) * M;
+            if (f >= 0) memcpy(dst, codes + (size_t)f * M, (size_t)M);
+            else memset(dst, 0, (size_t)M);
+        }
+}
+
+/* FusedPQ.approximateScoreFunctionFor (FusedPQ.java:119-123): a PQ scorer that also knows the packed neighbour codes */
+void jvo_scorer_set_packed_neighbors(jvo_scorer *s, const uint8_t *packed, int degree)
+{
+    s->packed = packed;
+    s->packed_degree = degree;
+}
+
+/* FusedPQDecoder.similarityToNeighbor (base:quantization/FusedPQDecoder.java:107-114, cosine :187-195): the neighbourIndex-th
+ * code row of origin's packed block through the same assembleAndSum / pqDecodedCosineSimilarity as similarityTo */
+float jvo_scorer_score_neighbor(jvo_scorer *s, int32_t origin, int neighborIndex)
+{
+    const uint8_t *c = s->packed + ((size_t)origin * s->packed_degree + neighborIndex) * s->M;
+    if (s->order) return warp_pq_score(s->metric, s->wlut, s->wmag, s->wbMag, s->k, c, s->M);
+    if (REF.h) {
+        if (s->metric == JVO_COSINE) return (1.f + REF.pqcos(c, 0, (size_t)s->M, s->k, s->lut, s->mag, s->bMag)) / 2.f;
+        return jvo_score_from_raw(s->metric, REF.adc(s->lut, s->k, c, 0, (size_t)s->M));
+    }
+    return jvo_pq_score_lut(s->metric, s->lut, s->mag, s->bMag, s->k, c, s->M);
 }
 
 float jvo_scorer_score(jvo_scorer *s, int32_t node)
@@ -1125,7 +1161,9 @@ static void search_one_layer(const jvo_graph *g, searcher *S, jvo_scorer *sf, in
             int32_t f = nb[i];
             if (f < 0) break;
             if (!is_add(&S->visited, f)) continue;
-            float sc = jvo_scorer_score(sf, f);
+            /* OnDiskGraphIndex.processNeighbors (base:graph/disk/OnDiskGraphIndex.java:639-661): a scorer that supports
+             * similarityToNeighbor scores level-0 neighbours from the expanded node's packed block */
+            float sc = (level == 0 && sf->kind == 1 && sf->packed) ? jvo_scorer_score_neighbor(sf, node, i) : jvo_scorer_score(sf, f);
             kh_push(&S->candidates, jvo_topk_key(sc, f));
             S->st.visited++;
         }

@@ -127,6 +127,12 @@ typedef struct {
 void jvo_scorer_set_order(jvo_scorer *s, int order);
 float jvo_compare_f32_warp(int metric, const float *q, const float *row, int dim);
 
+/* FusedPQ feature: packed neighbour codes (FusedPQ.java:122-141) and the decoder's similarityToNeighbor (FusedPQDecoder.java:84-114);
+ * a PQ scorer with packed neighbours makes jvo_graph_search take OnDiskGraphIndex.processNeighbors' edge-loading branch on level 0 */
+void jvo_fused_pq_pack(const int32_t *adj0, int32_t n, int degree, const uint8_t *codes, int M, uint8_t *packed_out);
+void jvo_scorer_set_packed_neighbors(jvo_scorer *s, const uint8_t *packed, int degree);
+float jvo_scorer_score_neighbor(jvo_scorer *s, int32_t origin, int neighborIndex);
+
 /* one query; approx scorer walks the graph, optional reranker re-scores the rerankK survivors.
  * Writes up to topK (node, score) pairs ordered best first; returns the count. */
 int jvo_graph_search(const jvo_graph *g, jvo_scorer *approx, jvo_scorer *reranker, int topK, int rerankK,

@@ -128,6 +128,9 @@ def load():
     sig("jvo_scorer_nvq", P, I, f32p, I, I, f32p, u8p, C.c_int64, f32p)
     sig("jvo_scorer_score", F, P, C.c_int32)
     sig("jvo_scorer_set_order", None, P, I)
+    sig("jvo_fused_pq_pack", None, i32p, C.c_int32, I, u8p, I, u8p)
+    sig("jvo_scorer_set_packed_neighbors", None, P, u8p, I)
+    sig("jvo_scorer_score_neighbor", F, P, C.c_int32, I)
     sig("jvo_compare_f32_warp", F, I, f32p, f32p, I)
     sig("jvo_scorer_free", None, P)
     sig("jvo_graph_search", I, C.POINTER(Graph), P, P, I, I, i32p, f32p, C.POINTER(Stats))

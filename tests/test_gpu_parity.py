@@ -574,6 +574,45 @@ def test_graph_search_pq_rerank_and_nvq_bq(jv, oracle):
         v.close()
 
 
+def test_fused_pq_layout_and_walk(jv, oracle):
+    # FusedPQ feature (FusedPQ.java:122-141, FusedPQDecoder.java:84-114, OnDiskGraphIndex.java:639-651): records packed on the device
+    # must equal the reference's writeInline layout byte for byte, and the walk that reads them must equal the oracle's
+    # edge-loading traversal — and therefore the plain PQ walk — id for id, score bit for score bit
+    rng = np.random.default_rng(73)
+    n, dim, k = 2500, 64, 256
+    data, adj, entry, upper_levels, entry_top = _hier_world(oracle, rng, n, dim, 16)
+    queries = o.random_unit_vectors(rng, 32, dim)
+    for M in (16, 10):  # M = 10: code rows padded to 12 bytes inside the record
+        cb, sizes, offsets = o.train_pq_numpy(rng, data[:1500], M, k, iters=2)
+        codes = o.encode_pq(oracle, cb, sizes, offsets, M, k, None, data)
+        packed = np.empty((n, 16, M), np.uint8)
+        oracle.jvo_fused_pq_pack(ip(adj), n, 16, bp(codes), M, bp(packed))
+        pqv, f32v = jv.PQVectors(codes, cb, dim, k), jv.F32Vectors(data)
+        for upper in (None, upper_levels):
+            e = entry if upper is None else entry_top
+            g = o.make_graph(adj, e, upper)
+            gi = jv.GraphIndex(adj, e, upper).fuse_pq(pqv)
+            rec = gi.fused_records()
+            cs = (M + 3) & ~3
+            assert np.array_equal(rec[:, :64].copy().view(np.int32), adj)
+            got_codes = rec[:, 64:64 + 16 * cs].reshape(n, 16, cs)
+            assert np.array_equal(got_codes[:, :, :M], packed) and not got_codes[:, :, M:].any()
+            for metric in METRICS:
+                def mk(q):
+                    sf = oracle.jvo_scorer_pq(metric, fp(cb), M, k, dim, None, bp(codes), n, fp(q))
+                    oracle.jvo_scorer_set_packed_neighbors(sf, bp(packed), 16)
+                    return sf
+                res = jv.GraphSearcher(gi).search(pqv, queries, metric, 10, 40, reranker=f32v)
+                want = _oracle_search(oracle, g, mk, queries, 10, 40, lambda q: oracle.jvo_scorer_f32(metric, fp(data), n, dim, fp(q)))
+                _assert_same_search(res, want, ("fused pq", M, metric, upper is not None))
+                plain = _oracle_search(oracle, g, lambda q: oracle.jvo_scorer_pq(metric, fp(cb), M, k, dim, None, bp(codes), n, fp(q)), queries, 10, 40,
+                                       lambda q: oracle.jvo_scorer_f32(metric, fp(data), n, dim, fp(q)))
+                assert np.array_equal(want[0], plain[0])  # the fused layout changes where codes are read from, never a score
+            gi.close()
+        pqv.close()
+        f32v.close()
+
+
 def test_graph_search_accept_threshold_rerank_floor(jv, oracle):
     # GraphSearcher.search(sp, topK, rerankK, threshold, rerankFloor, acceptOrds): GraphSearcher.java:166-181,427-431, NodeQueue.java:168-230
     rng = np.random.default_rng(61)
