@@ -133,6 +133,19 @@ JV_API int jv_query_end(jv_query q);
 /* PQ only: copy the query's partial-sums table (PQDecoder.java:41-54) back, lut_out[M*k] */
 JV_API int jv_query_get_lut(jv_query q, float *lut_out);
 
+/* ---- query batches: the host-driven seam with persistent state ----
+ * A batch of searches that the HOST drives hop by hop (GraphSearcher on the JVM, base:graph/GraphSearcher.java:406-457): the
+ * prepared queries (LUTs / bit packs / shifted copies) are built once and stay in HBM until jv_query_batch_end; a step uploads
+ * only ids + offsets through pinned staging owned by the batch and brings the scores back. */
+typedef struct jv_query_batch_s *jv_query_batch;
+JV_API int jv_query_batch_begin(jv_dataset ds, int metric, const float *queries, int nq, jv_query_batch *out);
+/* one step of all nq searches: query i scores ids[offsets[i] .. offsets[i+1]) -> scores_out in the same order; ONE launch.
+ * device_ms (optional): CUDA-event time of the scoring kernel alone */
+JV_API int jv_query_batch_score(jv_query_batch b, const int32_t *ids, const int32_t *offsets, float *scores_out, double *device_ms);
+/* one hop of search `query_index`: ids[n] -> scores_out[n]; the kernel reads / writes mapped pinned memory (no separate copies) */
+JV_API int jv_query_batch_score_one(jv_query_batch b, int query_index, const int32_t *ids, int n, float *scores_out);
+JV_API int jv_query_batch_end(jv_query_batch b);
+
 /* one step of many searches: query qi scores ids[offsets[qi] .. offsets[qi+1]) ; one launch for the whole step */
 JV_API int jv_score_multi(jv_dataset ds, int metric, const float *queries, int nq, const int32_t *ids,
                           const int32_t *offsets, float *scores_out);
@@ -182,6 +195,9 @@ JV_API int jv_nvq_encode_batch(const float *rows, int64_t n, int dim, int nsub, 
 JV_API int jv_bq_encode_dataset(jv_dataset f32, uint64_t *words_out);
 JV_API int jv_pq_encode_dataset(jv_dataset f32, int M, int k, const float *codebooks, const float *centroid, uint8_t *codes_out);
 JV_API int jv_nvq_encode_dataset(jv_dataset f32, int nsub, const float *mean, int learn, float *params_out, uint8_t *bytes_out);
+
+/* NVQ inline vectors without a host round trip: encode the resident fp32 rows into a NEW resident NVQ data set */
+JV_API int jv_nvq_encode_dataset_resident(jv_dataset f32, int nsub, const float *mean, int learn, jv_dataset *out);
 
 /* ---- graph: ImmutableGraphIndex adjacency in HBM + GraphSearcher traversal on the device ---- */
 /* adj0: [n][degree] int32, -1 padded (level 0). */

@@ -65,6 +65,8 @@ SYMBOLS = [
     ("jv_dataset_free", _I, [_P]), ("jv_dataset_size", _L, [_P]), ("jv_dataset_dim", _I, [_P]), ("jv_dataset_device_bytes", _L, [_P]),
     ("jv_query_begin", _I, [_P, f32p, _I, C.POINTER(_P)]), ("jv_score_batch", _I, [_P, i32p, _I, f32p]), ("jv_query_end", _I, [_P]),
     ("jv_query_get_lut", _I, [_P, f32p]),
+    ("jv_query_batch_begin", _I, [_P, _I, f32p, _I, C.POINTER(_P)]), ("jv_query_batch_score", _I, [_P, i32p, i32p, f32p, C.POINTER(C.c_double)]),
+    ("jv_query_batch_score_one", _I, [_P, _I, i32p, _I, f32p]), ("jv_query_batch_end", _I, [_P]),
     ("jv_score_multi", _I, [_P, _I, f32p, _I, i32p, i32p, f32p]), ("jv_score_pairs", _I, [_P, _I, i32p, i32p, _I, f32p]),
     ("jv_topk_bruteforce", _I, [_P, _I, f32p, _I, _I, i64p]),
     ("jv_topk_bruteforce_device", _I, [_P, _I, _P, _I, _I, _L, _P]), ("jv_topk_merge_device", _I, [_P, _I, _I, _I, _P]),
@@ -78,6 +80,7 @@ SYMBOLS = [
     ("jv_nvq_encode_batch", _I, [f32p, _L, _I, _I, f32p, _I, f32p, u8p]),
     ("jv_bq_encode_dataset", _I, [_P, u64p]), ("jv_pq_encode_dataset", _I, [_P, _I, _I, f32p, f32p, u8p]),
     ("jv_nvq_encode_dataset", _I, [_P, _I, f32p, _I, f32p, u8p]),
+    ("jv_nvq_encode_dataset_resident", _I, [_P, _I, f32p, _I, C.POINTER(_P)]),
     ("jv_graph_create", _I, [C.c_int32, _I, i32p, C.c_int32, C.POINTER(_P)]), ("jv_graph_add_level", _I, [_P, C.c_int32, i32p, i32p]),
     ("jv_graph_fuse_pq", _I, [_P, _P]), ("jv_graph_fused_download", _I, [_P, u8p, C.POINTER(_I)]),
     ("jv_graph_free", _I, [_P]), ("jv_graph_info", _I, [_P, i32p, C.POINTER(_I), C.POINTER(_I), i32p]),

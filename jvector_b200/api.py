@@ -147,6 +147,47 @@ class ScoreFunction:
             pass
 
 
+class QueryBatch:
+    """A batch of searches driven hop by hop from the host: prepared queries persist in HBM (jv_query_batch_*)."""
+
+    def __init__(self, vectors, queries, vsf):
+        lib = nat.init()
+        queries = c32(queries)
+        self._vectors = vectors
+        self.nq = queries.shape[0]
+        self._h = C.c_void_p()
+        check(lib.jv_query_batch_begin(vectors._h, int(vsf), fp(queries), self.nq, C.byref(self._h)))
+
+    def score_step(self, ids, offsets, return_ms=False):
+        """one step of all searches: query i scores ids[offsets[i]:offsets[i+1]] (one launch)"""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        out = np.empty(len(ids), dtype=np.float32)
+        ms = C.c_double()
+        check(nat.load().jv_query_batch_score(self._h, ip(ids), ip(offsets), fp(out), C.byref(ms)))
+        return (out, ms.value) if return_ms else out
+
+    def score_one(self, qi, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        out = np.empty(len(ids), dtype=np.float32)
+        check(nat.load().jv_query_batch_score_one(self._h, int(qi), ip(ids), len(ids), fp(out)))
+        return out
+
+    def single(self, qi):
+        return (self, qi)
+
+    def close(self):
+        if self._h:
+            nat.load().jv_query_batch_end(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def score_multi(vectors, vsf, queries, ids, offsets):
     """One step of many searches: query i scores ids[offsets[i]:offsets[i+1]] (one launch for the whole step)."""
     lib = nat.init()
@@ -215,6 +256,15 @@ def nvq_encode_all(rows, mean, nsub, learn=True):
     out = np.empty(rows.shape, dtype=np.uint8)
     check(lib.jv_nvq_encode_batch(fp(rows), rows.shape[0], rows.shape[1], nsub, fp(mean), 1 if learn else 0, fp(params), bp(out)))
     return params, out
+
+
+def nvq_encode_resident(f32_vectors, mean, nsub, learn=True):
+    """NVQuantization.encodeAll of rows already in HBM into a new resident NVQVectors (no host round trip)."""
+    lib = nat.init()
+    mean = c32(mean)
+    h = C.c_void_p()
+    check(lib.jv_nvq_encode_dataset_resident(f32_vectors._h, nsub, fp(mean), 1 if learn else 0, C.byref(h)))
+    return _Vectors(h, None)
 
 
 class GraphIndex:

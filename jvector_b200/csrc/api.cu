@@ -830,6 +830,45 @@ int jv_nvq_encode_dataset(jv_dataset f32, int nsub, const float *mean, int learn
     return nvq_encode_impl(nullptr, f32->d.rows, f32->d.stride, f32->d.n, f32->d.dim, nsub, mean, learn, params_out, bytes_out);
 }
 
+// NVQ "inline vectors" without a host round trip: encode the resident fp32 rows into a new resident NVQ data set
+int jv_nvq_encode_dataset_resident(jv_dataset f32, int nsub, const float *mean, int learn, jv_dataset *out)
+{
+    ON_DEVICE_OF(f32);
+    if (f32->d.kind != KIND_F32 || !mean || !out || nsub <= 0 || nsub > f32->d.dim) return fail(JV_ERR_INVALID, "nvq_encode_dataset_resident: bad arguments");
+    int rc;
+    if ((rc = t_ctx.init())) return rc;
+    const int dim = f32->d.dim;
+    const int64_t n = f32->d.n;
+    jv_dataset ds = new jv_dataset_s();
+    ds->device = f32->device;
+    memset(&ds->d, 0, sizeof(DataDesc));
+    DataDesc &d = ds->d;
+    d.kind = KIND_NVQ; d.dim = dim; d.n = n; d.nsub = nsub; d.stride = round4(dim); d.byte_stride = round4(dim);
+    std::vector<int> sizes, offsets;
+    pq_layout(dim, nsub, sizes, offsets);
+    uint8_t *db = nullptr;
+    float *dp = nullptr, *dm = nullptr;
+    int *dsz = nullptr, *doff = nullptr;
+    if ((rc = ds->alloc((void **)&db, (size_t)n * d.byte_stride)) || (rc = ds->alloc((void **)&dp, (size_t)n * nsub * 16)) ||
+        (rc = ds->alloc((void **)&dm, (size_t)d.stride * 4)) || (rc = ds->alloc((void **)&dsz, (size_t)nsub * 4)) ||
+        (rc = ds->alloc((void **)&doff, (size_t)nsub * 4))) {
+        delete ds;
+        return rc;
+    }
+    cudaStream_t s = t_ctx.stream;
+    cudaError_t e = cudaMemsetAsync(dm, 0, (size_t)d.stride * 4, s);
+    if (e == cudaSuccess && d.byte_stride != dim) e = cudaMemsetAsync(db, 0, (size_t)n * d.byte_stride, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dm, mean, (size_t)dim * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dsz, sizes.data(), (size_t)nsub * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(doff, offsets.data(), (size_t)nsub * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = launch_nvq_encode(f32->d.rows, n, f32->d.stride, nsub, dsz, doff, dm, learn, dp, db, d.byte_stride, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { delete ds; return cuda_fail(e, "nvq_encode_dataset_resident"); }
+    d.bytes = db; d.params = dp; d.mean = dm; d.sub_sizes = dsz; d.sub_offsets = doff;
+    *out = ds;
+    return JV_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ graph
 int jv_graph_create(int32_t n, int degree, const int32_t *adj0, int32_t entry_node, jv_graph *out)
 {
@@ -1225,6 +1264,150 @@ int jv_graph_build_stats(int64_t *scored_vectors, int64_t *batches, int64_t *dro
     if (scored_vectors) *scored_vectors = t_build_stats.searched;
     if (batches) *batches = t_build_stats.batches;
     if (dropped_backlinks) *dropped_backlinks = t_build_stats.dropped_backlinks;
+    return JV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ query batches (host-driven seam)
+// north_star's literal form of the path: the host expands the frontier and sends each hop's candidate set as one launch. What
+// makes that seam fast is what persists between calls: the prepared queries (LUTs / bit packs / shifted copies) stay in HBM for
+// the life of the batch, and ids / offsets / scores travel through pinned, device-mapped staging that belongs to the batch.
+struct jv_query_batch_s {
+    int device = 0;
+    jv_dataset ds = nullptr;
+    int metric = 0, nq = 0;
+    float *blobs = nullptr;        // [nq][blob_floats]
+    size_t blob_floats = 0;
+    // pinned + mapped staging (grown on demand)
+    int32_t *h_ids = nullptr, *h_off = nullptr;
+    float *h_scores = nullptr;
+    size_t cap_ids = 0, cap_off = 0;
+    int32_t *d_ids = nullptr, *d_off = nullptr;
+    float *d_scores = nullptr;
+    size_t dcap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static void query_batch_release(jv_query_batch_s *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    cudaFree(b->blobs); cudaFree(b->d_ids); cudaFree(b->d_off); cudaFree(b->d_scores);
+    cudaFreeHost(b->h_ids); cudaFreeHost(b->h_off); cudaFreeHost(b->h_scores);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+int jv_query_batch_begin(jv_dataset ds, int metric, const float *queries, int nq, jv_query_batch *out)
+{
+    ON_DEVICE_OF(ds);
+    if (!queries || !out || nq <= 0 || nq > 65535) return fail(JV_ERR_INVALID, "query_batch_begin: 1 <= nq <= 65535");
+    int rc = check_metric(ds->d, metric);
+    if (rc) return rc;
+    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(0, (size_t)nq * ds->d.dim * 4))) return rc;
+    jv_query_batch_s *b = new jv_query_batch_s();
+    b->device = ds->device; b->ds = ds; b->metric = metric; b->nq = nq; b->blob_floats = (size_t)blob_floats(ds->d);
+    cudaError_t e = cudaMalloc((void **)&b->blobs, (size_t)nq * b->blob_floats * 4);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t_ctx.dbuf[0], queries, (size_t)nq * ds->d.dim * 4, cudaMemcpyHostToDevice, t_ctx.stream);
+    if (e == cudaSuccess) e = launch_prepare(ds->d, metric, (const float *)t_ctx.dbuf[0], nq, b->blobs, t_ctx.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(t_ctx.stream);
+    if (e != cudaSuccess) { query_batch_release(b); return cuda_fail(e, "query_batch_begin"); }
+    *out = b;
+    return JV_OK;
+}
+
+static int query_batch_staging(jv_query_batch_s *b, size_t total, size_t noff)
+{
+    if (total > b->cap_ids) {
+        cudaFreeHost(b->h_ids); cudaFreeHost(b->h_scores);
+        b->h_ids = nullptr; b->h_scores = nullptr; b->cap_ids = 0;
+        const size_t want = total + total / 2 + 256;
+        CK(cudaHostAlloc((void **)&b->h_ids, want * 4, cudaHostAllocMapped), "cudaHostAlloc(ids)");
+        CK(cudaHostAlloc((void **)&b->h_scores, want * 4, cudaHostAllocMapped), "cudaHostAlloc(scores)");
+        b->cap_ids = want;
+    }
+    if (noff > b->cap_off) {
+        cudaFreeHost(b->h_off);
+        b->h_off = nullptr; b->cap_off = 0;
+        CK(cudaHostAlloc((void **)&b->h_off, (noff + 64) * 4, cudaHostAllocMapped), "cudaHostAlloc(offsets)");
+        b->cap_off = noff + 64;
+    }
+    if (total > b->dcap) {
+        cudaFree(b->d_ids); cudaFree(b->d_scores); cudaFree(b->d_off);
+        b->d_ids = nullptr; b->d_scores = nullptr; b->d_off = nullptr; b->dcap = 0;
+        const size_t want = total + total / 2 + 256;
+        CK(cudaMalloc((void **)&b->d_ids, want * 4), "cudaMalloc(ids)");
+        CK(cudaMalloc((void **)&b->d_scores, want * 4), "cudaMalloc(scores)");
+        CK(cudaMalloc((void **)&b->d_off, ((size_t)b->nq + 64) * 4), "cudaMalloc(offsets)");
+        b->dcap = want;
+    }
+    return JV_OK;
+}
+
+// one step of all the batch's searches: query i scores ids[offsets[i] .. offsets[i+1]); only ids + offsets go up, scores come down
+int jv_query_batch_score(jv_query_batch b, const int32_t *ids, const int32_t *offsets, float *scores_out, double *device_ms)
+{
+    ON_DEVICE_OF(b);
+    if (!ids || !offsets || !scores_out) return fail(JV_ERR_INVALID, "query_batch_score: null argument");
+    const int nq = b->nq;
+    const int total = offsets[nq];
+    int maxc = 0;
+    for (int i = 0; i < nq; i++) {
+        if (offsets[i + 1] < offsets[i]) return fail(JV_ERR_INVALID, "query_batch_score: offsets not monotone");
+        maxc = std::max(maxc, offsets[i + 1] - offsets[i]);
+    }
+    if (device_ms) *device_ms = 0.0;
+    if (total <= 0) return JV_OK;
+    int rc = query_batch_staging(b, (size_t)total, (size_t)nq + 1);
+    if (rc) return rc;
+    memcpy(b->h_ids, ids, (size_t)total * 4);
+    memcpy(b->h_off, offsets, ((size_t)nq + 1) * 4);
+    cudaStream_t s = b->stream;
+    CK(cudaMemcpyAsync(b->d_ids, b->h_ids, (size_t)total * 4, cudaMemcpyHostToDevice, s), "H2D ids");
+    CK(cudaMemcpyAsync(b->d_off, b->h_off, ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, s), "H2D offsets");
+    CK(cudaEventRecord(b->ev0, s), "event");
+    CK(launch_score_ragged(b->ds->d, b->metric, b->blobs, nq, b->d_ids, b->d_off, 0, maxc, b->d_scores, s), "score_ragged");
+    CK(cudaEventRecord(b->ev1, s), "event");
+    CK(cudaMemcpyAsync(b->h_scores, b->d_scores, (size_t)total * 4, cudaMemcpyDeviceToHost, s), "D2H scores");
+    CK(cudaStreamSynchronize(s), "sync");
+    memcpy(scores_out, b->h_scores, (size_t)total * 4);
+    if (device_ms) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+        *device_ms = ms;
+    }
+    return JV_OK;
+}
+
+// one hop of ONE search of the batch: the kernel reads the ids from, and writes the scores to, mapped pinned memory — one launch
+// and one stream synchronisation, no separate copies
+int jv_query_batch_score_one(jv_query_batch b, int query_index, const int32_t *ids, int n, float *scores_out)
+{
+    ON_DEVICE_OF(b);
+    if (query_index < 0 || query_index >= b->nq || n < 0 || (n > 0 && (!ids || !scores_out))) return fail(JV_ERR_INVALID, "query_batch_score_one: bad arguments");
+    if (n == 0) return JV_OK;
+    int rc = query_batch_staging(b, (size_t)n, 2);
+    if (rc) return rc;
+    memcpy(b->h_ids, ids, (size_t)n * 4);
+    int32_t *dids = nullptr;
+    float *dsc = nullptr;
+    CK(cudaHostGetDevicePointer((void **)&dids, b->h_ids, 0), "cudaHostGetDevicePointer");
+    CK(cudaHostGetDevicePointer((void **)&dsc, b->h_scores, 0), "cudaHostGetDevicePointer");
+    CK(launch_score_ragged(b->ds->d, b->metric, b->blobs + (size_t)query_index * b->blob_floats, 1, dids, nullptr, n, n, dsc, b->stream), "score_ragged");
+    CK(cudaStreamSynchronize(b->stream), "sync");
+    memcpy(scores_out, b->h_scores, (size_t)n * 4);
+    return JV_OK;
+}
+
+int jv_query_batch_end(jv_query_batch b)
+{
+    query_batch_release(b);
     return JV_OK;
 }
 

@@ -1244,6 +1244,43 @@ int jvo_graph_search(const jvo_graph *g, jvo_scorer *approx, jvo_scorer *reranke
     return jvo_graph_search_ex(g, approx, reranker, topK, rerankK, 0.0f, 0.0f, NULL, nodes_out, scores_out, stats);
 }
 
+/* ---- host memory for the CPU baseline: pages interleaved over the NUMA nodes (what `numactl --interleave=all` does), so that
+ *      128 threads gathering random rows do not all hit the one node a single-threaded first touch would have filled ---- */
+#include <dirent.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
+int jvo_numa_nodes(void)
+{
+    int n = 0;
+    DIR *d = opendir("/sys/devices/system/node");
+    if (!d) return 1;
+    struct dirent *e;
+    while ((e = readdir(d)) != NULL)
+        if (strncmp(e->d_name, "node", 4) == 0 && e->d_name[4] >= '0' && e->d_name[4] <= '9') n++;
+    closedir(d);
+    return n > 0 ? n : 1;
+}
+
+void *jvo_alloc_interleaved(size_t bytes)
+{
+    void *p = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return NULL;
+#ifdef SYS_mbind
+    {
+        unsigned long mask[16];
+        int nodes = jvo_numa_nodes();
+        memset(mask, 0, sizeof(mask));
+        for (int i = 0; i < nodes && i < 1024; i++) mask[i / (8 * sizeof(unsigned long))] |= 1ul << (i % (8 * sizeof(unsigned long)));
+        if (nodes > 1) syscall(SYS_mbind, p, bytes, 3 /* MPOL_INTERLEAVE */, mask, (unsigned long)(nodes + 1), 0u); /* best effort */
+    }
+#endif
+    return p;
+}
+
+void jvo_free_interleaved(void *p, size_t bytes) { if (p) munmap(p, bytes); }
+
 /* ---- multi-threaded batch driver (queries block-partitioned, one searcher per thread:
  *      jvector-examples/.../benchmarks/ThroughputBenchmark.java:213, datasets/SiftSmall.java:367-377) ---- */
 typedef struct {

@@ -156,6 +156,11 @@ double jvo_graph_search_batch(const jvo_graph *g, const jvo_dataset *ds, const f
                               int topK, int rerankK, int threads, int32_t *nodes_out, float *scores_out,
                               int64_t *scored_total);
 
+/* host buffers with pages interleaved over the NUMA nodes (CPU baseline only) */
+int jvo_numa_nodes(void);
+void *jvo_alloc_interleaved(size_t bytes);
+void jvo_free_interleaved(void *p, size_t bytes);
+
 /* multi-threaded NVQ encode (reference kernels when jvo_use_ref was called); returns seconds */
 double jvo_nvq_encode_batch(const float *rows, int64_t n, int dim, int nsub, const float *mean, int learn, int threads, float *params_out, uint8_t *bytes_out);
 

@@ -136,6 +136,9 @@ def load():
     sig("jvo_graph_search", I, C.POINTER(Graph), P, P, I, I, i32p, f32p, C.POINTER(Stats))
     sig("jvo_graph_search_ex", I, C.POINTER(Graph), P, P, I, I, F, F, C.POINTER(C.c_uint32), i32p, f32p, C.POINTER(Stats))
     sig("jvo_graph_search_batch", C.c_double, C.POINTER(Graph), C.POINTER(Dataset), f32p, I, I, I, I, i32p, f32p, i64p)
+    sig("jvo_numa_nodes", I)
+    sig("jvo_alloc_interleaved", C.c_void_p, C.c_size_t)
+    sig("jvo_free_interleaved", None, C.c_void_p, C.c_size_t)
     sig("jvo_nvq_encode_batch", C.c_double, f32p, C.c_int64, I, I, f32p, I, I, f32p, u8p)
     sig("jvo_bq_bruteforce_batch", C.c_double, u64p, C.c_int64, I, u64p, I, I, I, i64p)
     sig("jvo_graph_build_f32", C.c_int32, I, f32p, C.c_int32, I, I, I, F, F, i32p)
@@ -191,6 +194,18 @@ def load_ref():
     L.jvector_simd_get_active_isa.restype = C.c_char_p
     L.jvector_simd_get_max_isa_env.restype = C.c_char_p
     return L
+
+
+def interleaved_array(shape, dtype=np.float32):
+    """numpy array over a buffer whose pages are interleaved across the NUMA nodes (CPU-baseline inputs)"""
+    L = load()
+    count = int(np.prod(shape))
+    nbytes = count * np.dtype(dtype).itemsize
+    p = L.jvo_alloc_interleaved(nbytes)
+    if not p:
+        return np.empty(shape, dtype)
+    buf = (C.c_char * nbytes).from_address(p)
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)  # lives for the process (bench inputs)
 
 
 # ---------------------------------------------------------------------------------------------
