@@ -61,25 +61,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def gen_unit_rows_device(torch, seed, n, dim, dist="latent", chunk=262144):
+def gen_unit_rows_device(torch, seed, n, dim, dist="latent", chunk=262144, device="cuda"):
     """Synthetic float32 unit rows generated ON THE DEVICE (torch is plumbing here: RNG + one small matmul per chunk).
     dist="latent": x = normalise(z A + NOISE * e), z ~ N(0, I_32), A a fixed 32 x dim Gaussian map, e ~ N(0, I_dim): embedding-like
         data with neighbourhood structure, so recall@10 is a meaningful axis.
     dist="iid": i.i.d. N(0,1) rows normalised (SURVEY §8d's first suggestion; graph search on 1M x 768 i.i.d. rows reaches recall@10
         ~ 0.05 for the reference traversal and this one alike — distance concentration — so it is an option, not the headline)."""
-    g = torch.Generator(device="cuda")
+    g = torch.Generator(device=device)
     g.manual_seed(seed)
-    out = torch.empty((n, dim), dtype=torch.float32, device="cuda")
+    out = torch.empty((n, dim), dtype=torch.float32, device=device)
     A = None
     if dist == "latent":
-        ga = torch.Generator(device="cuda")
+        ga = torch.Generator(device=device)
         ga.manual_seed(SEED + 7)
-        A = torch.randn((LATENT, dim), generator=ga, device="cuda", dtype=torch.float32) / (LATENT ** 0.5)
+        A = torch.randn((LATENT, dim), generator=ga, device=device, dtype=torch.float32) / (LATENT ** 0.5)
     for i in range(0, n, chunk):
         j = min(n, i + chunk)
-        blk = torch.randn((j - i, dim), generator=g, device="cuda", dtype=torch.float32)
+        blk = torch.randn((j - i, dim), generator=g, device=device, dtype=torch.float32)
         if A is not None:
-            z = torch.randn((j - i, LATENT), generator=g, device="cuda", dtype=torch.float32)
+            z = torch.randn((j - i, LATENT), generator=g, device=device, dtype=torch.float32)
             blk = blk * NOISE + z @ A
         blk /= blk.norm(dim=1, keepdim=True)
         out[i:j] = blk

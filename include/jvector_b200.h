@@ -277,9 +277,31 @@ typedef struct {
     float alpha;       /* 1.2 */
     int add_hierarchy; /* HNSW-style upper levels (GraphIndexBuilder.java:562-575) */
     uint64_t seed;
-    int max_batch;     /* 0 = default */
+    int max_batch;     /* 0 = default (16384): nodes inserted per round; they play the reference's concurrently inserting threads */
+    int concurrent_window; /* in-progress peers each insert sees besides its beam (getConcurrentCandidates,
+                              GraphIndexBuilder.java:823-837): -1 = default (what fits the 128-candidate prune tile, <= 32), 0 = none */
 } jv_build_params;
 JV_API int jv_graph_build(jv_dataset f32, int metric, const jv_build_params *params, jv_graph *out, double *device_ms);
+/* The same build advanced batch by batch, for a build SHARDED over several GPUs (BASELINE config 5): every participant holds a
+ * replica of the rows and of the adjacency; per batch each one searches + prunes ITS slice (jv_builder_insert_slice), the caller
+ * all-gathers the slices (NCCL; jvector_b200/parallel.py sharded_build), every participant applies the whole batch — back-links in
+ * sorted order, so all replicas stay bit-identical — and the rows that passed overflow * M are re-pruned slice-wise and exchanged
+ * the same way. All *_device pointers are device buffers of the caller (the collective's send / receive buffers); work is
+ * enqueued on `cuda_stream`. Slices are positions [lo, hi) of the batch (insert) or of the sorted overflow list (re-prune). */
+typedef struct jv_builder_s *jv_builder;
+JV_API int jv_builder_create(jv_dataset f32, int metric, const jv_build_params *params, void *cuda_stream, jv_builder *out);
+JV_API int jv_builder_info(jv_builder b, int *degree, int *row_cap, int *max_batch);
+JV_API int jv_builder_next_batch(jv_builder b, int32_t *first, int32_t *count); /* count = 0: every node is inserted */
+JV_API int jv_builder_insert_slice(jv_builder b, int32_t first, int32_t count, int32_t lo, int32_t hi,
+                                   int32_t *rows_out_device /* [count][degree], rows lo..hi-1 written */, int32_t *deg_out_device /* [count] */);
+/* rows of the WHOLE batch; overflow_rows (optional, forces a stream sync): length of the sorted list of rows to re-prune */
+JV_API int jv_builder_apply_new(jv_builder b, int32_t first, int32_t count, const int32_t *rows_device, const int32_t *deg_device, int32_t *overflow_rows);
+JV_API int jv_builder_reprune_slice(jv_builder b, int32_t lo, int32_t hi, int32_t *rows_out_device /* [.][row_cap] */, int32_t *deg_out_device);
+JV_API int jv_builder_apply_repruned(jv_builder b, int32_t count, const int32_t *rows_device, const int32_t *deg_device);
+/* cleanup(): the sorted list of rows longer than M (enforceDegree), to be re-pruned with the two calls above */
+JV_API int jv_builder_collect_over_degree(jv_builder b, int32_t *rows);
+JV_API int jv_builder_finish(jv_builder b, jv_graph *out, double *device_ms);
+JV_API int jv_builder_free(jv_builder b);
 /* counters of this thread's last jv_graph_build (level 0): vectors scored by the insert searches, batches, back-links dropped */
 JV_API int jv_graph_build_stats(int64_t *scored_vectors, int64_t *batches, int64_t *dropped_backlinks);
 

@@ -159,7 +159,7 @@ private:
 class GraphIndexBuilder {
 public:
     GraphIndexBuilder(VectorSimilarityFunction vsf, int M, int beamWidth, float neighborOverflow, float alpha, bool addHierarchy, uint64_t seed = 0)
-        : vsf_(vsf), p_{M, beamWidth, neighborOverflow, alpha, addHierarchy ? 1 : 0, seed, 0} {}
+        : vsf_(vsf), p_{M, beamWidth, neighborOverflow, alpha, addHierarchy ? 1 : 0, seed, 0, -1} {}
     GraphIndex build(const F32Vectors &v)
     {
         jv_graph g = nullptr;

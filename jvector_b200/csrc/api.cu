@@ -1167,6 +1167,79 @@ int jv_graph_search_batch(jv_graph g, jv_dataset approx, jv_dataset reranker, in
     return jv_graph_search_batch_ex(g, approx, reranker, metric, queries, nq, topK, rerankK, nullptr, nodes_out, scores_out, stats);
 }
 
+static int build_params_check(const jv_build_params *params, BuildParams *bp)
+{
+    if (params->degree < 1 || params->degree > 64 || params->beam_width < 1 || params->beam_width > 256 || params->overflow < 1.0f || params->alpha < 1.0f)
+        return fail(JV_ERR_INVALID, "graph_build: need 1 <= degree <= 64, 1 <= beam <= 256, overflow >= 1, alpha >= 1");
+    bp->degree = params->degree; bp->beam = params->beam_width; bp->overflow = params->overflow; bp->alpha = params->alpha;
+    bp->max_batch = params->max_batch; bp->window = params->concurrent_window;
+    return JV_OK;
+}
+
+// HNSW-style levels (GraphIndexBuilder.java:562-575): level(node) = floor(-ln(U) / ln(M)); returns the members of every level >= 1
+// (ascending ids) and the entry node (the first node of the top level)
+static void assign_levels(int n, int degree, uint64_t seed, std::vector<std::vector<int32_t>> &members, int *entry)
+{
+    uint64_t st = seed ? seed : 0x9E3779B97F4A7C15ull;
+    auto next_u = [&st]() {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        return ((st >> 11) + 1) * (1.0 / 9007199254740993.0);
+    };
+    const double ml = degree == 1 ? 1.0 : 1.0 / log((double)degree);
+    std::vector<int> level(n);
+    int maxl = 0;
+    for (int i = 0; i < n; i++) {
+        level[i] = (int)(-log(next_u()) * ml);
+        maxl = std::max(maxl, level[i]);
+    }
+    *entry = 0;
+    for (int i = 0; i < n; i++)
+        if (level[i] == maxl) { *entry = i; break; }
+    members.assign(maxl, {});
+    for (int i = 0; i < n; i++)
+        for (int l = 1; l <= level[i]; l++) members[l - 1].push_back(i);
+}
+
+// every upper level is a Vamana graph over its members, built by the same device builder on the members' rows (one gather kernel)
+static int build_upper_levels(jv_graph g, jv_dataset f32, int metric, const BuildParams &bp, uint64_t seed, cudaStream_t s)
+{
+    const int n = (int)f32->d.n, degree = bp.degree;
+    std::vector<std::vector<int32_t>> members;
+    int entry = 0;
+    assign_levels(n, degree, seed, members, &entry);
+    g->g.entry_node = entry;
+    int rc;
+    for (size_t l = 0; l < members.size(); l++) {
+        const std::vector<int32_t> &ids = members[l];
+        const int cnt = (int)ids.size();
+        std::vector<int32_t> ladj((size_t)cnt * degree, -1);
+        if (cnt > 1) {
+            jv_dataset_s sub;
+            sub.device = f32->device;
+            memset(&sub.d, 0, sizeof(DataDesc));
+            sub.d.kind = KIND_F32; sub.d.dim = f32->d.dim; sub.d.stride = f32->d.stride; sub.d.n = cnt;
+            float *drows = nullptr;
+            int32_t *dadj = nullptr, *dids = nullptr;
+            if ((rc = sub.alloc((void **)&drows, (size_t)cnt * sub.d.stride * 4)) || (rc = sub.alloc((void **)&dadj, (size_t)cnt * degree * 4)) ||
+                (rc = sub.alloc((void **)&dids, (size_t)cnt * 4)))
+                return rc;
+            cudaError_t e = cudaMemcpyAsync(dids, ids.data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = launch_gather_rows(f32->d, dids, cnt, drows, s);
+            sub.d.rows = drows;
+            BuildStats bs2;
+            if (e == cudaSuccess) e = build_graph_flat(sub.d, metric, bp, dadj, g_sm_count, &bs2, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(ladj.data(), dadj, ladj.size() * 4, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) return cuda_fail(e, "build upper level");
+            for (auto &x : ladj)
+                if (x >= 0) x = ids[x];
+        }
+        g->level_ids.push_back(ids);
+        g->level_adj.push_back(ladj);
+    }
+    return graph_rebuild_upper(g);
+}
+
 int jv_graph_build(jv_dataset f32, int metric, const jv_build_params *params, jv_graph *out, double *device_ms)
 {
     ON_DEVICE_OF(f32);
@@ -1175,87 +1248,174 @@ int jv_graph_build(jv_dataset f32, int metric, const jv_build_params *params, jv
     if (rc) return rc;
     if ((rc = t_ctx.init())) return rc;
     cudaStream_t s = t_ctx.stream;
-    const int n = (int)f32->d.n, degree = params->degree;
-    if (degree < 1 || degree > 64 || params->beam_width < 1 || params->beam_width > 256 || params->overflow < 1.0f || params->alpha < 1.0f)
-        return fail(JV_ERR_INVALID, "graph_build: need 1 <= degree <= 64, 1 <= beam <= 256, overflow >= 1, alpha >= 1");
     BuildParams bp;
-    bp.degree = degree; bp.beam = params->beam_width; bp.overflow = params->overflow; bp.alpha = params->alpha; bp.max_batch = params->max_batch;
+    if ((rc = build_params_check(params, &bp))) return rc;
+    const int n = (int)f32->d.n, degree = params->degree;
     jv_graph g = new jv_graph_s();
     g->device = f32->device;
     memset(&g->g, 0, sizeof(GraphDesc));
     cudaError_t e = cudaMalloc((void **)&g->adj0, (size_t)n * degree * 4);
     if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaMalloc(adjacency)"); }
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0, s);
     BuildStats bs;
     e = build_graph_flat(f32->d, metric, bp, g->adj0, g_sm_count, &bs, s);
-    cudaEventRecord(e1, s);
+    t_build_stats = bs;
+    g->g.n = n; g->g.degree = degree; g->g.levels = 1; g->g.entry_node = 0; g->g.entry_level = 0; g->g.adj0 = g->adj0;
+    rc = e == cudaSuccess ? JV_OK : cuda_fail(e, "build_graph_flat");
+    if (!rc && params->add_hierarchy && n > 1) rc = build_upper_levels(g, f32, metric, bp, params->seed, s);
+    cudaEventRecord(e1, s);  // the upper levels are part of the build and of its time
     cudaStreamSynchronize(s);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    t_build_stats = bs;
-    if (e != cudaSuccess) { delete g; return cuda_fail(e, "build_graph_flat"); }
-    g->g.n = n; g->g.degree = degree; g->g.levels = 1; g->g.entry_node = 0; g->g.entry_level = 0; g->g.adj0 = g->adj0;
-    if (params->add_hierarchy && n > 1) {
-        // HNSW-style levels (GraphIndexBuilder.java:562-575): level(node) = floor(-ln(U) / ln(M)); every upper level is a
-        // Vamana graph over its members, built with the same device builder on the gathered rows.
-        uint64_t st = params->seed ? params->seed : 0x9E3779B97F4A7C15ull;
-        auto next_u = [&st]() {
-            st ^= st << 13; st ^= st >> 7; st ^= st << 17;
-            return ((st >> 11) + 1) * (1.0 / 9007199254740993.0);
-        };
-        const double ml = degree == 1 ? 1.0 : 1.0 / log((double)degree);
-        std::vector<int> level(n);
-        int maxl = 0;
-        for (int i = 0; i < n; i++) {
-            level[i] = (int)(-log(next_u()) * ml);
-            maxl = std::max(maxl, level[i]);
-        }
-        // the entry point is a node of the top level
-        int entry = 0;
-        for (int i = 0; i < n; i++)
-            if (level[i] == maxl) { entry = i; break; }
-        g->g.entry_node = entry;
-        std::vector<float> host_rows;
-        for (int l = 1; l <= maxl; l++) {
-            std::vector<int32_t> ids;
-            for (int i = 0; i < n; i++)
-                if (level[i] >= l) ids.push_back(i);
-            const int cnt = (int)ids.size();
-            std::vector<int32_t> ladj((size_t)cnt * degree, -1);
-            if (cnt > 1) {
-                // gather the members' rows into a temporary data set on the device
-                jv_dataset_s sub;
-                memset(&sub.d, 0, sizeof(DataDesc));
-                sub.d.kind = KIND_F32; sub.d.dim = f32->d.dim; sub.d.stride = f32->d.stride; sub.d.n = cnt;
-                float *drows = nullptr;
-                int32_t *dadj = nullptr;
-                if ((rc = sub.alloc((void **)&drows, (size_t)cnt * sub.d.stride * 4)) || (rc = sub.alloc((void **)&dadj, (size_t)cnt * degree * 4))) { delete g; return rc; }
-                for (int i = 0; i < cnt; i++) {
-                    e = cudaMemcpyAsync(drows + (size_t)i * sub.d.stride, f32->d.rows + (size_t)ids[i] * f32->d.stride, (size_t)sub.d.stride * 4,
-                                        cudaMemcpyDeviceToDevice, s);
-                    if (e != cudaSuccess) { delete g; return cuda_fail(e, "gather level rows"); }
-                }
-                sub.d.rows = drows;
-                BuildStats bs2;
-                e = build_graph_flat(sub.d, metric, bp, dadj, g_sm_count, &bs2, s);
-                if (e == cudaSuccess) e = cudaMemcpyAsync(ladj.data(), dadj, ladj.size() * 4, cudaMemcpyDeviceToHost, s);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-                if (e != cudaSuccess) { delete g; return cuda_fail(e, "build upper level"); }
-                for (auto &x : ladj)
-                    if (x >= 0) x = ids[x];
-            }
-            g->level_ids.push_back(ids);
-            g->level_adj.push_back(ladj);
-        }
-        if ((rc = graph_rebuild_upper(g))) { delete g; return rc; }
-    }
+    if (rc) { delete g; return rc; }
     if (device_ms) *device_ms = ms;
     *out = g;
+    return JV_OK;
+}
+
+// ---- the same build advanced batch by batch, for a build SHARDED over several GPUs (BASELINE config 5) ----------------------
+// Every rank holds a replica of the rows and of the adjacency. Per batch: each rank searches + prunes ITS slice of the batch
+// (jv_builder_insert_slice -> rows in a caller buffer), the slices are all-gathered by the caller (NCCL; jvector_b200/parallel.py),
+// every rank applies the whole batch deterministically (jv_builder_apply_new), then the rows that passed overflow * M are
+// re-pruned slice-wise and exchanged the same way. The device pointers are the caller's (e.g. torch tensors = the NCCL buffers).
+struct jv_builder_s {
+    int device = 0;
+    jv_dataset f32 = nullptr;
+    int metric = 0;
+    jv_build_params params;
+    BuildParams bp;
+    GraphBuilder *B = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr;
+};
+
+int jv_builder_create(jv_dataset f32, int metric, const jv_build_params *params, void *cuda_stream, jv_builder *out)
+{
+    ON_DEVICE_OF(f32);
+    if (!params || !out || f32->d.kind != KIND_F32) return fail(JV_ERR_INVALID, "builder_create: needs an fp32 data set");
+    int rc = check_metric(f32->d, metric);
+    if (rc) return rc;
+    jv_builder b = new jv_builder_s();
+    b->device = f32->device; b->f32 = f32; b->metric = metric; b->params = *params; b->stream = (cudaStream_t)cuda_stream;
+    if ((rc = build_params_check(params, &b->bp))) { delete b; return rc; }
+    cudaEventCreate(&b->e0);
+    cudaEventRecord(b->e0, b->stream);
+    cudaError_t e = builder_create(f32->d, metric, b->bp, g_sm_count, &b->B, b->stream);
+    if (e != cudaSuccess) { cudaEventDestroy(b->e0); delete b; return cuda_fail(e, "builder_create"); }
+    *out = b;
+    return JV_OK;
+}
+
+int jv_builder_info(jv_builder b, int *degree, int *row_cap, int *max_batch)
+{
+    if (!b) return fail(JV_ERR_INVALID, "builder_info: null");
+    if (degree) *degree = builder_degree(b->B);
+    if (row_cap) *row_cap = builder_row_cap(b->B);
+    if (max_batch) *max_batch = builder_max_batch(b->B);
+    return JV_OK;
+}
+
+int jv_builder_next_batch(jv_builder b, int32_t *first, int32_t *count)
+{
+    if (!b || !first || !count) return fail(JV_ERR_INVALID, "builder_next_batch: null");
+    int f = 0, c = 0;
+    const bool more = builder_next_batch(b->B, &f, &c);
+    *first = f;
+    *count = more ? c : 0;
+    return JV_OK;
+}
+
+int jv_builder_insert_slice(jv_builder b, int32_t first, int32_t count, int32_t lo, int32_t hi, int32_t *rows_out_device, int32_t *deg_out_device)
+{
+    ON_DEVICE_OF(b);
+    if (lo < 0 || hi > count || !rows_out_device || !deg_out_device) return fail(JV_ERR_INVALID, "builder_insert_slice: bad arguments");
+    CK(builder_insert_slice(b->B, first, count, lo, hi, rows_out_device, deg_out_device, b->stream), "builder_insert_slice");
+    return JV_OK;
+}
+
+int jv_builder_apply_new(jv_builder b, int32_t first, int32_t count, const int32_t *rows_device, const int32_t *deg_device, int32_t *overflow_rows)
+{
+    ON_DEVICE_OF(b);
+    if (!rows_device || !deg_device) return fail(JV_ERR_INVALID, "builder_apply_new: bad arguments");
+    CK(builder_apply_new(b->B, first, count, rows_device, deg_device, b->stream), "builder_apply_new");
+    if (overflow_rows) {
+        int c = 0;
+        CK(builder_list_count(b->B, &c, b->stream), "builder_list_count");
+        *overflow_rows = c;
+    }
+    return JV_OK;
+}
+
+int jv_builder_reprune_slice(jv_builder b, int32_t lo, int32_t hi, int32_t *rows_out_device, int32_t *deg_out_device)
+{
+    ON_DEVICE_OF(b);
+    if (!rows_out_device || !deg_out_device || lo < 0) return fail(JV_ERR_INVALID, "builder_reprune_slice: bad arguments");
+    CK(builder_reprune_slice(b->B, lo, hi, rows_out_device, deg_out_device, b->stream), "builder_reprune_slice");
+    return JV_OK;
+}
+
+int jv_builder_apply_repruned(jv_builder b, int32_t count, const int32_t *rows_device, const int32_t *deg_device)
+{
+    ON_DEVICE_OF(b);
+    CK(builder_apply_repruned(b->B, count, rows_device, deg_device, b->stream), "builder_apply_repruned");
+    return JV_OK;
+}
+
+int jv_builder_collect_over_degree(jv_builder b, int32_t *rows)
+{
+    ON_DEVICE_OF(b);
+    CK(builder_collect_over_degree(b->B, b->stream), "builder_collect_over_degree");
+    int c = 0;
+    CK(builder_list_count(b->B, &c, b->stream), "builder_list_count");
+    if (rows) *rows = c;
+    return JV_OK;
+}
+
+// compacts the level-0 adjacency into a graph; the upper levels (3 % of the nodes at M = 32) are built by every replica itself
+int jv_builder_finish(jv_builder b, jv_graph *out, double *device_ms)
+{
+    ON_DEVICE_OF(b);
+    if (!out) return fail(JV_ERR_INVALID, "builder_finish: null");
+    int rc;
+    if ((rc = t_ctx.init())) return rc;
+    const int n = (int)b->f32->d.n, degree = b->bp.degree;
+    jv_graph g = new jv_graph_s();
+    g->device = b->device;
+    memset(&g->g, 0, sizeof(GraphDesc));
+    cudaError_t e = cudaMalloc((void **)&g->adj0, (size_t)n * degree * 4);
+    if (e != cudaSuccess) { delete g; return cuda_fail(e, "cudaMalloc(adjacency)"); }
+    BuildStats bs;
+    e = builder_finish(b->B, g->adj0, &bs, b->stream);
+    t_build_stats = bs;
+    if (e != cudaSuccess) { delete g; return cuda_fail(e, "builder_finish"); }
+    g->g.n = n; g->g.degree = degree; g->g.levels = 1; g->g.entry_node = 0; g->g.entry_level = 0; g->g.adj0 = g->adj0;
+    if (b->params.add_hierarchy && n > 1 && (rc = build_upper_levels(g, b->f32, b->metric, b->bp, b->params.seed, b->stream))) { delete g; return rc; }
+    cudaEvent_t e1;
+    cudaEventCreate(&e1);
+    cudaEventRecord(e1, b->stream);
+    cudaStreamSynchronize(b->stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, b->e0, e1);
+    cudaEventDestroy(e1);
+    if (device_ms) *device_ms = ms;
+    *out = g;
+    return JV_OK;
+}
+
+int jv_builder_free(jv_builder b)
+{
+    if (!b) return JV_OK;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    else cudaDeviceSynchronize();
+    builder_destroy(b->B);
+    if (b->e0) cudaEventDestroy(b->e0);
+    delete b;
     return JV_OK;
 }
 

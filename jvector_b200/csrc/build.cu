@@ -16,8 +16,12 @@
 // reference are concurrency-order dependent, so parity is on scores and on the recall of the resulting graph
 // (SURVEY §8d C5), not on identical adjacency.
 #include <limits.h>
+#include <string.h>
 
+#include <algorithm>
 #include <vector>
+
+#include <cub/cub.cuh>
 
 #include "kernels.h"
 
@@ -44,7 +48,30 @@ struct PruneParams {
     const int32_t *cand;
     int cand_stride;
     int *mark;  // cleared for pruned nodes in mode 1
+    // mode 0: the W nodes around a batch node in insertion order are candidates too — the batch plays the reference's set of
+    // concurrently inserting threads, whose in-progress nodes every insert scores and merges into its candidates
+    // (GraphIndexBuilder.java:611-612,669,823-837 getConcurrentCandidates). Batch = nodes [batch_first, batch_first + batch_count).
+    int window, batch_first, batch_count;
+    // out-of-place results (sharded build: the slice's rows travel before they are applied): row i of this launch goes to
+    // out_rows[(out_base + i) * out_stride ..] and out_deg[out_base + i]; nullptr = write adj / deg in place
+    int32_t *out_rows;
+    int *out_deg;
+    int out_stride, out_base;
+    int list_base;  // mode 1: nodes = list[list_base + i]
 };
+
+// candidate i of node v: the search result while i < cand_stride, then the in-progress window (skipping v itself)
+__device__ __forceinline__ int32_t prune_candidate(const PruneParams &P, const int32_t *cand, int nc_search, int v, int i)
+{
+    if (i < nc_search) return cand[i];
+    if (P.mode != 0 || P.window <= 0) return -1;
+    const int j = i - nc_search;  // 0 .. window-1
+    const int half = P.window >> 1;
+    int w = v - half + j;
+    if (w >= v) w += 1;  // skip v: the window holds `window` OTHER nodes
+    if (w < P.batch_first || w >= P.batch_first + P.batch_count) return -1;
+    return w;
+}
 
 __device__ __forceinline__ void bitonic_sort_desc_prune(long long *keys, int n_pow2)
 {
@@ -121,22 +148,23 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_kernel(PruneParams P)
     for (float a = 1.0f; a <= P.alpha + 1e-6f; a += 0.2f) alpha_max = a;
 
     for (int it = blockIdx.x; it < total; it += gridDim.x) {
-        const int v = P.mode == 0 ? P.node_base + it : P.list[it];
+        const int v = P.mode == 0 ? P.node_base + it : P.list[P.list_base + it];
         const int32_t *cand;
-        int nc;
+        int nc, ncs;
         if (P.mode == 0) {
             cand = P.cand + (size_t)it * P.cand_stride;
-            nc = P.cand_stride;
+            ncs = P.cand_stride;
+            nc = ncs + P.window;
         } else {
             cand = P.adj + (size_t)v * P.row_cap;
-            nc = min(P.deg[v], P.row_cap);
+            ncs = nc = min(P.deg[v], P.row_cap);
         }
         nc = min(nc, PRUNE_MAXC);
         prepare_blob(P.d, P.metric, P.d.rows + (size_t)v * P.d.stride, blob, red);
         // exact scores of the candidates against v, as sortable keys (two rows per warp at a time)
         for (int i = warp; i < PRUNE_MAXC; i += 2 * NW) {
             const int i2 = i + NW;
-            const int32_t ca = i < nc ? cand[i] : -1, cb = i2 < nc ? cand[i2] : -1;
+            const int32_t ca = i < nc ? prune_candidate(P, cand, ncs, v, i) : -1, cb = i2 < nc ? prune_candidate(P, cand, ncs, v, i2) : -1;
             const bool va = ca >= 0 && ca != v, vb = cb >= 0 && cb != v;
             long long ka = KEY_MIN, kb = KEY_MIN;
             if (va || vb) {
@@ -209,11 +237,13 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_kernel(PruneParams P)
         __syncthreads();
         if (tid == 0) {
             int w = 0;
-            int32_t *row = P.adj + (size_t)v * P.row_cap;
+            int32_t *row = P.out_rows ? P.out_rows + (size_t)(P.out_base + it) * P.out_stride : P.adj + (size_t)v * P.row_cap;
+            const int width = P.out_rows ? P.out_stride : P.row_cap;
             for (int i = 0; i < nvalid; i++)
                 if (state[i] == 1) row[w++] = key_node(keys[i]);
-            for (int i = w; i < P.row_cap; i++) row[i] = -1;
-            P.deg[v] = w;
+            for (int i = w; i < width; i++) row[i] = -1;
+            if (P.out_rows) P.out_deg[P.out_base + it] = w;
+            else P.deg[v] = w;
             if (P.mode == 1 && P.mark) P.mark[v] = 0;
         }
         __syncthreads();
@@ -255,21 +285,22 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_gram_kernel(PruneParams P
     for (float a = 1.0f; a <= P.alpha + 1e-6f; a += 0.2f) alpha_max = a;
 
     for (int it = blockIdx.x; it < total; it += gridDim.x) {
-        const int v = P.mode == 0 ? P.node_base + it : P.list[it];
+        const int v = P.mode == 0 ? P.node_base + it : P.list[P.list_base + it];
         const int32_t *cand;
-        int nc;
+        int nc, ncs;
         if (P.mode == 0) {
             cand = P.cand + (size_t)it * P.cand_stride;
-            nc = P.cand_stride;
+            ncs = P.cand_stride;
+            nc = ncs + P.window;
         } else {
             cand = P.adj + (size_t)v * P.row_cap;
-            nc = min(P.deg[v], P.row_cap);
+            ncs = nc = min(P.deg[v], P.row_cap);
         }
         nc = min(nc, TILE);
         prepare_blob(P.d, P.metric, P.d.rows + (size_t)v * P.d.stride, blob, red);
         for (int i = warp; i < TILE; i += 2 * NW) {
             const int i2 = i + NW;
-            const int32_t ca = i < nc ? cand[i] : -1, cb = (i2 < TILE && i2 < nc) ? cand[i2] : -1;
+            const int32_t ca = i < nc ? prune_candidate(P, cand, ncs, v, i) : -1, cb = (i2 < TILE && i2 < nc) ? prune_candidate(P, cand, ncs, v, i2) : -1;
             const bool va = ca >= 0 && ca != v, vb = cb >= 0 && cb != v;
             long long ka = KEY_MIN, kb = KEY_MIN;
             if (va || vb) {
@@ -397,11 +428,13 @@ __global__ void __launch_bounds__(PRUNE_THREADS) prune_gram_kernel(PruneParams P
         __syncthreads();
         if (tid == 0) {
             int w = 0;
-            int32_t *row = P.adj + (size_t)v * P.row_cap;
+            int32_t *row = P.out_rows ? P.out_rows + (size_t)(P.out_base + it) * P.out_stride : P.adj + (size_t)v * P.row_cap;
+            const int width = P.out_rows ? P.out_stride : P.row_cap;
             for (int i = 0; i < nvalid; i++)
                 if (state[i] == 1) row[w++] = ids[i];
-            for (int i = w; i < P.row_cap; i++) row[i] = -1;
-            P.deg[v] = w;
+            for (int i = w; i < width; i++) row[i] = -1;
+            if (P.out_rows) P.out_deg[P.out_base + it] = w;
+            else P.deg[v] = w;
             if (P.mode == 1 && P.mark) P.mark[v] = 0;
         }
         __syncthreads();
@@ -415,31 +448,96 @@ static size_t gram_smem_bytes(const DataDesc &d)
     return (b + 15) & ~(size_t)15;
 }
 
-// back-links: for every selected neighbour v of a new node u append u to v's row (ConcurrentNeighborMap.backlink)
-__global__ void __launch_bounds__(256) backlink_kernel(int32_t *adj, int *deg, int row_cap, int degree, int node_base, int count, int hard_max,
-                                                       int *mark, int32_t *prune_list, int *prune_count, unsigned long long *dropped)
+// ------------------------------------------------------------------------------------------------
+// back-links (ConcurrentNeighborMap.backlink, ConcurrentNeighborMap.java:158-165): for every selected neighbour t of a new
+// node u, append u to t's row. Deterministic: the (t, u) pairs of a batch are SORTED, pair i lands at deg_before[t] + (rank of i
+// inside t's segment), so every replica of a sharded build applies a batch to bit-identical adjacency (atomics would order the
+// appends by timing, and which back-link a full row drops would differ between replicas).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) apply_rows_kernel(int32_t *adj, int *deg, int row_cap, int degree, int first, int count, const int32_t *rows,
+                                                         const int *rdeg, unsigned long long *pairs)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= count * degree) return;
-    const int u = node_base + idx / degree, j = idx % degree;
-    const int32_t v = adj[(size_t)u * row_cap + j];
-    if (v < 0) return;
-    const int pos = atomicAdd(&deg[v], 1);
-    if (pos < row_cap) adj[(size_t)v * row_cap + pos] = u;
+    if (idx >= count * row_cap) return;
+    const int i = idx / row_cap, j = idx - i * row_cap;
+    const int u = first + i;
+    const int32_t t = j < degree ? rows[(size_t)i * degree + j] : -1;
+    adj[(size_t)u * row_cap + j] = t;
+    if (j == 0) deg[u] = rdeg[i];
+    if (j < degree) pairs[(size_t)i * degree + j] = t >= 0 ? (((unsigned long long)(unsigned)t << 32) | (unsigned)u) : ~0ull;  // ~0 sorts last
+}
+
+__device__ __forceinline__ int lower_bound_u64(const unsigned long long *a, int n, unsigned long long key)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// pairs sorted ascending. Thread i appends its u; the head of each segment publishes the new degree and flags the row when it
+// passed overflow * M (ConcurrentNeighborMap.java:300: the row is then re-pruned).
+__global__ void __launch_bounds__(256) backlink_sorted_kernel(int32_t *adj, int *deg, int row_cap, int hard_max, const unsigned long long *pairs, int npairs,
+                                                              unsigned char *head_flag, int32_t *head_target, unsigned long long *dropped)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const unsigned long long p = pairs[i];
+    head_flag[i] = 0;
+    head_target[i] = -1;
+    if (p == ~0ull) return;
+    const int t = (int)(p >> 32), u = (int)(unsigned)p;
+    const int seg0 = lower_bound_u64(pairs, npairs, (unsigned long long)(unsigned)t << 32);
+    const int d0 = deg[t];  // no thread writes deg[t] before every pair of the segment has read it: see below
+    const int pos = d0 + (i - seg0);
+    if (pos < row_cap) adj[(size_t)t * row_cap + pos] = u;
     else atomicAdd(dropped, 1ull);
-    if (pos + 1 > hard_max && atomicExch(&mark[v], 1) == 0) prune_list[atomicAdd(prune_count, 1)] = v;
+    if (i == seg0) {
+        // segment head: remember the target and whether the row now passes overflow * M. The new degree itself is published by
+        // publish_deg_kernel, a second launch, because the other pairs of the segment still read deg[t] in this one.
+        const int seg1 = lower_bound_u64(pairs, npairs, (unsigned long long)((unsigned)t + 1u) << 32);
+        const int nd = min(row_cap, d0 + (seg1 - seg0));
+        head_target[i] = t;
+        head_flag[i] = nd > hard_max ? 1 : 0;
+    }
 }
 
-__global__ void __launch_bounds__(256) clamp_deg_kernel(int *deg, int n, int row_cap)
+__global__ void __launch_bounds__(256) publish_deg_kernel(int *deg, int row_cap, const unsigned long long *pairs, int npairs)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && deg[i] > row_cap) deg[i] = row_cap;
+    if (i >= npairs) return;
+    const unsigned long long p = pairs[i];
+    if (p == ~0ull) return;
+    const int t = (int)(p >> 32);
+    if (i > 0 && (int)(pairs[i - 1] >> 32) == t) return;  // not a segment head
+    const int seg1 = lower_bound_u64(pairs, npairs, (unsigned long long)((unsigned)t + 1u) << 32);
+    deg[t] = min(row_cap, deg[t] + (seg1 - i));
 }
 
-__global__ void __launch_bounds__(256) collect_over_degree_kernel(const int *deg, int n, int degree, int32_t *list, int *count)
+__global__ void __launch_bounds__(256) flag_over_degree_kernel(const int *deg, int n, int degree, unsigned char *flag)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && deg[i] > degree) list[atomicAdd(count, 1)] = i;
+    if (i < n) flag[i] = deg[i] > degree ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(int32_t *a, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = i;
+}
+
+// re-pruned rows coming back from the exchange: row i replaces adj[list[i]]
+__global__ void __launch_bounds__(256) scatter_rows_kernel(int32_t *adj, int *deg, int row_cap, const int32_t *list, int count, const int32_t *rows, const int *rdeg)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * row_cap) return;
+    const int i = idx / row_cap, j = idx - i * row_cap;
+    const int v = list[i];
+    adj[(size_t)v * row_cap + j] = rows[(size_t)i * row_cap + j];
+    if (j == 0) deg[v] = rdeg[i];
 }
 
 __global__ void __launch_bounds__(256) compact_adj_kernel(const int32_t *adj, const int *deg, int n, int row_cap, int degree, int32_t *out)
@@ -448,6 +546,26 @@ __global__ void __launch_bounds__(256) compact_adj_kernel(const int32_t *adj, co
     if (idx >= (long long)n * degree) return;
     const int v = (int)(idx / degree), j = (int)(idx % degree);
     out[idx] = j < min(deg[v], degree) ? adj[(size_t)v * row_cap + j] : -1;
+}
+
+// rows [ids[i]] of a data set gathered into a dense one (upper levels of the hierarchy, repair pass): one warp per row
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ rows, int stride, const int32_t *__restrict__ ids, int count, float *__restrict__ out)
+{
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= count) return;
+    const float4 *src = reinterpret_cast<const float4 *>(rows + (size_t)ids[warp] * stride);
+    float4 *dst = reinterpret_cast<float4 *>(out + (size_t)warp * stride);
+    for (int i = lane; i < (stride >> 2); i += 32) dst[i] = ldg_stream(src + i);
+}
+
+cudaError_t launch_gather_rows(const DataDesc &f32, const int32_t *ids_dev, int count, float *out_dev, cudaStream_t s)
+{
+    if (count <= 0) return cudaSuccess;
+    const long long blocks = ((long long)count * 32 + 255) / 256;
+    gather_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(f32.rows, f32.stride, ids_dev, count, out_dev);
+    g_launches++;
+    return cudaGetLastError();
 }
 
 static size_t prune_smem_bytes(const DataDesc &d)
@@ -460,7 +578,7 @@ template <int METRIC>
 static cudaError_t launch_prune_t(const PruneParams &P, int grid, size_t smem, cudaStream_t s)
 {
     // candidate sets that fit a tile go through the Gram-matrix kernel; anything larger keeps the incremental kernel
-    const int ncmax = P.mode == 0 ? P.cand_stride : P.row_cap;
+    const int ncmax = P.mode == 0 ? P.cand_stride + P.window : P.row_cap;
     cudaError_t e;
     if (ncmax <= 64) {
         const size_t gs = gram_smem_bytes<64>(P.d);
@@ -488,119 +606,271 @@ static cudaError_t launch_prune(const PruneParams &P, int grid, size_t smem, cud
 #define JV_TRY(x)                      \
     do {                               \
         err = (x);                     \
-        if (err != cudaSuccess) goto done; \
+        if (err != cudaSuccess) return err; \
     } while (0)
 
+// ------------------------------------------------------------------------------------------------
+// GraphBuilder: the device-resident state of one flat (single level) build, advanced batch by batch. One rank of a sharded
+// build calls insert_slice / reprune_slice for ITS part of a batch; the rows travel (NCCL all-gather in jvector_b200/parallel.py,
+// nothing at all on one GPU) and every replica applies the whole batch with apply_new / apply_repruned, deterministically.
+// ------------------------------------------------------------------------------------------------
+struct GraphBuilder {
+    DataDesc d;
+    int metric = 0, sm_count = 0;
+    BuildParams bp;
+    int n = 0, degree = 0, beam = 0, hard_max = 0, row_cap = 0, max_batch = 0, window = 0;
+    int inserted = 1;  // node 0 is the entry point with an empty list
+    int32_t *adj = nullptr, *res_nodes = nullptr, *list = nullptr, *head_target = nullptr, *iota = nullptr;
+    int *deg = nullptr, *mark = nullptr, *list_count = nullptr, *work_counter = nullptr;
+    float *res_scores = nullptr;
+    unsigned long long *dropped = nullptr, *pairs = nullptr, *pairs_sorted = nullptr;
+    unsigned char *head_flag = nullptr, *node_flag = nullptr;
+    SearchCounters *counters = nullptr;
+    uint8_t *overflow = nullptr;
+    void *scratch = nullptr, *cub_tmp = nullptr;
+    size_t scratch_bytes = 0, cub_bytes = 0;
+    int32_t *own_rows = nullptr;  // single-GPU path: the slice buffers are the builder's own
+    int *own_deg = nullptr;
+    int32_t *own_rp_rows = nullptr;
+    int *own_rp_deg = nullptr;
+    size_t own_rp_cap = 0;
+    BuildStats st = {0, 0, 0, 0};
+    size_t psmem = 0;
+    int prune_grid = 0;
+};
+
+static void builder_free(GraphBuilder *B)
+{
+    if (!B) return;
+    cudaFree(B->adj); cudaFree(B->res_nodes); cudaFree(B->list); cudaFree(B->head_target); cudaFree(B->iota); cudaFree(B->deg); cudaFree(B->mark);
+    cudaFree(B->list_count); cudaFree(B->work_counter); cudaFree(B->res_scores); cudaFree(B->dropped); cudaFree(B->pairs); cudaFree(B->pairs_sorted);
+    cudaFree(B->head_flag); cudaFree(B->node_flag); cudaFree(B->counters); cudaFree(B->overflow); cudaFree(B->scratch); cudaFree(B->cub_tmp);
+    cudaFree(B->own_rows); cudaFree(B->own_deg); cudaFree(B->own_rp_rows); cudaFree(B->own_rp_deg);
+    delete B;
+}
+
+void builder_destroy(GraphBuilder *B) { builder_free(B); }
+
+cudaError_t builder_create(const DataDesc &d, int metric, const BuildParams &bp, int sm_count, GraphBuilder **out, cudaStream_t s)
+{
+    const int n = (int)d.n;
+    if (d.kind != KIND_F32 || bp.degree < 1 || bp.degree > 64 || bp.beam < 1 || bp.beam > PRUNE_MAXC) return cudaErrorInvalidValue;
+    GraphBuilder *B = new GraphBuilder();
+    B->d = d; B->metric = metric; B->bp = bp; B->sm_count = sm_count; B->n = n; B->degree = bp.degree; B->beam = bp.beam;
+    B->hard_max = (int)(bp.overflow * bp.degree);  // ConcurrentNeighborMap.java:300
+    B->row_cap = std::max(2 * bp.degree, B->hard_max + 1);
+    if (B->row_cap > MAX_DEGREE) { delete B; return cudaErrorInvalidValue; }
+    B->max_batch = bp.max_batch > 0 ? bp.max_batch : 16384;
+    // in-progress window: as many concurrently inserting peers as still fit the 128-candidate Gram tile next to the beam
+    B->window = bp.window >= 0 ? bp.window : std::max(0, std::min(32, 128 - bp.beam));
+    B->psmem = prune_smem_bytes(d);
+    B->prune_grid = sm_count * 5;  // ~10 KB of shared memory per CTA: register-limited residency
+    cudaError_t err = cudaSuccess;
+    const size_t mb = (size_t)B->max_batch;
+#define ALLOC(ptr, bytes)                                                  \
+    do {                                                                   \
+        err = cudaMalloc((void **)&(ptr), (bytes));                        \
+        if (err != cudaSuccess) { builder_free(B); return err; }           \
+    } while (0)
+    ALLOC(B->adj, (size_t)n * B->row_cap * 4);
+    ALLOC(B->deg, (size_t)n * 4);
+    ALLOC(B->mark, (size_t)n * 4);
+    ALLOC(B->res_nodes, mb * B->beam * 4);
+    ALLOC(B->res_scores, mb * B->beam * 4);
+    ALLOC(B->list, (size_t)n * 4);
+    ALLOC(B->iota, (size_t)n * 4);
+    ALLOC(B->node_flag, (size_t)n);
+    ALLOC(B->list_count, 16);
+    ALLOC(B->work_counter, 16);
+    ALLOC(B->dropped, 16);
+    ALLOC(B->counters, sizeof(SearchCounters));
+    ALLOC(B->overflow, mb);
+    ALLOC(B->pairs, mb * B->degree * 8);
+    ALLOC(B->pairs_sorted, mb * B->degree * 8);
+    ALLOC(B->head_flag, mb * B->degree);
+    ALLOC(B->head_target, mb * B->degree * 4);
+    ALLOC(B->own_rows, mb * B->degree * 4);
+    ALLOC(B->own_deg, mb * 4);
+#undef ALLOC
+    {
+        size_t b1 = 0, b2 = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, b1, B->pairs, B->pairs_sorted, (int)(mb * B->degree), 0, 64, s);
+        cub::DeviceSelect::Flagged(nullptr, b2, B->iota, B->node_flag, B->list, B->list_count, n, s);
+        B->cub_bytes = std::max(b1, b2) + 256;
+        err = cudaMalloc(&B->cub_tmp, B->cub_bytes);
+        if (err != cudaSuccess) { builder_free(B); return err; }
+    }
+    JV_TRY(cudaMemsetAsync(B->adj, 0xff, (size_t)n * B->row_cap * 4, s));
+    JV_TRY(cudaMemsetAsync(B->deg, 0, (size_t)n * 4, s));
+    JV_TRY(cudaMemsetAsync(B->mark, 0, (size_t)n * 4, s));
+    JV_TRY(cudaMemsetAsync(B->dropped, 0, 16, s));
+    JV_TRY(cudaMemsetAsync(B->list_count, 0, 16, s));
+    JV_TRY(cudaMemsetAsync(B->counters, 0, sizeof(SearchCounters), s));
+    iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(B->iota, n);
+    g_launches++;
+    *out = B;
+    return cudaGetLastError();
+}
+
+// the next batch: half of what is already inserted (so early nodes see a connected graph), at most max_batch
+bool builder_next_batch(GraphBuilder *B, int *first, int *count)
+{
+    if (B->inserted >= B->n) return false;
+    int batch = B->inserted / 2;
+    if (batch < 1) batch = 1;
+    if (batch > B->max_batch) batch = B->max_batch;
+    if (batch > B->n - B->inserted) batch = B->n - B->inserted;
+    *first = B->inserted;
+    *count = batch;
+    return true;
+}
+
+static PruneParams prune_params(const GraphBuilder *B)
+{
+    PruneParams P;
+    memset(&P, 0, sizeof(P));
+    P.d = B->d; P.metric = B->metric; P.degree = B->degree; P.row_cap = B->row_cap; P.alpha = B->bp.alpha; P.adj = B->adj; P.deg = B->deg; P.mark = B->mark;
+    return P;
+}
+
+// batch positions [lo, hi): beam search of the graph as it stands + robust prune of (beam U in-progress window) -> rows_out
+// [batch][degree] at positions lo..hi-1, deg_out likewise. Reads adjacency, writes none of it.
+cudaError_t builder_insert_slice(GraphBuilder *B, int first, int count, int lo, int hi, int32_t *rows_out, int *deg_out, cudaStream_t s)
+{
+    cudaError_t err = cudaSuccess;
+    if (!rows_out) { rows_out = B->own_rows; deg_out = B->own_deg; }
+    const int m = hi - lo;
+    if (m <= 0) return cudaSuccess;
+    GraphDesc g = {};
+    g.n = B->n; g.degree = B->row_cap; g.levels = 1; g.entry_node = 0; g.entry_level = 0; g.adj0 = B->adj;
+    SearchPlan plan;
+    JV_TRY(plan_search(B->d, nullptr, g, B->beam, B->beam, m, 0, 0, B->sm_count, &plan));
+    const size_t need = search_scratch_bytes(plan);
+    if (need > B->scratch_bytes) {
+        if (B->scratch) cudaFree(B->scratch);
+        B->scratch = nullptr;
+        B->scratch_bytes = 0;
+        JV_TRY(cudaMalloc(&B->scratch, need));
+        B->scratch_bytes = need;
+    }
+    JV_TRY(launch_search(g, B->d, nullptr, B->metric, B->d.rows + (size_t)(first + lo) * B->d.stride, m, B->beam, B->beam, plan, B->scratch, B->work_counter,
+                         B->res_nodes, B->res_scores, B->counters, B->overflow, nullptr, B->d.stride, nullptr, s));
+    PruneParams P = prune_params(B);
+    P.mode = 0; P.node_base = first + lo; P.count = m; P.cand = B->res_nodes; P.cand_stride = B->beam;
+    P.window = B->window; P.batch_first = first; P.batch_count = count;
+    P.out_rows = rows_out; P.out_deg = deg_out; P.out_stride = B->degree; P.out_base = lo;
+    JV_TRY(launch_prune(P, m < B->prune_grid ? m : B->prune_grid, B->psmem, s));
+    return cudaSuccess;
+}
+
+// the whole batch's rows (this rank's own slice + the gathered ones): write them, back-link them deterministically, and leave
+// the SORTED list of rows that passed overflow * M in B->list (count in B->list_count[0])
+cudaError_t builder_apply_new(GraphBuilder *B, int first, int count, const int32_t *rows, const int *rdeg, cudaStream_t s)
+{
+    cudaError_t err = cudaSuccess;
+    if (!rows) { rows = B->own_rows; rdeg = B->own_deg; }
+    const int npairs = count * B->degree;
+    apply_rows_kernel<<<(count * B->row_cap + 255) / 256, 256, 0, s>>>(B->adj, B->deg, B->row_cap, B->degree, first, count, rows, rdeg, B->pairs);
+    g_launches++;
+    size_t tb = B->cub_bytes;
+    JV_TRY(cub::DeviceRadixSort::SortKeys(B->cub_tmp, tb, B->pairs, B->pairs_sorted, npairs, 0, 64, s));
+    g_launches++;
+    backlink_sorted_kernel<<<(npairs + 255) / 256, 256, 0, s>>>(B->adj, B->deg, B->row_cap, B->hard_max, B->pairs_sorted, npairs, B->head_flag, B->head_target, B->dropped);
+    g_launches++;
+    publish_deg_kernel<<<(npairs + 255) / 256, 256, 0, s>>>(B->deg, B->row_cap, B->pairs_sorted, npairs);
+    g_launches++;
+    tb = B->cub_bytes;
+    JV_TRY(cub::DeviceSelect::Flagged(B->cub_tmp, tb, B->head_target, B->head_flag, B->list, B->list_count, npairs, s));  // sorted by target: heads are
+    g_launches++;
+    B->inserted = first + count;
+    B->st.batches++;
+    return cudaGetLastError();
+}
+
+// rows list[lo .. hi) re-pruned (VamanaDiversityProvider.retainDiverse over the row itself). rows_out == nullptr: in place, with
+// the count read on the device (one-GPU path, no host round trip); otherwise out-of-place into rows_out [.][row_cap] at lo..hi-1.
+cudaError_t builder_reprune_slice(GraphBuilder *B, int lo, int hi, int32_t *rows_out, int *deg_out, cudaStream_t s)
+{
+    PruneParams P = prune_params(B);
+    P.mode = 1; P.list = B->list;
+    if (!rows_out) {
+        P.count_ptr = B->list_count;
+        return launch_prune(P, B->prune_grid, B->psmem, s);
+    }
+    if (hi <= lo) return cudaSuccess;
+    P.count = hi - lo; P.list_base = lo; P.out_rows = rows_out; P.out_deg = deg_out; P.out_stride = B->row_cap; P.out_base = lo;
+    return launch_prune(P, std::min(hi - lo, B->prune_grid), B->psmem, s);
+}
+
+cudaError_t builder_apply_repruned(GraphBuilder *B, int count, const int32_t *rows, const int *rdeg, cudaStream_t s)
+{
+    if (count <= 0) return cudaSuccess;
+    scatter_rows_kernel<<<(count * B->row_cap + 255) / 256, 256, 0, s>>>(B->adj, B->deg, B->row_cap, B->list, count, rows, rdeg);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// cleanup() of the reference: enforceDegree on every row longer than M. Leaves the sorted list of those rows in B->list.
+cudaError_t builder_collect_over_degree(GraphBuilder *B, cudaStream_t s)
+{
+    cudaError_t err = cudaSuccess;
+    flag_over_degree_kernel<<<(B->n + 255) / 256, 256, 0, s>>>(B->deg, B->n, B->degree, B->node_flag);
+    g_launches++;
+    size_t tb = B->cub_bytes;
+    JV_TRY(cub::DeviceSelect::Flagged(B->cub_tmp, tb, B->iota, B->node_flag, B->list, B->list_count, B->n, s));
+    g_launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t builder_list_count(GraphBuilder *B, int *count_host, cudaStream_t s)
+{
+    cudaError_t err = cudaSuccess;
+    JV_TRY(cudaMemcpyAsync(count_host, B->list_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    return cudaStreamSynchronize(s);
+}
+
+cudaError_t builder_finish(GraphBuilder *B, int32_t *adj_out_dev, BuildStats *stats, cudaStream_t s)
+{
+    cudaError_t err = cudaSuccess;
+    const long long total = (long long)B->n * B->degree;
+    compact_adj_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(B->adj, B->deg, B->n, B->row_cap, B->degree, adj_out_dev);
+    g_launches++;
+    JV_TRY(cudaGetLastError());
+    SearchCounters hc;
+    unsigned long long hd = 0;
+    JV_TRY(cudaMemcpyAsync(&hc, B->counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    JV_TRY(cudaMemcpyAsync(&hd, B->dropped, sizeof(hd), cudaMemcpyDeviceToHost, s));
+    JV_TRY(cudaStreamSynchronize(s));
+    B->st.searched = (long long)hc.visited;
+    B->st.dropped_backlinks = (long long)hd;
+    if (stats) *stats = B->st;
+    // an insert search that overflowed its visited table left its node without neighbours; the graph is still valid (the node is
+    // reachable through later back-links) but the caller is told
+    return hc.overflowed ? cudaErrorLaunchOutOfResources : cudaSuccess;
+}
+
+int builder_row_cap(const GraphBuilder *B) { return B->row_cap; }
+int builder_degree(const GraphBuilder *B) { return B->degree; }
+int builder_max_batch(const GraphBuilder *B) { return B->max_batch; }
+
+// the whole build on one GPU: no exchange, no host synchronisation between batches
 cudaError_t build_graph_flat(const DataDesc &d, int metric, const BuildParams &bp, int32_t *adj_out_dev, int sm_count,
                              BuildStats *stats, cudaStream_t s)
 {
-    const int n = (int)d.n;
-    const int degree = bp.degree, beam = bp.beam;
-    if (d.kind != KIND_F32 || degree < 1 || degree > 64 || beam < 1 || beam > PRUNE_MAXC) return cudaErrorInvalidValue;
-    const int hard_max = (int)(bp.overflow * degree);  // ConcurrentNeighborMap.java:300
-    int row_cap = 2 * degree;
-    if (row_cap < hard_max + 1) row_cap = hard_max + 1;
-    if (row_cap > MAX_DEGREE) return cudaErrorInvalidValue;
-    const int max_batch = bp.max_batch > 0 ? bp.max_batch : 16384;
-
-    cudaError_t err = cudaSuccess;
-    int32_t *adj = nullptr, *res_nodes = nullptr, *prune_list = nullptr;
-    int *deg = nullptr, *mark = nullptr, *prune_count = nullptr, *work_counter = nullptr;
-    float *res_scores = nullptr;
-    unsigned long long *dropped = nullptr;
-    SearchCounters *counters = nullptr;
-    uint8_t *overflow = nullptr;
-    void *scratch = nullptr;
-    size_t scratch_bytes = 0;
-    BuildStats st = {0, 0, 0, 0};
-    const size_t psmem = prune_smem_bytes(d);
-    const int prune_grid = sm_count * 5;  // ~10 KB of shared memory per CTA: register-limited residency
-
-    JV_TRY(cudaMalloc(&adj, (size_t)n * row_cap * sizeof(int32_t)));
-    JV_TRY(cudaMemsetAsync(adj, 0xff, (size_t)n * row_cap * sizeof(int32_t), s));
-    JV_TRY(cudaMalloc(&deg, (size_t)n * sizeof(int)));
-    JV_TRY(cudaMemsetAsync(deg, 0, (size_t)n * sizeof(int), s));
-    JV_TRY(cudaMalloc(&mark, (size_t)n * sizeof(int)));
-    JV_TRY(cudaMemsetAsync(mark, 0, (size_t)n * sizeof(int), s));
-    JV_TRY(cudaMalloc(&res_nodes, (size_t)max_batch * beam * sizeof(int32_t)));
-    JV_TRY(cudaMalloc(&res_scores, (size_t)max_batch * beam * sizeof(float)));
-    JV_TRY(cudaMalloc(&prune_list, (size_t)n * sizeof(int32_t)));
-    JV_TRY(cudaMalloc(&prune_count, sizeof(int)));
-    JV_TRY(cudaMalloc(&work_counter, sizeof(int)));
-    JV_TRY(cudaMalloc(&dropped, sizeof(unsigned long long)));
-    JV_TRY(cudaMemsetAsync(dropped, 0, sizeof(unsigned long long), s));
-    JV_TRY(cudaMalloc(&counters, sizeof(SearchCounters)));
-    JV_TRY(cudaMemsetAsync(counters, 0, sizeof(SearchCounters), s));
-    JV_TRY(cudaMalloc(&overflow, (size_t)max_batch));
-
-    {
-        GraphDesc g = {};
-        g.n = n; g.degree = row_cap; g.levels = 1; g.entry_node = 0; g.entry_level = 0;
-        g.adj0 = adj; g.upper_row = nullptr; g.upper_adj = nullptr; g.upper_off = nullptr;
-        int inserted = 1;  // node 0 is the entry point with an empty list
-        while (inserted < n) {
-            int batch = inserted / 2;
-            if (batch < 1) batch = 1;
-            if (batch > max_batch) batch = max_batch;
-            if (batch > n - inserted) batch = n - inserted;
-            // (1) beam search of the current graph for every node of the batch
-            SearchPlan plan;
-            JV_TRY(plan_search(d, nullptr, g, beam, beam, batch, 0, 0, sm_count, &plan));
-            const size_t need = search_scratch_bytes(plan);
-            if (need > scratch_bytes) {
-                if (scratch) cudaFree(scratch);
-                scratch = nullptr;
-                JV_TRY(cudaMalloc(&scratch, need));
-                scratch_bytes = need;
-            }
-            JV_TRY(launch_search(g, d, nullptr, metric, d.rows + (size_t)inserted * d.stride, batch, beam, beam, plan, scratch, work_counter,
-                                 res_nodes, res_scores, counters, overflow, nullptr, d.stride, nullptr, s));
-            // (2) robust prune of each beam -> the new node's list
-            PruneParams P;
-            P.d = d; P.metric = metric; P.degree = degree; P.row_cap = row_cap; P.alpha = bp.alpha; P.adj = adj; P.deg = deg;
-            P.mode = 0; P.node_base = inserted; P.list = nullptr; P.count_ptr = nullptr; P.count = batch; P.cand = res_nodes;
-            P.cand_stride = beam; P.mark = mark;
-            JV_TRY(launch_prune(P, batch < prune_grid ? batch : prune_grid, psmem, s));
-            // (3) back-links, then re-prune every neighbour that passed overflow * M
-            JV_TRY(cudaMemsetAsync(prune_count, 0, sizeof(int), s));
-            {
-                const int threads = batch * degree;
-                backlink_kernel<<<(threads + 255) / 256, 256, 0, s>>>(adj, deg, row_cap, degree, inserted, batch, hard_max, mark, prune_list, prune_count, dropped);
-                g_launches++;
-                clamp_deg_kernel<<<(n + 255) / 256, 256, 0, s>>>(deg, n, row_cap);
-                g_launches++;
-            }
-            P.mode = 1; P.list = prune_list; P.count_ptr = prune_count; P.count = 0;
-            JV_TRY(launch_prune(P, prune_grid, psmem, s));
-            inserted += batch;
-            st.batches++;
-        }
-        // cleanup(): enforceDegree on every list longer than M, then emit [n][degree]
-        JV_TRY(cudaMemsetAsync(prune_count, 0, sizeof(int), s));
-        collect_over_degree_kernel<<<(n + 255) / 256, 256, 0, s>>>(deg, n, degree, prune_list, prune_count);
-        g_launches++;
-        PruneParams P;
-        P.d = d; P.metric = metric; P.degree = degree; P.row_cap = row_cap; P.alpha = bp.alpha; P.adj = adj; P.deg = deg;
-        P.mode = 1; P.node_base = 0; P.list = prune_list; P.count_ptr = prune_count; P.count = 0; P.cand = nullptr; P.cand_stride = 0;
-        P.mark = mark;
-        JV_TRY(launch_prune(P, prune_grid, psmem, s));
-        const long long total = (long long)n * degree;
-        compact_adj_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(adj, deg, n, row_cap, degree, adj_out_dev);
-        g_launches++;
-        JV_TRY(cudaGetLastError());
-        SearchCounters hc;
-        unsigned long long hd = 0;
-        JV_TRY(cudaMemcpyAsync(&hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
-        JV_TRY(cudaMemcpyAsync(&hd, dropped, sizeof(hd), cudaMemcpyDeviceToHost, s));
-        JV_TRY(cudaStreamSynchronize(s));
-        st.searched = (long long)hc.visited;
-        st.dropped_backlinks = (long long)hd;
-        if (hc.overflowed) err = cudaErrorLaunchOutOfResources;
+    GraphBuilder *B = nullptr;
+    cudaError_t err = builder_create(d, metric, bp, sm_count, &B, s);
+    if (err != cudaSuccess) return err;
+    int first, count;
+    while (err == cudaSuccess && builder_next_batch(B, &first, &count)) {
+        err = builder_insert_slice(B, first, count, 0, count, nullptr, nullptr, s);
+        if (err == cudaSuccess) err = builder_apply_new(B, first, count, nullptr, nullptr, s);
+        if (err == cudaSuccess) err = builder_reprune_slice(B, 0, 0, nullptr, nullptr, s);
     }
-done:
-    if (stats) *stats = st;
-    cudaFree(adj); cudaFree(deg); cudaFree(mark); cudaFree(res_nodes); cudaFree(res_scores); cudaFree(prune_list);
-    cudaFree(prune_count); cudaFree(work_counter); cudaFree(dropped); cudaFree(counters); cudaFree(overflow); cudaFree(scratch);
+    if (err == cudaSuccess) err = builder_collect_over_degree(B, s);
+    if (err == cudaSuccess) err = builder_reprune_slice(B, 0, 0, nullptr, nullptr, s);
+    if (err == cudaSuccess) err = builder_finish(B, adj_out_dev, stats, s);
+    else if (stats) *stats = B->st;
+    builder_free(B);
     return err;
 }
 

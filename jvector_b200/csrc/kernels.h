@@ -112,6 +112,7 @@ struct BuildParams {
     int degree, beam;
     float overflow, alpha;
     int max_batch;
+    int window;  // in-progress peers every insert sees besides its beam (-1 = default: what fits the 128-candidate tile, at most 32)
 };
 struct BuildStats {
     long long searched, pruned, dropped_backlinks, batches;
@@ -119,5 +120,22 @@ struct BuildStats {
 // flat Vamana graph over rows [0, n) of an f32 data set; adj_out_dev [n][degree] (-1 padded); entry node is 0
 cudaError_t build_graph_flat(const DataDesc &f32, int metric, const BuildParams &bp, int32_t *adj_out_dev, int sm_count,
                              BuildStats *stats, cudaStream_t s);
+// the same build advanced batch by batch; a sharded build calls the *_slice functions for its part of each batch and moves the
+// rows between the replicas itself (see build.cu)
+struct GraphBuilder;
+cudaError_t builder_create(const DataDesc &d, int metric, const BuildParams &bp, int sm_count, GraphBuilder **out, cudaStream_t s);
+void builder_destroy(GraphBuilder *B);
+bool builder_next_batch(GraphBuilder *B, int *first, int *count);
+cudaError_t builder_insert_slice(GraphBuilder *B, int first, int count, int lo, int hi, int32_t *rows_out, int *deg_out, cudaStream_t s);
+cudaError_t builder_apply_new(GraphBuilder *B, int first, int count, const int32_t *rows, const int *rdeg, cudaStream_t s);
+cudaError_t builder_reprune_slice(GraphBuilder *B, int lo, int hi, int32_t *rows_out, int *deg_out, cudaStream_t s);
+cudaError_t builder_apply_repruned(GraphBuilder *B, int count, const int32_t *rows, const int *rdeg, cudaStream_t s);
+cudaError_t builder_collect_over_degree(GraphBuilder *B, cudaStream_t s);
+cudaError_t builder_list_count(GraphBuilder *B, int *count_host, cudaStream_t s);
+cudaError_t builder_finish(GraphBuilder *B, int32_t *adj_out_dev, BuildStats *stats, cudaStream_t s);
+int builder_row_cap(const GraphBuilder *B);
+int builder_degree(const GraphBuilder *B);
+int builder_max_batch(const GraphBuilder *B);
+cudaError_t launch_gather_rows(const DataDesc &f32, const int32_t *ids_dev, int count, float *out_dev, cudaStream_t s);
 
 }  // namespace jv

@@ -123,3 +123,78 @@ def gpu_sharded_bruteforce(dist, vectors, vsf, id_base):
     sb = ShardedBruteForce(dist, local_topk, merge)
     sb.status = lambda: int(status[1].item())
     return sb
+
+
+def sharded_build(dist, vectors, vsf, M=32, beamWidth=100, neighborOverflow=1.2, alpha=1.2, addHierarchy=True, seed=0, max_batch=0, concurrent_window=-1):
+    """GraphIndexBuilder.build with the insert scoring SHARDED over the ranks of `dist` (BASELINE config 5).
+
+    Every rank holds a replica of the rows (`vectors`, resident fp32) and of the adjacency. Per batch of inserted nodes: each rank
+    runs the beam searches + robust prunes of ITS slice (jv_builder_insert_slice), ONE all-gather moves the new rows, every rank
+    applies the whole batch (sorted back-links: the replicas stay bit-identical), then the rows that passed overflow * M are re-pruned
+    slice-wise and all-gathered the same way. NCCL calls and kernels share torch's current stream. dist = None: one rank (the
+    same code path, no collective). Returns (GraphIndex, device_ms, exchanged_bytes)."""
+    import ctypes as C
+
+    import torch
+
+    from . import _native as nat
+    from .api import GraphIndex
+    lib = nat.init()
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    params = nat.BuildParams(M, beamWidth, neighborOverflow, alpha, 1 if addHierarchy else 0, seed, max_batch, concurrent_window)
+    st = torch.cuda.current_stream().cuda_stream
+    b = C.c_void_p()
+    nat.check(lib.jv_builder_create(vectors._h, int(vsf), C.byref(params), C.c_void_p(st), C.byref(b)))
+    deg_, cap_, mb_ = C.c_int(), C.c_int(), C.c_int()
+    nat.check(lib.jv_builder_info(b, C.byref(deg_), C.byref(cap_), C.byref(mb_)))
+    degree, row_cap, mb = deg_.value, cap_.value, mb_.value
+    exchanged = [0]
+    bufs = {}
+
+    def buf(name, rows, width):
+        t = bufs.get(name)
+        if t is None or t.shape[0] < rows:
+            t = torch.empty((max(rows, 1) + max(rows, 1) // 4, width), dtype=torch.int32, device="cuda")
+            bufs[name] = t
+        return t
+
+    def exchange(count, width, produce):
+        """slice-wise produce(lo, hi, rows_ptr, deg_ptr) on this rank, all-gather, return (rows_all, deg_all) holding positions 0..count-1"""
+        chunk = (count + world - 1) // world
+        lo, hi = min(count, rank * chunk), min(count, (rank + 1) * chunk)
+        send, sdeg = buf("send%d" % width, chunk, width), buf("sdeg", chunk, 1)
+        # the C call writes batch positions lo..hi-1 of a [count][width] array: point it so that position lo is row 0 of the send buffer
+        nat.check(produce(lo, hi, C.c_void_p(send.data_ptr() - lo * width * 4), C.c_void_p(sdeg.data_ptr() - lo * 4)))
+        if world == 1:
+            return send, sdeg
+        allr, alld = buf("all%d" % width, world * chunk, width), buf("alld", world * chunk, 1)
+        dist.all_gather_into_tensor(allr[:world * chunk], send[:chunk])
+        dist.all_gather_into_tensor(alld[:world * chunk], sdeg[:chunk])
+        exchanged[0] += world * chunk * (width + 1) * 4
+        return allr, alld
+
+    def reprune_round(L):
+        if L <= 0:
+            return
+        rows, dg = exchange(L, row_cap, lambda lo, hi, rp, dp: lib.jv_builder_reprune_slice(b, lo, hi, rp, dp))
+        nat.check(lib.jv_builder_apply_repruned(b, L, C.c_void_p(rows.data_ptr()), C.c_void_p(dg.data_ptr())))
+
+    first, count, L = C.c_int32(), C.c_int32(), C.c_int32()
+    try:
+        while True:
+            nat.check(lib.jv_builder_next_batch(b, C.byref(first), C.byref(count)))
+            if count.value == 0:
+                break
+            f, c = first.value, count.value
+            rows, dg = exchange(c, degree, lambda lo, hi, rp, dp: lib.jv_builder_insert_slice(b, f, c, lo, hi, rp, dp))
+            nat.check(lib.jv_builder_apply_new(b, f, c, C.c_void_p(rows.data_ptr()), C.c_void_p(dg.data_ptr()), C.byref(L)))
+            reprune_round(L.value)
+        nat.check(lib.jv_builder_collect_over_degree(b, C.byref(L)))
+        reprune_round(L.value)
+        g = C.c_void_p()
+        ms = C.c_double()
+        nat.check(lib.jv_builder_finish(b, C.byref(g), C.byref(ms)))
+    finally:
+        lib.jv_builder_free(b)
+    return GraphIndex(_handle=g), ms.value, exchanged[0]

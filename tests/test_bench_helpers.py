@@ -10,14 +10,15 @@ sys.path.insert(0, ROOT)
 
 
 def test_gen_unit_rows_deterministic_and_unit_norm():
+    import torch
+
     import bench
-    a = bench.gen_unit_rows(123, 300, 64, "latent", chunk=128)
-    b = bench.gen_unit_rows(123, 300, 64, "latent", chunk=128)
+    gen = lambda seed, dist, chunk=128: bench.gen_unit_rows_device(torch, seed, 300, 64, dist, chunk=chunk, device="cpu").numpy()
+    a, b = gen(123, "latent"), gen(123, "latent")
     assert np.array_equal(a, b) and a.dtype == np.float32 and a.shape == (300, 64)
     np.testing.assert_allclose(np.linalg.norm(a, axis=1), 1.0, rtol=1e-5)
-    c = bench.gen_unit_rows(124, 300, 64, "latent", chunk=128)
-    assert not np.array_equal(a, c)
-    iid = bench.gen_unit_rows(123, 300, 64, "iid")
+    assert not np.array_equal(a, gen(124, "latent"))
+    iid = gen(123, "iid")
     # the latent model has neighbourhood structure: pairwise similarities spread far wider than for i.i.d. rows
     assert (a @ a.T)[np.triu_indices(300, 1)].std() > 1.4 * (iid @ iid.T)[np.triu_indices(300, 1)].std()
 
@@ -38,4 +39,4 @@ def test_measured_peaks_and_traffic_table():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         assert peak == float(json.load(open(p))["hbm_gbs"]) and src.startswith("measured")
-    assert bench.NCU_TRAFFIC[("c2", 1_000_000, 10_000, 100, "latent")] > 9e10
+    assert bench.NCU_TRAFFIC[("c2", 1_000_000, 10_000, 100)] > 9e10

@@ -703,6 +703,36 @@ def test_graph_build_recall_siftsmall(jv, sift):
     vec.close()
 
 
+def test_stepwise_builder_equals_one_call_build(jv):
+    # the build is deterministic (sorted back-links, exact traversal): the batch-by-batch driver a sharded build uses
+    # (jvector_b200/parallel.py sharded_build, here with one rank) must produce the adjacency of jv_graph_build, bit for bit
+    from jvector_b200 import parallel as par
+    rng = np.random.default_rng(88)
+    n, dim = 12000, 64
+    A = rng.standard_normal((10, dim)).astype(np.float32)
+    x = rng.standard_normal((n, 10)).astype(np.float32) @ A + 0.3 * rng.standard_normal((n, dim)).astype(np.float32)
+    data = np.ascontiguousarray(x / np.linalg.norm(x, axis=1, keepdims=True), dtype=np.float32)
+    vec = jv.F32Vectors(data)
+    kw = dict(M=16, beamWidth=60, neighborOverflow=1.2, alpha=1.2, addHierarchy=True, seed=5, max_batch=1024)
+    g1 = jv.GraphIndexBuilder(o.DOT_PRODUCT, **kw).build(vec)
+    g1b = jv.GraphIndexBuilder(o.DOT_PRODUCT, **kw).build(vec)
+    g2, ms, _ = par.sharded_build(None, vec, o.DOT_PRODUCT, **kw)
+    for lvl in range(g1.info()["levels"]):
+        i1, a1 = g1.level(lvl)
+        i1b, a1b = g1b.level(lvl)
+        i2, a2 = g2.level(lvl)
+        assert np.array_equal(a1, a1b), "the one-call build is not reproducible"
+        assert np.array_equal(i1, i2) and np.array_equal(a1, a2), (lvl, int((a1 != a2).any(axis=1).sum()))
+    # in-batch visibility: with the in-progress window some neighbours come from the same batch as the node
+    _, adj = g1.level(0)
+    g0 = jv.GraphIndexBuilder(o.DOT_PRODUCT, concurrent_window=0, **kw).build(vec)
+    _, adj0 = g0.level(0)
+    assert not np.array_equal(adj, adj0)
+    for g in (g1, g1b, g2, g0):
+        g.close()
+    vec.close()
+
+
 def test_errors(jv):
     rows = np.zeros((4, 8), np.float32)
     vec = jv.F32Vectors(rows)
