@@ -120,6 +120,13 @@ JV_API int jv_dataset_register_nvq(const uint8_t *bytes, const float *params, in
  * them alive until jv_dataset_free. 16-byte aligned, row_stride = dim rounded up to 4 floats, padding floats zero. */
 JV_API int jv_dataset_adopt_f32_device(const float *rows_device, int64_t n, int dim, int row_stride, jv_dataset *out);
 JV_API int jv_dataset_device(jv_dataset ds);
+/* ImmutablePQVectors' code-vs-code scoring (base:quantization/ImmutablePQVectors.java:63-105): build the triangular
+ * centroid-vs-centroid table of ProductQuantization.createCodebookPartialSums (ProductQuantization.java:609-628; 12.6 MB at M = 96,
+ * k = 256) in HBM; jv_score_pairs on this data set then sums table entries — assembleAndSumPQ, native-c:
+ * src/jvector_simd_kernels.cpp:729-815 — instead of recomputing centroid distances. EUCLIDEAN and DOT_PRODUCT have their own
+ * tables, COSINE uses the dot-product one. */
+JV_API int jv_dataset_pq_pair_table(jv_dataset pq, int metric);
+JV_API int jv_dataset_pq_pair_table_download(jv_dataset pq, int metric, float *table_out /* [M][k (k + 1) / 2] */);
 JV_API int jv_dataset_free(jv_dataset ds);
 JV_API int64_t jv_dataset_size(jv_dataset ds);
 JV_API int jv_dataset_dim(jv_dataset ds);
@@ -191,6 +198,9 @@ JV_API int jv_pq_encode_batch(const float *rows, int64_t n, int dim, int M, int 
                               const float *centroid, uint8_t *codes_out);
 JV_API int jv_nvq_encode_batch(const float *rows, int64_t n, int dim, int nsub, const float *mean, int learn,
                                float *params_out, uint8_t *bytes_out);
+/* the assignment step of k-means (KMeansPlusPlusClusterer.getNearestCluster, base:quantization/KMeansPlusPlusClusterer.java:329-342)
+ * for a batch of points [n][dim] against centroids [k][dim]: index of the nearest centroid, first minimum wins */
+JV_API int jv_kmeans_assign_batch(const float *points, int64_t n, int dim, const float *centroids, int k, int32_t *assignments_out);
 /* the same encoders over rows that are already resident in HBM (a registered fp32 data set): no host->device copy */
 JV_API int jv_bq_encode_dataset(jv_dataset f32, uint64_t *words_out);
 JV_API int jv_pq_encode_dataset(jv_dataset f32, int M, int k, const float *codebooks, const float *centroid, uint8_t *codes_out);

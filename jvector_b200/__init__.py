@@ -11,10 +11,10 @@ mirror of the reference's interface for that path, used by the tests and the ben
 """
 from . import api
 from .api import (BQVectors, F32Vectors, GraphIndex, GraphIndexBuilder, GraphSearcher, NVQVectors, PQVectors, QueryBatch, ScoreFunction,
-                  SearchResult, VectorSimilarityFunction, bq_encode_all, nvq_encode_all, nvq_encode_resident, pack_accept_bits, pq_encode_all,
+                  SearchResult, VectorSimilarityFunction, bq_encode_all, kmeans_assign, nvq_encode_all, nvq_encode_resident, pack_accept_bits, pq_encode_all,
                   score_multi, topk_bruteforce)
 from ._native import JVectorB200Error, init, load
 
 __all__ = ["VectorSimilarityFunction", "F32Vectors", "PQVectors", "BQVectors", "NVQVectors", "ScoreFunction", "GraphIndex",
            "GraphSearcher", "GraphIndexBuilder", "SearchResult", "score_multi", "topk_bruteforce", "bq_encode_all",
-           "pq_encode_all", "nvq_encode_all", "nvq_encode_resident", "QueryBatch", "pack_accept_bits", "JVectorB200Error", "init", "load"]
+           "pq_encode_all", "nvq_encode_all", "nvq_encode_resident", "QueryBatch", "kmeans_assign", "pack_accept_bits", "JVectorB200Error", "init", "load"]

@@ -84,6 +84,26 @@ class PQVectors(_Vectors):
         super().__init__(h, None)
 
 
+    def build_pair_table(self, vsf):
+        """ImmutablePQVectors: the triangular centroid-vs-centroid table in HBM; diversity_scores then sums table entries"""
+        check(nat.load().jv_dataset_pq_pair_table(self._h, int(vsf)))
+        return self
+
+    def pair_table(self, vsf):
+        out = np.empty(self.M * (self.k * (self.k + 1) // 2), dtype=np.float32)
+        check(nat.load().jv_dataset_pq_pair_table_download(self._h, int(vsf), fp(out)))
+        return out
+
+
+def kmeans_assign(points, centroids):
+    """KMeansPlusPlusClusterer.getNearestCluster for a batch of points (the Lloyd assignment step), one launch."""
+    lib = nat.init()
+    points, centroids = c32(points), c32(centroids)
+    out = np.empty(points.shape[0], dtype=np.int32)
+    check(lib.jv_kmeans_assign_batch(fp(points), points.shape[0], points.shape[1], fp(centroids), centroids.shape[0], ip(out)))
+    return out
+
+
 class BQVectors(_Vectors):
     """base:quantization/BQVectors.java — words [n][ceil(dim/64)] uint64."""
 

@@ -420,6 +420,51 @@ int jv_dataset_register_nvq(const uint8_t *bytes, const float *params, int64_t n
     return JV_OK;
 }
 
+static int check_metric(const DataDesc &d, int metric);
+
+int jv_dataset_pq_pair_table(jv_dataset pq, int metric)
+{
+    ON_DEVICE_OF(pq);
+    if (pq->d.kind != KIND_PQ) return fail(JV_ERR_INVALID, "pq_pair_table: not a PQ data set");
+    int rc = check_metric(pq->d, metric);
+    if (rc) return rc;
+    const int which = metric == JV_METRIC_EUCLIDEAN ? 0 : 1;  // cosine sums the dot-product table (ImmutablePQVectors.java:78-92)
+    if (pq->d.pair_table[which]) return JV_OK;
+    if ((rc = t_ctx.init())) return rc;
+    float *t = nullptr;
+    const size_t entries = (size_t)pq->d.M * ((size_t)pq->d.k * (pq->d.k + 1) / 2);
+    if ((rc = pq->alloc((void **)&t, entries * 4))) return rc;
+    CK(launch_pq_pair_table(pq->d, which == 0, t, t_ctx.stream), "pq_pair_table");
+    CK(cudaStreamSynchronize(t_ctx.stream), "pq_pair_table");
+    pq->d.pair_table[which] = t;
+    return JV_OK;
+}
+
+int jv_dataset_pq_pair_table_download(jv_dataset pq, int metric, float *table_out)
+{
+    ON_DEVICE_OF(pq);
+    const int which = metric == JV_METRIC_EUCLIDEAN ? 0 : 1;
+    if (pq->d.kind != KIND_PQ || !pq->d.pair_table[which] || !table_out) return fail(JV_ERR_INVALID, "pq_pair_table_download: no table for this metric");
+    const size_t entries = (size_t)pq->d.M * ((size_t)pq->d.k * (pq->d.k + 1) / 2);
+    CK(cudaMemcpy(table_out, pq->d.pair_table[which], entries * 4, cudaMemcpyDeviceToHost), "D2H pair table");
+    return JV_OK;
+}
+
+int jv_kmeans_assign_batch(const float *points, int64_t n, int dim, const float *centroids, int k, int32_t *assignments_out)
+{
+    NEED_INIT();
+    if (!points || !centroids || !assignments_out || n <= 0 || dim <= 0 || k <= 0) return fail(JV_ERR_INVALID, "kmeans_assign: bad arguments");
+    int rc;
+    if ((rc = t_ctx.init()) || (rc = t_ctx.ensure(0, (size_t)n * dim * 4)) || (rc = t_ctx.ensure(1, (size_t)n * 4)) || (rc = t_ctx.ensure(2, (size_t)k * dim * 4))) return rc;
+    cudaStream_t s = t_ctx.stream;
+    CK(cudaMemcpyAsync(t_ctx.dbuf[0], points, (size_t)n * dim * 4, cudaMemcpyHostToDevice, s), "H2D points");
+    CK(cudaMemcpyAsync(t_ctx.dbuf[2], centroids, (size_t)k * dim * 4, cudaMemcpyHostToDevice, s), "H2D centroids");
+    CK(launch_kmeans_assign((const float *)t_ctx.dbuf[0], n, dim, dim, (const float *)t_ctx.dbuf[2], k, (int32_t *)t_ctx.dbuf[1], s), "kmeans_assign");
+    CK(cudaMemcpyAsync(assignments_out, t_ctx.dbuf[1], (size_t)n * 4, cudaMemcpyDeviceToHost, s), "D2H assignments");
+    CK(cudaStreamSynchronize(s), "sync");
+    return JV_OK;
+}
+
 int jv_dataset_adopt_f32_device(const float *rows_device, int64_t n, int dim, int row_stride, jv_dataset *out)
 {
     NEED_INIT();

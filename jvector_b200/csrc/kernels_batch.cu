@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) score_pairs_kernel(DataDesc d, const int3
     const int x = a[warp], y = b[warp];
     float sc;
     if (KIND == KIND_F32) sc = pair_f32<METRIC>(d, x, y, lane);
-    else if (KIND == KIND_PQ) sc = pair_pq<METRIC>(d, x, y, lane);
+    else if (KIND == KIND_PQ) sc = d.pair_table[METRIC == JV_METRIC_EUCLIDEAN ? 0 : 1] ? pair_pq_table<METRIC>(d, x, y, lane) : pair_pq<METRIC>(d, x, y, lane);
     else sc = pair_bq(d, x, y, lane);
     if (lane == 0) out[warp] = sc;
 }
@@ -717,6 +717,80 @@ cudaError_t launch_pq_encode(const DataDesc &pq, const float *rows_dev, long lon
     const long long blocks = (warps * 32 + 255) / 256;
     if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
     pq_encode_kernel<<<(unsigned)blocks, 256, 0, s>>>(pq, rows_dev, n, row_stride, codes_dev);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// ProductQuantization.createCodebookPartialSums (ProductQuantization.java:609-628): for every sub-space the upper triangle
+// (i <= j) of centroid-vs-centroid dot products or squared L2 distances, rows in order. One thread per entry.
+__global__ void __launch_bounds__(256) pq_pair_table_kernel(DataDesc pq, int euclidean, float *__restrict__ table)
+{
+    const int block = pq.k * (pq.k + 1) / 2;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)pq.M * block) return;
+    const int m = (int)(e / block), t = (int)(e - (long long)m * block);
+    // invert t = i k - i (i - 1) / 2 + (j - i): i = the largest row whose first entry is <= t
+    int i = (int)((2.0 * pq.k + 1.0 - sqrt((2.0 * pq.k + 1.0) * (2.0 * pq.k + 1.0) - 8.0 * t)) / 2.0);
+    while (i > 0 && i * pq.k - i * (i - 1) / 2 > t) i--;
+    while ((i + 1) * pq.k - (i + 1) * i / 2 <= t) i++;
+    const int j = i + (t - (i * pq.k - i * (i - 1) / 2));
+    const int sz = pq.sub_sizes[m];
+    const float *cb = pq.codebooks + (size_t)pq.k * pq.sub_offsets[m];
+    const float *x = cb + (size_t)i * sz, *y = cb + (size_t)j * sz;
+    float s = 0.f;
+    for (int c = 0; c < sz; c++) {
+        if (euclidean) {
+            const float df = __fsub_rn(x[c], y[c]);
+            s = fmaf(df, df, s);
+        } else s = fmaf(x[c], y[c], s);
+    }
+    table[e] = s;
+}
+
+cudaError_t launch_pq_pair_table(const DataDesc &pq, int euclidean, float *table_dev, cudaStream_t s)
+{
+    const long long total = (long long)pq.M * (pq.k * (pq.k + 1) / 2);
+    pq_pair_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pq, euclidean, table_dev);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// KMeansPlusPlusClusterer.getNearestCluster (base:quantization/KMeansPlusPlusClusterer.java:329-342) for a batch of points: the
+// assignment step of Lloyd's iterations (and, per sub-space, what ProductQuantization.encode does). One warp per point, lanes
+// stride over the centroids, first minimum wins.
+__global__ void __launch_bounds__(256) kmeans_assign_kernel(const float *__restrict__ points, long long n, int dim, int point_stride,
+                                                            const float *__restrict__ centroids, int k, int32_t *__restrict__ assign)
+{
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const float *v = points + warp * point_stride;
+    float best = 3.402823466e+38f;  // Float.MAX_VALUE
+    int bi = 0x7fffffff;
+    for (int c = lane; c < k; c += 32) {
+        const float *cen = centroids + (size_t)c * dim;
+        float s = 0.f;
+        for (int j = 0; j < dim; j++) {
+            const float df = __fsub_rn(v[j], cen[j]);
+            s = __fadd_rn(s, __fmul_rn(df, df));
+        }
+        if (s < best) { best = s; bi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) assign[warp] = bi == 0x7fffffff ? 0 : bi;
+}
+
+cudaError_t launch_kmeans_assign(const float *points_dev, long long n, int dim, int point_stride, const float *centroids_dev, int k, int32_t *assign_dev, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    const long long blocks = (n * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    kmeans_assign_kernel<<<(unsigned)blocks, 256, 0, s>>>(points_dev, n, dim, point_stride, centroids_dev, k, assign_dev);
     g_launches++;
     return cudaGetLastError();
 }

@@ -30,6 +30,9 @@ struct DataDesc {
     const int *sub_offsets;  // [M] (pq) or [nsub] (nvq)
     const float *centroid;   // pq global centroid or nullptr
     const float *mag;        // pq ||centroid||^2 table [M*k] (cosine)
+    // pq centroid-vs-centroid tables of ProductQuantization.createCodebookPartialSums (ProductQuantization.java:609-628):
+    // [M][k (k + 1) / 2] upper triangles, [0] squared L2, [1] dot product; nullptr until jv_dataset_pq_pair_table builds one
+    const float *pair_table[2];
     // bq: words [n][W] u64
     const unsigned long long *words;
     int W;
@@ -472,6 +475,40 @@ __device__ __forceinline__ float pair_pq(const DataDesc &d, int a, int b, int la
             }
         }
         s = __fadd_rn(s, t); n1 = __fadd_rn(n1, tx); n2 = __fadd_rn(n2, ty);
+    }
+    s = group_sum<32>(s);
+    if (METRIC == JV_METRIC_COSINE) {
+        n1 = group_sum<32>(n1);
+        n2 = group_sum<32>(n2);
+        s = __fdiv_rn(s, __fsqrt_rn(__fmul_rn(n1, n2)));
+    }
+    return score_map(METRIC, s);
+}
+
+// assembleAndSumPQ (base:vector/DefaultVectorUtilSupport.java:321-336, native-c:src/jvector_simd_kernels.cpp:729-815) composed as
+// ImmutablePQVectors.diversityFunctionFor does (base:quantization/ImmutablePQVectors.java:63-105): per sub-space one gather from the
+// triangular centroid-vs-centroid table at (min(c1, c2), max(c1, c2)); cosine needs the two self sums as well.
+__device__ __forceinline__ int tri_index(int a, int b, int k)
+{
+    const int r = min(a, b), c = max(a, b);
+    return r * k - (r * (r - 1) / 2) + (c - r);
+}
+
+template <int METRIC>
+__device__ __forceinline__ float pair_pq_table(const DataDesc &d, int a, int b, int lane)
+{
+    const uint8_t *ca = d.codes + (size_t)a * d.code_stride, *cb = d.codes + (size_t)b * d.code_stride;
+    const float *T = d.pair_table[METRIC == JV_METRIC_EUCLIDEAN ? 0 : 1];
+    const int k = d.k, block = k * (k + 1) / 2;
+    float s = 0.f, n1 = 0.f, n2 = 0.f;
+    for (int m = lane; m < d.M; m += 32) {
+        const float *Tm = T + (size_t)m * block;
+        const int x = ca[m], y = cb[m];
+        s = __fadd_rn(s, __ldg(Tm + tri_index(x, y, k)));
+        if (METRIC == JV_METRIC_COSINE) {
+            n1 = __fadd_rn(n1, __ldg(Tm + tri_index(x, x, k)));
+            n2 = __fadd_rn(n2, __ldg(Tm + tri_index(y, y, k)));
+        }
     }
     s = group_sum<32>(s);
     if (METRIC == JV_METRIC_COSINE) {

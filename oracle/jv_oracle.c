@@ -267,6 +267,32 @@ float jvo_pq_pair_sum(const float *table, int M, int k, const uint8_t *c1, const
     return res;
 }
 
+/* ImmutablePQVectors.diversityFunctionFor (base:quantization/ImmutablePQVectors.java:63-105): code-vs-code score from the
+ * triangular table (assembleAndSumPQ); `table` is the squared-L2 table for EUCLIDEAN, the dot-product table otherwise */
+float jvo_pq_diversity_table(int metric, const float *table, int M, int k, const uint8_t *c1, const uint8_t *c2)
+{
+    float sum = jvo_pq_pair_sum(table, M, k, c1, c2);
+    if (metric == JVO_EUCLIDEAN) return 1.f / (1.f + sum);
+    if (metric == JVO_DOT_PRODUCT) return (1.f + sum) / 2.f;
+    float n1 = jvo_pq_pair_sum(table, M, k, c1, c1), n2 = jvo_pq_pair_sum(table, M, k, c2, c2);
+    float cosine = sum / (float)sqrt((double)(n1 * n2));
+    return (1.f + cosine) / 2.f;
+}
+
+/* KMeansPlusPlusClusterer.getNearestCluster (base:quantization/KMeansPlusPlusClusterer.java:329-342) for a batch of points */
+void jvo_kmeans_assign(const float *points, int64_t n, int dim, const float *centroids, int k, int32_t *assign)
+{
+    for (int64_t p = 0; p < n; p++) {
+        float minDistance = 3.402823466e+38f;
+        int nearest = 0;
+        for (int i = 0; i < k; i++) {
+            float d = jvo_l2_f32(points + (size_t)p * dim, centroids + (size_t)i * dim, dim);
+            if (d < minDistance) { minDistance = d; nearest = i; }
+        }
+        assign[p] = nearest;
+    }
+}
+
 /* ============================================================================================
  * BQ — base:quantization/BinaryQuantization.java:88-110, base:vector/DefaultVectorUtilSupport.java:342-348,
  * base:quantization/BQVectors.java:116-118

@@ -77,6 +77,8 @@ void jvo_nvq_cosine_8bit(const float *q, const uint8_t *b, int n, float alpha, f
 void jvo_nvq_encode_subvector(const float *v, int n, int learn, float *params_out, uint8_t *bytes_out);
 /* encode a whole vector: subtract mean, split into nsub sub-vectors (layout as jvo_pq_layout) */
 void jvo_nvq_encode(const float *v, const float *mean, int dim, int nsub, int learn, float *params_out, uint8_t *bytes_out);
+float jvo_pq_diversity_table(int metric, const float *table, int M, int k, const uint8_t *c1, const uint8_t *c2);
+void jvo_kmeans_assign(const float *points, int64_t n, int dim, const float *centroids, int k, int32_t *assign);
 /* the same sums and parameter search under an explicit summation order (see jv_oracle.c): lanes = 1 sequential,
  * lanes = 32 strided accumulators + xor butterfly (a GPU warp's order) */
 float jvo_nvq_loss_lanes(const float *v, int n, float alpha, float x0, float minv, float maxv, int nbits, int lanes);

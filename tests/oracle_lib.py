@@ -101,6 +101,8 @@ def load():
     sig("jvo_pq_diversity_direct", F, f32p, i32p, i32p, I, I, I, u8p, u8p)
     sig("jvo_pq_pair_table", None, f32p, i32p, i32p, I, I, I, f32p)
     sig("jvo_pq_pair_sum", F, f32p, I, I, u8p, u8p)
+    sig("jvo_pq_diversity_table", F, I, f32p, I, I, u8p, u8p)
+    sig("jvo_kmeans_assign", None, f32p, C.c_int64, I, f32p, I, i32p)
     sig("jvo_bq_encode", None, f32p, I, u64p)
     sig("jvo_hamming", I, u64p, u64p, I)
     sig("jvo_bq_score", F, u64p, u64p, I, I)

@@ -150,6 +150,45 @@ def test_pq_encode_exact(jv, oracle):
         assert np.array_equal(got, codes)  # code bytes: bit-exact
 
 
+@pytest.mark.parametrize("dim,M", [(64, 8), (100, 7), (768, 96)])
+def test_pq_pair_table_and_assemble_and_sum_pq(jv, oracle, dim, M):
+    # a-9: ProductQuantization.createCodebookPartialSums (triangular table, ProductQuantization.java:609-628) built on the device and
+    # ImmutablePQVectors' code-vs-code scores summed from it (assembleAndSumPQ, ImmutablePQVectors.java:63-105)
+    rng = np.random.default_rng(dim)
+    n, k = 400, 256
+    data, cb, sizes, offsets, cen, codes, _ = _pq(rng, oracle, n, dim, M, False)
+    pqv = jv.PQVectors(codes, cb, dim, k)
+    a = rng.integers(0, n, 300).astype(np.int32)
+    b = rng.integers(0, n, 300).astype(np.int32)
+    b[:10] = a[:10]
+    for metric in METRICS:
+        tm = o.EUCLIDEAN if metric == o.EUCLIDEAN else o.DOT_PRODUCT
+        want_t = np.empty(M * (k * (k + 1) // 2), np.float32)
+        oracle.jvo_pq_pair_table(fp(cb), ip(sizes), ip(offsets), M, k, tm, fp(want_t))
+        pqv.build_pair_table(metric)
+        got_t = pqv.pair_table(metric)
+        np.testing.assert_allclose(got_t, want_t, rtol=1e-5, atol=1e-6)
+        got = pqv.diversity_scores(a, b, metric)
+        want = np.array([oracle.jvo_pq_diversity_table(metric, fp(want_t), M, k, bp(codes[x]), bp(codes[y])) for x, y in zip(a, b)], np.float32)
+        close(got, want, scale=1e-2)
+    pqv.close()
+
+
+def test_kmeans_assignment_step(jv, oracle):
+    # f-4: KMeansPlusPlusClusterer.getNearestCluster for a batch of points; first minimum wins, so duplicated centroids tie to the lower index
+    rng = np.random.default_rng(4)
+    for dim, k, n in ((8, 256, 5000), (3, 17, 1000), (96, 40, 700)):
+        pts = rng.standard_normal((n, dim)).astype(np.float32)
+        cen = rng.standard_normal((k, dim)).astype(np.float32)
+        cen[k - 1] = cen[2]
+        pts[:5] = cen[2]
+        want = np.empty(n, np.int32)
+        oracle.jvo_kmeans_assign(fp(pts), n, dim, fp(cen), k, ip(want))
+        got = jv.kmeans_assign(pts, cen)
+        assert np.array_equal(got, want), np.flatnonzero(got != want)[:5]
+        assert (got[:5] == 2).all()
+
+
 # ------------------------------------------------------------------------------------------------ BQ
 @pytest.mark.parametrize("dim", [1, 63, 64, 65, 128, 1000, 1536])
 def test_bq_exact(jv, oracle, dim):
