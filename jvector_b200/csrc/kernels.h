@@ -91,7 +91,9 @@ struct SearchPlan {
     int list_alloc;   // entries per list buffer (>= list_cap, >= sort_pow2)
     int sort_pow2;    // next power of two >= rerankK
     int visited_cap;  // power of two
-    int blob_in_global;  // PQ LUT kept in an L2-resident global slice per CTA instead of shared memory
+    int blob_in_global;  // PQ: (part of) the LUT lives in an L2-resident global slice per CTA
+    int pq_smem_m;       // PQ: LUT rows of sub-spaces [0, pq_smem_m) stay in shared memory
+    int pq_wide;         // PQ: the 64-register build of the kernel (residency is limited by shared memory anyway)
     int blob_floats;
 };
 // acceptOrds / threshold / rerankFloor of GraphSearcher.search (base:graph/GraphSearcher.java:166-181,427-431, NodeQueue.java:168-230)

@@ -81,8 +81,11 @@ __device__ __forceinline__ float block_sum(float v, float *red)
 // ------------------------------------------------------------------------------------------------
 // prepare_blob: whole CTA. q: raw query [dim] in global memory. blob: global or shared, blob_floats() long.
 // ------------------------------------------------------------------------------------------------
-__device__ inline void prepare_blob(const DataDesc &d, int metric, const float *__restrict__ q, float *blob, float *red)
+// PQ only: sub-spaces m < split_m write their k entries through `blob` (shared memory in the search kernel), the others and the
+// trailing <q', q'> through `blob_hi` (a per-CTA global slice that stays in L2); both are indexed m * k + c. Default: one array.
+__device__ inline void prepare_blob(const DataDesc &d, int metric, const float *__restrict__ q, float *blob, float *red, float *blob_hi = nullptr, int split_m = 1 << 30)
 {
+    if (!blob_hi) blob_hi = blob;
     const int tid = threadIdx.x, nt = blockDim.x;
     if (d.kind == KIND_F32) {
         float acc = 0.f;
@@ -124,7 +127,7 @@ __device__ inline void prepare_blob(const DataDesc &d, int metric, const float *
                             s = fmaf(df, df, s);
                         } else s = fmaf(cen[j], qv[j], s);
                     }
-                    blob[m * d.k + c] = s;
+                    (m < split_m ? blob : blob_hi)[m * d.k + c] = s;
                 }
             } else {
                 for (int c = lane; c < d.k; c += 32) {
@@ -138,7 +141,7 @@ __device__ inline void prepare_blob(const DataDesc &d, int metric, const float *
                             s = fmaf(df, df, s);
                         } else s = fmaf(cen[j], qq, s);
                     }
-                    blob[m * d.k + c] = s;
+                    (m < split_m ? blob : blob_hi)[m * d.k + c] = s;
                 }
             }
         }
@@ -149,7 +152,7 @@ __device__ inline void prepare_blob(const DataDesc &d, int metric, const float *
             acc = fmaf(qq, qq, acc);
         }
         float bm = block_sum(acc, red);
-        if (tid == 0) blob[total] = bm;
+        if (tid == 0) blob_hi[total] = bm;
     } else if (d.kind == KIND_BQ) {
         // BinaryQuantization.java:96-109: bit j of word i = (v[64 i + j] > 0)
         unsigned long long *w = reinterpret_cast<unsigned long long *>(blob);
@@ -259,8 +262,11 @@ __device__ __forceinline__ void score_f32_pair(const DataDesc &d, const float *b
 // (DefaultVectorUtilSupport.java:303-309; native-c:...:662-724,821-879). 8 lanes per code row, 4 codes per 32-bit load.
 // ------------------------------------------------------------------------------------------------
 template <int METRIC>
-__device__ __forceinline__ float score_pq_codes(const DataDesc &d, const float *lut, const uint8_t *__restrict__ c, int g)
+__device__ __forceinline__ float score_pq_codes(const DataDesc &d, const float *lut_lo, const uint8_t *__restrict__ c, int g, const float *lut_hi = nullptr,
+                                                int split_m = 1 << 30)
 {
+    // sub-spaces m < split_m (a multiple of 4) are looked up in lut_lo, the rest (and the cosine query norm) in lut_hi
+    if (!lut_hi) lut_hi = lut_lo;
     const int k = d.k, M = d.M;
     float s = 0.f, a = 0.f;
     const int M4 = M >> 2;
@@ -268,6 +274,7 @@ __device__ __forceinline__ float score_pq_codes(const DataDesc &d, const float *
     for (int j = g; j < M4; j += 8) {
         const uint32_t w = __ldg(c4 + j);
         const int base = (4 * j) * k;
+        const float *lut = 4 * j < split_m ? lut_lo : lut_hi;
         const int i0 = base + (int)(w & 255u), i1 = base + k + (int)((w >> 8) & 255u), i2 = base + 2 * k + (int)((w >> 16) & 255u),
                   i3 = base + 3 * k + (int)(w >> 24);
         s = __fadd_rn(s, lut[i0]); s = __fadd_rn(s, lut[i1]); s = __fadd_rn(s, lut[i2]); s = __fadd_rn(s, lut[i3]);
@@ -278,21 +285,21 @@ __device__ __forceinline__ float score_pq_codes(const DataDesc &d, const float *
     }
     for (int m = 4 * M4 + g; m < M; m += 8) {
         const int idx = m * k + (int)c[m];
-        s = __fadd_rn(s, lut[idx]);
+        s = __fadd_rn(s, (m < split_m ? lut_lo : lut_hi)[idx]);
         if (METRIC == JV_METRIC_COSINE) a = __fadd_rn(a, __ldg(d.mag + idx));
     }
     s = group_sum<8>(s);
     if (METRIC == JV_METRIC_COSINE) {
         a = group_sum<8>(a);
-        s = __fdiv_rn(s, __fsqrt_rn(__fmul_rn(a, lut[M * k])));  // native-c:...:879
+        s = __fdiv_rn(s, __fsqrt_rn(__fmul_rn(a, lut_hi[M * k])));  // native-c:...:879
     }
     return score_map(METRIC, s);
 }
 
 template <int METRIC>
-__device__ __forceinline__ float score_pq(const DataDesc &d, const float *lut, int node, int g)
+__device__ __forceinline__ float score_pq(const DataDesc &d, const float *lut, int node, int g, const float *lut_hi = nullptr, int split_m = 1 << 30)
 {
-    return score_pq_codes<METRIC>(d, lut, d.codes + (size_t)node * d.code_stride, g);
+    return score_pq_codes<METRIC>(d, lut, d.codes + (size_t)node * d.code_stride, g, lut_hi, split_m);
 }
 
 // ------------------------------------------------------------------------------------------------

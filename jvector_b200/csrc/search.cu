@@ -19,6 +19,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace jv {
@@ -44,8 +46,9 @@ struct SearchParams {
     SearchCounters *counters;
     uint8_t *overflow;
     const int32_t *query_index;
-    int blobA_floats, blobR_floats;
-    float *blob_global;  // PQ "LUT in L2" mode: per-CTA slices of global scratch hold the prepared query instead of shared memory
+    int blobA_floats, blobR_floats, smemA_floats;  // smemA_floats: what the walking scorer's prepared query takes of shared memory
+    float *blob_global;  // PQ: per-CTA slices of global scratch (L2 resident) hold the LUT rows of the sub-spaces >= pq_smem_m
+    int pq_smem_m;       // PQ: sub-spaces [0, pq_smem_m) keep their LUT rows in shared memory (multiple of 4; M = all, 0 = none)
     // acceptOrds / threshold / rerankFloor of GraphSearcher.search(sp, topK, rerankK, threshold, rerankFloor, acceptOrds)
     const uint32_t *accept_bits;  // bit (node & 31) of word (node >> 5); nullptr = Bits.ALL
     long long accept_stride;      // words between two queries' bitsets (0 = one bitset shared by the batch)
@@ -162,14 +165,20 @@ constexpr uint8_t F_ACCEPTED = 2;  // acceptOrds.get(node) && score >= threshold
 //   is re-run by the host with a larger list (overflow code 2), never answered approximately;
 //   upper levels: a node refused by addTopCandidate is neither a result nor evicted, so it is removed from the list at once
 //   (setEntryPointsFromPreviousLayer re-queues results + evicted only, GraphSearcher.java:316-323).
-template <int KIND, int METRIC>
-__global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_MINB_PQ : JV_SEARCH_MINB)) graph_search_kernel(SearchParams P)
+// MINB: resident CTAs per SM the register allocation is capped for. PQ is compiled twice: 6 (40 registers; the L2-LUT mode, where
+// nothing else limits residency) and 4 (64 registers; the modes whose shared-memory LUT part allows at most 4-5 CTAs anyway).
+template <int KIND, int METRIC, int MINB>
+__global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(SearchParams P)
 {
     constexpr int G = GroupOf<KIND>::value;
     constexpr int NG = SEARCH_THREADS / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *blobA = P.blob_global ? P.blob_global + (size_t)blockIdx.x * P.blobA_floats : reinterpret_cast<float *>(smem_raw);
-    float *blobR = reinterpret_cast<float *>(smem_raw) + (P.blob_global ? 0 : P.blobA_floats);
+    // prepared query of the walking scorer. PQ: the LUT may be split, rows of sub-spaces < pq_smem_m in shared memory (blobA), the
+    // others in this CTA's global slice (blobH); every other kind: all of it in shared memory
+    float *blobA = reinterpret_cast<float *>(smem_raw);
+    float *blobH = P.blob_global ? P.blob_global + (size_t)blockIdx.x * P.blobA_floats : blobA;
+    const int splitm = (KIND == KIND_PQ && P.blob_global) ? P.pq_smem_m : (1 << 30);
+    float *blobR = reinterpret_cast<float *>(smem_raw) + P.smemA_floats;
     long long *keys0 = reinterpret_cast<long long *>(blobR + P.blobR_floats);
     long long *keys1 = keys0 + P.list_alloc;
     long long *cand_keys = keys1 + P.list_alloc;
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
         unsigned long long dbg_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
         JV_T(t_q0);
-        prepare_blob(P.approx, P.metric, q, blobA, red);
+        prepare_blob(P.approx, P.metric, q, blobA, red, blobH, splitm);
         if (P.has_rerank) prepare_blob(P.rerank, P.metric, q, blobR, red);
         {
             int4 *t4 = reinterpret_cast<int4 *>(table);
@@ -217,7 +226,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
         uint8_t *fcur = flags0, *fnxt = flags1;
         // initializeInternal: score the entry node, mark it visited (GraphSearcher.java:346-348)
         if (group == 0) {
-            const float sc = score_row<KIND, METRIC>(P.approx, blobA, P.g.entry_node, lane);
+            const float sc = KIND == KIND_PQ ? score_pq<METRIC>(P.approx, blobA, P.g.entry_node, lane, blobH, splitm) : score_row<KIND, METRIC>(P.approx, blobA, P.g.entry_node, lane);
             if (lane == 0) {
                 const int32_t en = P.g.entry_node;
                 cur[0] = topk_key(sc, en);
@@ -345,7 +354,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
                     const uint8_t *codes0 = rec + 4 * degree;
                     for (int i = group; i < n; i += NG) {
                         const int32_t f = cand_ids[i];
-                        const float sc = score_pq_codes<METRIC>(P.approx, blobA, codes0 + (size_t)cand_slot[i] * P.g.fused_code_stride, lane);
+                        const float sc = score_pq_codes<METRIC>(P.approx, blobA, codes0 + (size_t)cand_slot[i] * P.g.fused_code_stride, lane, blobH, splitm);
                         if (lane == 0) {
                             cand_keys[i] = topk_key(sc, f);
                             if (P.filtered) cand_acc[i] = ((!acc || ((acc[f >> 5] >> (f & 31)) & 1u)) && sc >= P.threshold) ? F_ACCEPTED : 0;
@@ -354,7 +363,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, (KIND == KIND_PQ ? JV_SEARCH_M
                 } else {
                     for (int i = group; i < n; i += NG) {
                         const int32_t f = cand_ids[i];
-                        const float sc = score_row<KIND, METRIC>(P.approx, blobA, f, lane);
+                        const float sc = KIND == KIND_PQ ? score_pq<METRIC>(P.approx, blobA, f, lane, blobH, splitm) : score_row<KIND, METRIC>(P.approx, blobA, f, lane);
                         if (lane == 0) {
                             cand_keys[i] = topk_key(sc, f);
                             if (P.filtered) cand_acc[i] = ((!acc || ((acc[f >> 5] >> (f & 31)) & 1u)) && sc >= P.threshold) ? F_ACCEPTED : 0;
@@ -583,10 +592,17 @@ static int next_pow2i(int v)
     return p;
 }
 
-static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, int rerankK, int list_alloc, bool blob_in_global)
+// shared-memory floats of the walking scorer's prepared query: everything, except for a PQ LUT of which only the rows of the
+// first pq_smem_m sub-spaces stay in shared memory
+static int search_smemA_floats(const DataDesc &approx, int pq_smem_m)
 {
-    size_t b = 0;
-    if (!blob_in_global) b += (size_t)blob_floats(approx) * 4;
+    if (approx.kind != KIND_PQ || pq_smem_m >= approx.M) return blob_floats(approx);
+    return (pq_smem_m * approx.k + 3) & ~3;
+}
+
+static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, int rerankK, int list_alloc, int pq_smem_m)
+{
+    size_t b = (size_t)search_smemA_floats(approx, pq_smem_m) * 4;
     if (rerank) b += (size_t)blob_floats(*rerank) * 4;
     b += (size_t)list_alloc * 8 * 2;                  // the two list buffers
     b += (size_t)MAX_DEGREE * 8;                      // candidate keys of one hop
@@ -596,32 +612,38 @@ static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, 
     return (b + 15) & ~(size_t)15;
 }
 
-template <int KIND, int METRIC>
+constexpr int MINB_DEFAULT = JV_SEARCH_MINB, MINB_PQ_LITE = JV_SEARCH_MINB_PQ, MINB_PQ_WIDE = 4;
+
+template <int KIND, int METRIC, int MINB>
 static cudaError_t occupancy_of(size_t smem, int *blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(graph_search_kernel<KIND, METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(graph_search_kernel<KIND, METRIC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, graph_search_kernel<KIND, METRIC>, SEARCH_THREADS, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, graph_search_kernel<KIND, METRIC, MINB>, SEARCH_THREADS, smem);
 }
 
-#define JV_SEARCH_DISPATCH(kind, metric, CALL)                                                  \
+#define JV_SEARCH_DISPATCH(kind, metric, pq_wide, CALL)                                                  \
     do {                                                                                        \
         if ((kind) == KIND_F32) {                                                               \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN); }       \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT); }              \
-            else { CALL(KIND_F32, JV_METRIC_COSINE); }                                          \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN, MINB_DEFAULT); }       \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT, MINB_DEFAULT); }              \
+            else { CALL(KIND_F32, JV_METRIC_COSINE, MINB_DEFAULT); }                                          \
+        } else if ((kind) == KIND_PQ && (pq_wide)) {                                            \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_PQ, JV_METRIC_EUCLIDEAN, MINB_PQ_WIDE); } \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_PQ, JV_METRIC_DOT, MINB_PQ_WIDE); } \
+            else { CALL(KIND_PQ, JV_METRIC_COSINE, MINB_PQ_WIDE); }                             \
         } else if ((kind) == KIND_PQ) {                                                         \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_PQ, JV_METRIC_EUCLIDEAN); }        \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_PQ, JV_METRIC_DOT); }               \
-            else { CALL(KIND_PQ, JV_METRIC_COSINE); }                                           \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_PQ, JV_METRIC_EUCLIDEAN, MINB_PQ_LITE); } \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_PQ, JV_METRIC_DOT, MINB_PQ_LITE); } \
+            else { CALL(KIND_PQ, JV_METRIC_COSINE, MINB_PQ_LITE); }                             \
         } else if ((kind) == KIND_BQ) {                                                         \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_BQ, JV_METRIC_EUCLIDEAN); }        \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_BQ, JV_METRIC_DOT); }               \
-            else { CALL(KIND_BQ, JV_METRIC_COSINE); }                                           \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_BQ, JV_METRIC_EUCLIDEAN, MINB_DEFAULT); }        \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_BQ, JV_METRIC_DOT, MINB_DEFAULT); }               \
+            else { CALL(KIND_BQ, JV_METRIC_COSINE, MINB_DEFAULT); }                                           \
         } else {                                                                                \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_NVQ, JV_METRIC_EUCLIDEAN); }       \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_NVQ, JV_METRIC_DOT); }              \
-            else { CALL(KIND_NVQ, JV_METRIC_COSINE); }                                          \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_NVQ, JV_METRIC_EUCLIDEAN, MINB_DEFAULT); }       \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_NVQ, JV_METRIC_DOT, MINB_DEFAULT); }              \
+            else { CALL(KIND_NVQ, JV_METRIC_COSINE, MINB_DEFAULT); }                                          \
         }                                                                                       \
     } while (0)
 
@@ -645,18 +667,25 @@ cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const Gr
     // (profiles/r1_search_phase_cycles.md). When five LUTs do not fit an SM's shared memory the LUT lives in an L2-resident
     // global slice per CTA instead: residency becomes register-limited (5 CTAs per SM) and the gathers are served by L2.
     // Measured on c3: 19.25 ms -> 13.1 ms per 10 000 queries. JV_PQ_LUT=smem|l2 overrides.
+    // Round 2: the LUT may be SPLIT — rows of the first pq_smem_m sub-spaces in shared memory, the rest in the L2 slice — which
+    // trades L2 gather traffic against residency continuously (JV_PQ_LUT=smem|l2 or JV_PQ_LUT_SMEM_M=<sub-spaces> override).
     plan->blob_in_global = 0;
+    plan->pq_smem_m = approx.kind == KIND_PQ ? approx.M : 0;
     if (approx.kind == KIND_PQ) {
         const char *mode = getenv("JV_PQ_LUT");
-        if (mode && mode[0] == 'l') plan->blob_in_global = 1;
-        else if (mode && mode[0] == 's') plan->blob_in_global = 0;
-        else plan->blob_in_global = (size_t)blob_floats(approx) * 4 * 5 > 200 * 1024 ? 1 : 0;
+        const char *msub = getenv("JV_PQ_LUT_SMEM_M");
+        if (msub) plan->pq_smem_m = std::max(0, std::min(approx.M, atoi(msub))) & ~3;
+        else if (mode && mode[0] == 'l') plan->pq_smem_m = 0;
+        else if (mode && mode[0] == 's') plan->pq_smem_m = approx.M;
+        else plan->pq_smem_m = (size_t)blob_floats(approx) * 4 * 5 > 200 * 1024 ? 0 : approx.M;
+        plan->blob_in_global = plan->pq_smem_m < approx.M ? 1 : 0;
     }
     plan->blob_floats = blob_floats(approx);
-    plan->smem_bytes = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, plan->blob_in_global != 0);
-    if (plan->smem_bytes > 227 * 1024 && approx.kind == KIND_PQ && !plan->blob_in_global) {
-        plan->blob_in_global = 1;  // a long list next to a LUT: keep the list in shared memory, move the LUT to L2
-        plan->smem_bytes = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, true);
+    plan->smem_bytes = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, plan->pq_smem_m);
+    if (plan->smem_bytes > 227 * 1024 && approx.kind == KIND_PQ && plan->pq_smem_m > 0) {
+        plan->pq_smem_m = 0;  // a long list next to a LUT: keep the list in shared memory, move the whole LUT to L2
+        plan->blob_in_global = 1;
+        plan->smem_bytes = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, 0);
     }
     if (plan->smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
     int vcap = visited_cap_hint > 0 ? visited_cap_hint : next_pow2i(4 * rerankK * (g.degree > 16 ? g.degree : 16));
@@ -666,8 +695,18 @@ cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const Gr
     int bps = 0;
     cudaError_t e = cudaSuccess;
     const int metric_for_occ = JV_METRIC_DOT;
-#define CALL(K, M) e = occupancy_of<K, M>(plan->smem_bytes, &bps)
-    JV_SEARCH_DISPATCH(approx.kind, metric_for_occ, CALL);
+#define CALL(K, M, B) e = occupancy_of<K, M, B>(plan->smem_bytes, &bps)
+    JV_SEARCH_DISPATCH(approx.kind, metric_for_occ, false, CALL);
+    plan->pq_wide = 0;
+    if (e == cudaSuccess && approx.kind == KIND_PQ) {
+        // the 64-register build wherever shared memory (not registers) is what limits residency
+        int bw = 0;
+        const int lite = bps;
+        JV_SEARCH_DISPATCH(approx.kind, metric_for_occ, true, CALL);
+        bw = bps;
+        if (e == cudaSuccess && bw >= lite) plan->pq_wide = 1;
+        else bps = lite;
+    }
 #undef CALL
     if (e != cudaSuccess) return e;
     if (bps < 1) return cudaErrorInvalidValue;
@@ -727,6 +766,8 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
     P.overflow = overflow_flags_dev;
     P.query_index = query_index_dev;
     P.blobA_floats = blob_floats(approx);
+    P.pq_smem_m = plan.pq_smem_m;
+    P.smemA_floats = search_smemA_floats(approx, plan.pq_smem_m);
     P.blobR_floats = rerank ? blob_floats(*rerank) : 0;
     P.blob_global = nullptr;
     if (plan.blob_in_global) {
@@ -742,12 +783,12 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
 #endif
     cudaError_t e = cudaMemsetAsync(work_counter_dev, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
-#define CALL(K, M)                                                                                                              \
-    do {                                                                                                                        \
-        e = cudaFuncSetAttribute(graph_search_kernel<K, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes); \
-        if (e == cudaSuccess) graph_search_kernel<K, M><<<plan.ctas, SEARCH_THREADS, plan.smem_bytes, s>>>(P);                  \
+#define CALL(K, M, B)                                                                                                              \
+    do {                                                                                                                           \
+        e = cudaFuncSetAttribute(graph_search_kernel<K, M, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes); \
+        if (e == cudaSuccess) graph_search_kernel<K, M, B><<<plan.ctas, SEARCH_THREADS, plan.smem_bytes, s>>>(P);                  \
     } while (0)
-    JV_SEARCH_DISPATCH(approx.kind, metric, CALL);
+    JV_SEARCH_DISPATCH(approx.kind, metric, plan.pq_wide != 0, CALL);
 #undef CALL
     if (e != cudaSuccess) return e;
     g_launches++;
