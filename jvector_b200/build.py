@@ -10,8 +10,8 @@ LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libjvector_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CU = ["kernels_batch.cu", "bq_imma.cu", "search.cu", "build.cu", "api.cu"]
-CPP = ["legacy_host.cpp", "legacy_simd.cpp"]
-HEADERS = ["common.cuh", "scorers.cuh", "kernels.h", os.path.join("..", "..", "include", "jvector_b200.h")]
+CPP = ["legacy_host.cpp", "legacy_simd.cpp", "legacy_avx512.cpp"]
+HEADERS = ["common.cuh", "scorers.cuh", "kernels.h", "legacy_avx512.h", os.path.join("..", "..", "include", "jvector_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: only explicit fmaf() fuses (NVQ bit tricks and score maps must round like the reference's scalar code)
 EXTRA = os.environ.get("JV_NVCC_EXTRA", "").split()
@@ -41,7 +41,10 @@ def build(force=False, verbose=False):
                 cmd = [NVCC] + ARCH + NVFLAGS + ["-c", s, "-o", o]
             else:
                 # legacy_host.cpp: explicit fmaf only (NVQ bit tricks); legacy_simd.cpp: let the vectoriser fuse (target_clones pick the ISA)
-                host = "-fPIC,-fvisibility=hidden,-O3,-ffp-contract=fast,-fno-math-errno" if src == "legacy_simd.cpp" else "-fPIC,-fvisibility=hidden,-O3,-mfma,-ffp-contract=off"
+                # legacy_host.cpp: explicit fmaf only (NVQ bit tricks); legacy_simd.cpp: let the vectoriser fuse (target_clones pick the ISA);
+                # legacy_avx512.cpp: intrinsics under per-function target attributes, explicit FMAs only
+                host = {"legacy_simd.cpp": "-fPIC,-fvisibility=hidden,-O3,-ffp-contract=fast,-fno-math-errno",
+                        "legacy_avx512.cpp": "-fPIC,-fvisibility=hidden,-O3,-ffp-contract=off,-fno-math-errno"}.get(src, "-fPIC,-fvisibility=hidden,-O3,-mfma,-ffp-contract=off")
                 cmd = [NVCC, "-O3", "-std=c++17", "-Xcompiler", host, "-c", s, "-o", o]
             jobs.append((src, cmd))
 

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include "../../include/jvector_b200.h"
+#include "legacy_avx512.h"
 
 namespace {
 
@@ -52,6 +53,7 @@ struct Nvq {
         scale = (logistic_nqt(maxv, sa, sx0) - bias) / levels;
     }
     inline float dq(float b) const { return logit_nqt(fmaf(b, scale, bias), isa, sx0); }
+    inline jvl::NvqScalars scalars() const { return jvl::NvqScalars{sa, isa, sx0, bias, scale}; }
 };
 
 }  // namespace
@@ -80,6 +82,7 @@ void min_in_place_f32(float *v1, const float *v2, size_t length)
 float assemble_and_sum_f32(const float *data, int dataBase, const unsigned char *baseOffsets, int baseOffsetsOffset, size_t baseOffsetsLength)
 {
     const unsigned char *c = baseOffsets + baseOffsetsOffset;
+    if (jvl::cpu_has_avx512()) return jvl::assemble_and_sum_avx512(data, dataBase, c, baseOffsetsLength);
     float s = 0.f;
     for (size_t i = 0; i < baseOffsetsLength; i++) s += data[(size_t)dataBase * i + c[i]];
     return s;
@@ -91,6 +94,7 @@ float assemble_and_sum_pq_f32(const float *data, size_t subspaceCount, const uns
     const int k = clusterCount;
     const size_t block = (size_t)k * (k + 1) / 2;
     const unsigned char *c1 = baseOffsets1 + baseOffsetsOffset1, *c2 = baseOffsets2 + baseOffsetsOffset2;
+    if (jvl::cpu_has_avx512()) return jvl::assemble_and_sum_pq_avx512(data, subspaceCount, c1, c2, clusterCount);
     float res = 0.f;
     for (size_t i = 0; i < subspaceCount; i++) {
         const int a = c1[i], b = c2[i];
@@ -104,6 +108,7 @@ float pq_decoded_cosine_similarity_f32(const unsigned char *baseOffsets, int bas
                                        const float *partialSums, const float *aMagnitude, float bMagnitude)
 {
     const unsigned char *c = baseOffsets + baseOffsetsOffset;
+    if (jvl::cpu_has_avx512()) return jvl::pq_decoded_cosine_avx512(c, baseOffsetsLength, clusterCount, partialSums, aMagnitude, bMagnitude);
     float s = 0.f, a = 0.f;
     for (size_t i = 0; i < baseOffsetsLength; i++) {
         const size_t idx = (size_t)clusterCount * i + c[i];
@@ -117,6 +122,7 @@ void calculate_partial_sums_dot_f32(const float *codebook, int codebookIndex, si
 {
     const float *q = query + queryOffset;
     float *out = partialSums + (size_t)codebookIndex * clusterCount;
+    if (jvl::cpu_has_avx512()) { jvl::partial_sums_avx512(codebook, size, clusterCount, q, out, 0); return; }
     for (int c = 0; c < clusterCount; c++) {
         const float *cen = codebook + (size_t)c * size;
         float s = 0.f;
@@ -129,6 +135,7 @@ void calculate_partial_sums_euclidean_f32(const float *codebook, int codebookInd
 {
     const float *q = query + queryOffset;
     float *out = partialSums + (size_t)codebookIndex * clusterCount;
+    if (jvl::cpu_has_avx512()) { jvl::partial_sums_avx512(codebook, size, clusterCount, q, out, 1); return; }
     for (int c = 0; c < clusterCount; c++) {
         const float *cen = codebook + (size_t)c * size;
         float s = 0.f;
@@ -140,6 +147,7 @@ void calculate_partial_sums_euclidean_f32(const float *codebook, int codebookInd
 void calculate_partial_sums_self_magnitude_f32(const float *codebook, int codebookIndex, size_t size, int clusterCount, float *partialSums)
 {
     float *out = partialSums + (size_t)codebookIndex * clusterCount;
+    if (jvl::cpu_has_avx512()) { jvl::partial_sums_avx512(codebook, size, clusterCount, nullptr, out, 2); return; }
     for (int c = 0; c < clusterCount; c++) {
         const float *cen = codebook + (size_t)c * size;
         float s = 0.f;
@@ -153,6 +161,7 @@ void nvq_quantize_8bit(const float *vector, size_t length, float alpha, float x0
     const float delta = maxValue - minValue, sa = alpha / delta, sx0 = x0 * delta;
     const float bias = logistic_nqt(minValue, sa, sx0);
     const float inv = 255.0f / (logistic_nqt(maxValue, sa, sx0) - bias);
+    if (jvl::cpu_has_avx512()) { jvl::nvq_quantize_avx512(vector, length, sa, -sa * sx0, bias, inv, destination); return; }
     for (size_t i = 0; i < length; i++) {
         const float a = fmaf(logistic_nqt(vector[i], sa, sx0) - bias, inv, 0.5f);
         const int q = (int)a;
@@ -163,6 +172,7 @@ void nvq_quantize_8bit(const float *vector, size_t length, float alpha, float x0
 float nvq_loss(const float *vector, size_t length, float alpha, float x0, float minValue, float maxValue, int nBits)
 {
     const Nvq c(alpha, x0, minValue, maxValue, (float)((1 << nBits) - 1));
+    if (jvl::cpu_has_avx512()) return jvl::nvq_loss_avx512(vector, length, c.scalars(), -c.sa * c.sx0);
     const float inv = 1.0f / c.scale;
     float s = 0.f;
     for (size_t i = 0; i < length; i++) {
@@ -176,6 +186,7 @@ float nvq_loss(const float *vector, size_t length, float alpha, float x0, float 
 float nvq_uniform_loss(const float *vector, size_t length, float minValue, float maxValue, int nBits)
 {
     const float constant = (float)((1 << nBits) - 1), delta = maxValue - minValue;
+    if (jvl::cpu_has_avx512()) return jvl::nvq_uniform_loss_avx512(vector, length, minValue, maxValue, constant);
     float s = 0.f;
     for (size_t i = 0; i < length; i++) {
         const float r = (vector[i] - minValue) * (constant / delta);
@@ -189,6 +200,7 @@ float nvq_uniform_loss(const float *vector, size_t length, float minValue, float
 float nvq_square_l2_distance_8bit(const float *vector, const unsigned char *quantized, size_t length, float alpha, float x0, float minValue, float maxValue)
 {
     const Nvq c(alpha, x0, minValue, maxValue, 255.0f);
+    if (jvl::cpu_has_avx512()) return jvl::nvq_l2_avx512(vector, quantized, length, c.scalars());
     float s = 0.f;
     for (size_t i = 0; i < length; i++) { const float d = vector[i] - c.dq((float)quantized[i]); s = fmaf(d, d, s); }
     return s;
@@ -197,6 +209,7 @@ float nvq_square_l2_distance_8bit(const float *vector, const unsigned char *quan
 float nvq_dot_product_8bit(const float *vector, const unsigned char *quantized, size_t length, float alpha, float x0, float minValue, float maxValue)
 {
     const Nvq c(alpha, x0, minValue, maxValue, 255.0f);
+    if (jvl::cpu_has_avx512()) return jvl::nvq_dot_avx512(vector, quantized, length, c.scalars());
     float s = 0.f;
     for (size_t i = 0; i < length; i++) s = fmaf(vector[i], c.dq((float)quantized[i]), s);
     return s;
@@ -207,6 +220,10 @@ int64_t nvq_cosine_8bit_packed(const float *vector, const unsigned char *quantiz
 {
     const Nvq c(alpha, x0, minValue, maxValue, 255.0f);
     float s = 0.f, bm = 0.f;
+    if (jvl::cpu_has_avx512()) {
+        jvl::nvq_cosine_avx512(vector, quantized, length, c.scalars(), centroid, &s, &bm);
+        return ((int64_t)f2i(bm) << 32) | (int64_t)(uint32_t)f2i(s);
+    }
     for (size_t i = 0; i < length; i++) {
         const float e = c.dq((float)quantized[i]) + centroid[i];
         s = fmaf(vector[i], e, s);

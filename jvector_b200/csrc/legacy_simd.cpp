@@ -8,6 +8,7 @@
 #include <stddef.h>
 
 #include "../../include/jvector_b200.h"
+#include "legacy_avx512.h"
 
 #define JV_CLONES __attribute__((target_clones("avx512f", "avx2,fma", "default")))
 
@@ -27,6 +28,7 @@ JV_CLONES float dot_product_f32(const float *a, size_t aoffset, const float *b, 
 {
     a += aoffset;
     b += boffset;
+    if (jvl::cpu_has_avx512()) return jvl::dot_avx512(a, b, length);
     float acc[W] = {0.f};
     size_t i = 0;
     for (; i + W <= length; i += W)
@@ -39,6 +41,7 @@ JV_CLONES float euclidean_f32(const float *a, size_t aoffset, const float *b, si
 {
     a += aoffset;
     b += boffset;
+    if (jvl::cpu_has_avx512()) return jvl::l2_avx512(a, b, length);
     float acc[W] = {0.f};
     size_t i = 0;
     for (; i + W <= length; i += W)
@@ -57,6 +60,7 @@ JV_CLONES float cosine_f32(const float *a, size_t aoffset, const float *b, size_
 {
     a += aoffset;
     b += boffset;
+    if (jvl::cpu_has_avx512()) return jvl::cosine_avx512(a, b, length);
     float s[W] = {0.f}, aa[W] = {0.f}, bb[W] = {0.f};
     size_t i = 0;
     for (; i + W <= length; i += W)

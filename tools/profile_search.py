@@ -1,8 +1,12 @@
 #!/usr/bin/env python
-"""Profiling helper (keeps ncu away from the graph build):
-   python tools/profile_search.py --prepare   # build the c2 graph, save the adjacency under /tmp
-   ncu ... python tools/profile_search.py --run [--workload c2|c3]   # load it, launch graph_search_kernel 3 times
-Same data / parameters as bench.py (workload c2 / c3)."""
+"""Search-kernel tuning / profiling helper: ONE process builds the c2 world (rows generated on the device, graph, PQ codes, FusedPQ
+records) and then times graph_search_kernel under every requested setting of the runtime knobs, which the library re-reads on
+each call:
+
+    python tools/profile_search.py --sweep                      # c2 + c3 over JV_PQ_LUT_SMEM_M x JV_FUSED_PQ
+    ncu ... python tools/profile_search.py --workload c3 --reps 2   # a plain run for the profiler (no sweep)
+
+Same data and parameters as bench.py (workloads c2 / c3)."""
 import argparse
 import os
 import sys
@@ -13,46 +17,55 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench  # noqa: E402
-import jvector_b200 as jv  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--prepare", action="store_true")
-ap.add_argument("--run", action="store_true")
-ap.add_argument("--workload", default="c2")
+ap.add_argument("--sweep", action="store_true")
+ap.add_argument("--workload", default="c3", choices=["c2", "c3"])
 ap.add_argument("--n", type=int, default=1_000_000)
 ap.add_argument("--nq", type=int, default=10_000)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--dir", default="/tmp/jv_profile")
+ap.add_argument("--smem-m", default="0,24,32,48,64,96")
 a = ap.parse_args()
-os.makedirs(a.dir, exist_ok=True)
-VSF = jv.VectorSimilarityFunction
-jv.init(0)
-base = bench.gen_unit_rows(bench.SEED, a.n, 768)
-vec = jv.F32Vectors(base)
-if a.prepare:
-    gi = jv.GraphIndexBuilder(VSF.DOT_PRODUCT, M=32, beamWidth=100, neighborOverflow=1.2, alpha=1.2, addHierarchy=True, seed=bench.SEED).build(vec)
-    inf = gi.info()
-    np.save(os.path.join(a.dir, "entry.npy"), np.array([inf["entry_node"], inf["levels"]]))
-    for l in range(inf["levels"]):
-        ids, adj = gi.level(l)
-        np.save(os.path.join(a.dir, "ids%d.npy" % l), ids)
-        np.save(os.path.join(a.dir, "adj%d.npy" % l), adj)
-    if a.workload == "c3":
-        import oracle_lib as o
-        rs = np.random.default_rng(bench.SEED + 99)
-        cb, _, _ = o.train_pq_numpy(rs, base[rs.choice(a.n, 20000, replace=False)], 96, 256, iters=6)
-        np.save(os.path.join(a.dir, "cb.npy"), cb)
-        np.save(os.path.join(a.dir, "codes.npy"), jv.pq_encode_all(base, cb, 96, 256))
-    print("prepared", inf)
-if a.run:
-    entry, levels = np.load(os.path.join(a.dir, "entry.npy"))
-    upper = [(np.load(os.path.join(a.dir, "ids%d.npy" % l)), np.load(os.path.join(a.dir, "adj%d.npy" % l))) for l in range(1, int(levels))]
-    gi = jv.GraphIndex(np.load(os.path.join(a.dir, "adj0.npy")), int(entry), upper)
-    queries = bench.gen_unit_rows(bench.SEED + 1, a.nq, 768)
-    s = jv.GraphSearcher(gi)
-    approx, rr = vec, None
-    if a.workload == "c3":
-        approx, rr = jv.PQVectors(np.load(os.path.join(a.dir, "codes.npy")), np.load(os.path.join(a.dir, "cb.npy")), 768, 256), vec
+
+args = argparse.Namespace(impl="b200", n=a.n, dim=768, nq=a.nq, dist="latent", topk=10, gt_queries=500)
+cx = bench.Ctx(args)
+jv, VSF = cx.jv, cx.VSF
+w = bench.World2(cx)
+s = jv.GraphSearcher(w.gi)
+
+
+def run(approx, rr, label):
+    best = None
     for _ in range(a.reps):
-        r = s.search(approx, queries, VSF.DOT_PRODUCT, 10, 100, reranker=rr)
-        print("device_ms %.3f visited/q %.1f qps %.0f" % (r.device_ms, r.visitedCount / a.nq, a.nq / (r.device_ms / 1e3)))
+        r = s.search(approx, w.queries, VSF.DOT_PRODUCT, 10, 100, reranker=rr)
+        best = r if best is None or r.device_ms < best.device_ms else best
+    rec = bench.recall_at_k(best.nodes[:w.ngt], w.gt_nodes, 10)
+    print("%-44s device_ms %8.3f  qps %9.0f  visited/q %.1f  recall@10 %.4f" % (label, best.device_ms, a.nq / (best.device_ms / 1e3), best.visitedCount / a.nq, rec), flush=True)
+    return best
+
+
+if a.sweep or a.workload == "c2":
+    run(w.vec, None, "c2 fp32 walk")
+if a.sweep or a.workload == "c3":
+    import oracle_lib as o
+    rs = np.random.default_rng(bench.SEED + 99)
+    sel = np.sort(rs.choice(a.n, min(a.n, 20000), replace=False))
+    sample = w.base_dev[cx.torch.from_numpy(sel).cuda()].cpu().numpy()
+    cb, _, _ = o.train_pq_numpy(rs, sample, 96, 256, iters=6)
+    codes = jv.pq_encode_all(w.vec, cb, 96, 256)
+    pqv = jv.PQVectors(codes, cb, 768, 256)
+    w.gi.fuse_pq(pqv)
+    if a.sweep:
+        ref = None
+        for fused in ("1", "0"):
+            os.environ["JV_FUSED_PQ"] = fused
+            for m in a.smem_m.split(","):
+                os.environ["JV_PQ_LUT_SMEM_M"] = m
+                r = run(pqv, w.vec, "c3 PQ walk fused=%s lut_smem_m=%s" % (fused, m))
+                if ref is None:
+                    ref = r.nodes
+                elif not np.array_equal(ref, r.nodes):
+                    print("   !! id lists differ from the first configuration")
+        del os.environ["JV_FUSED_PQ"], os.environ["JV_PQ_LUT_SMEM_M"]
+    else:
+        run(pqv, w.vec, "c3 PQ walk (defaults)")
