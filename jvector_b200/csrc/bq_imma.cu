@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(IMMA_THREADS, 2) bq_imma_kernel(ImmaParams P)
     const int wm = warp & 3, wn = warp >> 2;
     const int nact = P.n_active ? *P.n_active : P.nq;  // tile columns past the active queries are padding (qid = -1, never pass)
     const long long rows_total = MODE == 1 ? (long long)P.S : P.n;
-    const long long r0 = (long long)blockIdx.y * BM;
+    const long long r0 = ((long long)blockIdx.y + (long long)blockIdx.z * gridDim.y) * BM;  // row tiles fold over y and z (gridDim.y <= 65535)
     if (r0 >= rows_total) return;
     const int W4 = P.W32 >> 2;  // W32 = 2 W is a multiple of 4 (bq_imma_supported: W even), so every row is a whole number of uint4
 
@@ -474,9 +474,14 @@ cudaError_t launch_bq_topk_imma(const DataDesc &d, const float *queries_dev, int
     const size_t smem = (size_t)(BM + BN) * (W32 + 4) * 4 + (size_t)(BM + 2 * BN) * 4;
     if ((e = cudaFuncSetAttribute(bq_imma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(bq_imma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    auto row_grid = [](unsigned qtiles, long long rows) {
+        const long long tiles = (rows + BM - 1) / BM;
+        const unsigned gy = (unsigned)(tiles < 32768 ? tiles : 32768);
+        return dim3(qtiles, gy, (unsigned)((tiles + gy - 1) / gy));
+    };
     // 2. sample pass
     {
-        dim3 grid(nq_pad / BN, (S + BM - 1) / BM);
+        dim3 grid = row_grid(nq_pad / BN, S);
         bq_imma_kernel<1><<<grid, IMMA_THREADS, smem, s>>>(P);
         g_launches++;
     }
@@ -496,7 +501,6 @@ cudaError_t launch_bq_topk_imma(const DataDesc &d, const float *queries_dev, int
     const int sort_cap = 4096;
     const size_t ssm = hsm + 8 + (size_t)sort_cap * 8;
     if ((e = cudaFuncSetAttribute(bq_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm)) != cudaSuccess) return e;
-    const unsigned rows_tiles = (unsigned)((d.n + BM - 1) / BM);
     for (int pass = 0; pass < 3; pass++) {
         const int *qlist = pass == 0 ? nullptr : (pass == 1 ? qla : qlb);
         const int *nact = pass == 0 ? nullptr : &counters[pass - 1];
@@ -504,7 +508,7 @@ cudaError_t launch_bq_topk_imma(const DataDesc &d, const float *queries_dev, int
         int *nnext = pass == 2 ? nullptr : &counters[pass];
         P.qlist = qlist;
         P.n_active = nact;
-        dim3 grid(pass == 0 ? nq_pad / BN : 1, rows_tiles);
+        dim3 grid = row_grid(pass == 0 ? nq_pad / BN : 1, d.n);
         bq_imma_kernel<0><<<grid, IMMA_THREADS, smem, s>>>(P);
         g_launches++;
         bq_select_kernel<<<pass == 0 ? nq : min(nq, 65535), 256, ssm, s>>>(buf, cnt, BQ_IMMA_CAP, k, d.n, d.dim, pb, thr, safe, t2, keys_out_dev, qlist, nact, qnext,
