@@ -4,7 +4,7 @@ records) and then times graph_search_kernel under every requested setting of the
 each call:
 
     python tools/profile_search.py --sweep                      # c2 + c3 over JV_PQ_LUT_SMEM_M x JV_FUSED_PQ
-    ncu ... python tools/profile_search.py --workload c3 --reps 2   # a plain run for the profiler (no sweep)
+    ncu --profile-from-start off ... python tools/profile_search.py --workload c3 --reps 1 --ncu   # only the timed launches are profiled
 
 Same data and parameters as bench.py (workloads c2 / c3)."""
 import argparse
@@ -25,6 +25,7 @@ ap.add_argument("--n", type=int, default=1_000_000)
 ap.add_argument("--nq", type=int, default=10_000)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--smem-m", default="0,24,32,48,64,96")
+ap.add_argument("--ncu", action="store_true", help="bracket the timed launches with cudaProfilerStart/Stop (ncu --profile-from-start off)")
 a = ap.parse_args()
 
 args = argparse.Namespace(impl="b200", n=a.n, dim=768, nq=a.nq, dist="latent", topk=10, gt_queries=500)
@@ -36,9 +37,14 @@ s = jv.GraphSearcher(w.gi)
 
 def run(approx, rr, label):
     best = None
+    if a.ncu:
+        s.search(approx, w.queries, VSF.DOT_PRODUCT, 10, 100, reranker=rr)  # warm-up outside the profiled range
+        cx.torch.cuda.cudart().cudaProfilerStart()
     for _ in range(a.reps):
         r = s.search(approx, w.queries, VSF.DOT_PRODUCT, 10, 100, reranker=rr)
         best = r if best is None or r.device_ms < best.device_ms else best
+    if a.ncu:
+        cx.torch.cuda.cudart().cudaProfilerStop()
     rec = bench.recall_at_k(best.nodes[:w.ngt], w.gt_nodes, 10)
     print("%-44s device_ms %8.3f  qps %9.0f  visited/q %.1f  recall@10 %.4f" % (label, best.device_ms, a.nq / (best.device_ms / 1e3), best.visitedCount / a.nq, rec), flush=True)
     return best
