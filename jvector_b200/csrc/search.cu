@@ -289,6 +289,14 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                 // the fp32 / NVQ paths are bandwidth-bound and must not waste it): the entries right behind p are the likeliest to
                 // be expanded next, so touch their adjacency rows and prefetch their neighbours' code rows into L2.
                 // Reads only; results unchanged.
+                if (lvl == 0 && (KIND == KIND_F32 || KIND == KIND_NVQ)) {
+                    // bandwidth-bound kinds speculate on the ADJACENCY rows only (128 B each, nothing next to the 3 KB rows): the next
+                    // pops are most likely the unexpanded entries right behind p, and their rows then come from L2 instead of DRAM
+                    if (tid >= 32 && tid < 36) {
+                        const int pp = p + (tid - 31);
+                        if (pp < size && !(fcur[pp] & F_EXPANDED)) prefetch_l2(P.g.adj0 + (size_t)key_node(cur[pp]) * degree);
+                    }
+                }
                 if (lvl == 0 && (KIND == KIND_PQ || KIND == KIND_BQ)) {
                     const int w = tid >> 5;
                     if (w >= 1 && w <= 3) {
