@@ -237,7 +237,7 @@ def topk_bruteforce(vectors, vsf, queries, k):
 def bq_encode_all(rows):
     """BinaryQuantization.encodeAll. rows: a host array, or F32Vectors already resident in HBM (no upload)."""
     lib = nat.init()
-    if isinstance(rows, F32Vectors):
+    if isinstance(rows, _Vectors):
         out = np.empty((rows.size(), (rows.dimension() + 63) // 64), dtype=np.uint64)
         check(lib.jv_bq_encode_dataset(rows._h, wp(out)))
         return out
@@ -252,7 +252,7 @@ def pq_encode_all(rows, codebooks, M, k=256, centroid=None):
     lib = nat.init()
     codebooks = c32(codebooks).reshape(-1)
     cen = c32(centroid) if centroid is not None else None
-    if isinstance(rows, F32Vectors):
+    if isinstance(rows, _Vectors):
         out = np.empty((rows.size(), M), dtype=np.uint8)
         check(lib.jv_pq_encode_dataset(rows._h, M, k, fp(codebooks), fp(cen), bp(out)))
         return out
@@ -266,7 +266,7 @@ def nvq_encode_all(rows, mean, nsub, learn=True):
     """NVQuantization.encodeAll. rows: a host array, or F32Vectors already resident in HBM (no upload)."""
     lib = nat.init()
     mean = c32(mean)
-    if isinstance(rows, F32Vectors):
+    if isinstance(rows, _Vectors):
         params = np.empty((rows.size(), nsub, 4), dtype=np.float32)
         out = np.empty((rows.size(), rows.dimension()), dtype=np.uint8)
         check(lib.jv_nvq_encode_dataset(rows._h, nsub, fp(mean), 1 if learn else 0, fp(params), bp(out)))

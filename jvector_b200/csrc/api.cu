@@ -673,7 +673,7 @@ static int topk_bq_imma_enqueue(jv_dataset ds, const float *queries_dev, int nq,
         const int cq = std::min(chunk, nq - q0);
         // one status word per call: chunks after the first accumulate through a scratch word
         int *st = q0 == 0 ? status_dev : tmp;
-        CK(launch_bq_topk_imma(ds->d, queries_dev + (size_t)q0 * ds->d.dim, cq, k, (long long)id_base, t_ctx.dbuf[7], keys_dev + (size_t)q0 * k, st, s), "bq_topk_imma");
+        CK(launch_bq_topk_imma(ds->d, queries_dev + (size_t)q0 * ds->d.dim, cq, k, (long long)id_base, t_ctx.dbuf[7], keys_dev + (size_t)q0 * k, st, g_sm_count, s), "bq_topk_imma");
         if (q0 > 0) CK(launch_add_int(status_dev, tmp, s), "status");
     }
     return JV_OK;

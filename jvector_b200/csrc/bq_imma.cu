@@ -20,6 +20,7 @@
 //      the common path has no host synchronisation.
 // Row ids inside the keys are global (local row + id_base), so the keys can be the NCCL send buffer of a range-sharded base.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -426,15 +427,18 @@ static int bq_imma_sample_rows(long long n)
     return (int)(n < s ? n : s);
 }
 
+constexpr int NQ_ALIGN = 256;  // query count padded to the tcgen05 tile (a multiple of the IMMA tile)
+
 size_t bq_imma_scratch_bytes(long long n, int nq, int W)
 {
-    const int nq_pad = (nq + BN - 1) / BN * BN, W32 = 2 * W;
+    const int nq_pad = (nq + NQ_ALIGN - 1) / NQ_ALIGN * NQ_ALIGN, W32 = 2 * W;
     size_t b = 0;
     b += (size_t)nq_pad * W32 * 4 + 256;                     // qbits
     b += ((size_t)nq_pad * 4 + 256) * 7;                     // pb, thr, safe, t2, cnt, qlist a / b
     b += 64 + 256;                                           // counters
     b += (size_t)nq_pad * bq_imma_sample_rows(n) * 2 + 256;  // hdm
     b += (size_t)nq * BQ_IMMA_CAP * 8 + 256;                 // buf
+    b += bq_umma_image_bytes(nq, W) + 256;                   // pre-swizzled query images of the tcgen05 filter pass
     return b + 1024;
 }
 
@@ -445,10 +449,13 @@ bool bq_imma_supported(const DataDesc &d, int k)
 }
 
 cudaError_t launch_bq_topk_imma(const DataDesc &d, const float *queries_dev, int nq, int k, long long id_base, void *scratch_dev,
-                                long long *keys_out_dev, int *unresolved_dev, cudaStream_t s)
+                                long long *keys_out_dev, int *unresolved_dev, int sm_count, cudaStream_t s)
 {
     if (nq <= 0) return cudaSuccess;
-    const int nq_pad = (nq + BN - 1) / BN * BN, W32 = 2 * d.W;
+    const int nq_pad = (nq + NQ_ALIGN - 1) / NQ_ALIGN * NQ_ALIGN, W32 = 2 * d.W;
+    // JV_BQ_FILTER=umma: the full filter pass on tcgen05 (bq_umma.cu); default: the IMMA kernel of this file
+    const char *fm = getenv("JV_BQ_FILTER");
+    const bool use_umma = fm && fm[0] == 'u' && bq_umma_supported(d);
     char *p = reinterpret_cast<char *>(scratch_dev);
     auto take = [&p](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
     uint32_t *qbits = reinterpret_cast<uint32_t *>(take((size_t)nq_pad * W32 * 4));
@@ -463,6 +470,7 @@ cudaError_t launch_bq_topk_imma(const DataDesc &d, const float *queries_dev, int
     const int S = bq_imma_sample_rows(d.n);
     unsigned short *hdm = reinterpret_cast<unsigned short *>(take((size_t)nq_pad * S * 2));
     long long *buf = reinterpret_cast<long long *>(take((size_t)nq * BQ_IMMA_CAP * 8));
+    uint8_t *images = reinterpret_cast<uint8_t *>(take(bq_umma_image_bytes(nq, d.W)));
     cudaError_t e;
 
     bq_pack_queries_kernel<<<(nq_pad * 32 + 255) / 256, 256, 0, s>>>(queries_dev, nq, nq_pad, d.dim, W32, qbits, pb);
@@ -508,9 +516,13 @@ cudaError_t launch_bq_topk_imma(const DataDesc &d, const float *queries_dev, int
         int *nnext = pass == 2 ? nullptr : &counters[pass];
         P.qlist = qlist;
         P.n_active = nact;
-        dim3 grid = row_grid(pass == 0 ? nq_pad / BN : 1, d.n);
-        bq_imma_kernel<0><<<grid, IMMA_THREADS, smem, s>>>(P);
-        g_launches++;
+        if (pass == 0 && use_umma) {
+            if ((e = launch_bq_umma_filter(d, qbits, nq, nq_pad, t2, pb, buf, cnt, BQ_IMMA_CAP, id_base, images, sm_count, s)) != cudaSuccess) return e;
+        } else {
+            dim3 grid = row_grid(pass == 0 ? nq_pad / BN : 1, d.n);
+            bq_imma_kernel<0><<<grid, IMMA_THREADS, smem, s>>>(P);
+            g_launches++;
+        }
         bq_select_kernel<<<pass == 0 ? nq : min(nq, 65535), 256, ssm, s>>>(buf, cnt, BQ_IMMA_CAP, k, d.n, d.dim, pb, thr, safe, t2, keys_out_dev, qlist, nact, qnext,
                                                                            nnext, sort_cap, unresolved_dev);
         g_launches++;

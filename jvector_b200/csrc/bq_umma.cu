@@ -1,0 +1,314 @@
+// bq_umma.cu — the FILTER pass of the BQ Hamming top-k (see bq_imma.cu for the whole pipeline) on the 5th-generation tensor
+// cores: tcgen05.mma kind::i8 (u8 x u8 -> s32, exact), accumulators in TMEM, operands in shared memory in the canonical K-major
+// SWIZZLE_128B layout, warp-specialised roles connected by mbarriers.
+//
+//   D[128 rows][256 queries] += A[128][K] * B[256][K]^T,  A / B = {0,1} bytes expanded from bit words, K = dim rounded to 128
+//
+// Why a second kernel next to the IMMA one: the legacy IMMA path tops out at 917 TOP/s and re-expands both operands in every
+// warp tile; here the row tile is expanded ONCE per CTA tile into shared memory (producer warps), the query tile arrives as a
+// pre-expanded, pre-swizzled 32 KB image by one bulk copy, and one elected thread issues 128 x 256 x 32 MMAs.
+//
+// Roles (384 threads): warp 0 = B producer (cp.async.bulk of the query image chunk), warp 1 = MMA issuer + TMEM owner,
+// warps 4-7 = epilogue (tcgen05.ld: warp w may touch TMEM lanes 32 (w % 4) ..), warps 8-11 = A producers (bits -> bytes, swizzled
+// 128-bit stores, fence.proxy.async, arrive). Pipelines: full[s] / empty[s] over 4 operand stages of 48 KB, tmem_full[a] /
+// tmem_empty[a] over two 256-column accumulators, so the epilogue of one tile overlaps the MMAs of the next.
+// Every spin-wait is bounded and traps: a wrong barrier count aborts the launch instead of hanging the device.
+#include <limits.h>
+
+#include "kernels.h"
+
+namespace jv {
+
+namespace {
+
+constexpr int UM = 128;           // rows per tile (MMA M)
+constexpr int UN = 256;           // queries per tile (MMA N)
+constexpr int UKC = 128;          // K bytes per stage (one 128-byte swizzle atom wide)
+constexpr int USTAGES = 4;
+constexpr int UTHREADS = 384;
+constexpr int A_STAGE_BYTES = UM * UKC;  // 16 KB
+constexpr int B_STAGE_BYTES = UN * UKC;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int N_A_PRODUCERS = 128;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, unsigned phase)
+{
+    for (unsigned spins = 0; !mbar_try_wait(bar, phase); ++spins)
+        if (spins > (1u << 28)) __trap();  // a pipeline bug must abort the launch, not hang the device
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute/arch/mma_sm100_desc.hpp SmemDescriptor; canonical layout
+// ((8,n),2):((8,SBO),1) in 16-byte units): rows 128 B apart inside an 8-row atom, atoms SBO = 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);  // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused by swizzled K-major layouts), bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell), bits [46,48)
+    d |= (uint64_t)2 << 61;                       // layout type SWIZZLE_128B, bits [61,64)
+    return d;
+}
+
+// instruction descriptor (InstrDescriptor): c = S32 (2) at [4,6), a = b = U8 (0), K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t UMMA_IDESC = (2u << 4) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// the query tile as shared-memory images: [qtile][kchunk][UN rows x 128 B], swizzled exactly as the MMA reads it
+__global__ void __launch_bounds__(256) bq_query_image_kernel(const uint32_t *__restrict__ qbits, int nq_pad, int W32, int kchunks, uint8_t *__restrict__ images)
+{
+    // one thread per (query, 16-byte chunk): 16 bits -> 16 bytes
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)nq_pad * kchunks * 8;
+    if (idx >= total) return;
+    const int j = (int)(idx & 7);
+    const long long t = idx >> 3;
+    const int kc = (int)(t % kchunks), q = (int)(t / kchunks);
+    const uint32_t w = qbits[(size_t)q * W32 + kc * 4 + (j >> 1)];
+    const uint32_t bits = (j & 1) ? (w >> 16) : (w & 0xffffu);
+    uint4 v;
+    v.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
+    v.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+    v.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+    v.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+    const int qt = q / UN, r = q % UN;
+    uint8_t *img = images + ((size_t)qt * kchunks + kc) * B_STAGE_BYTES;
+    *reinterpret_cast<uint4 *>(img + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)) = v;
+}
+
+struct UmmaParams {
+    const uint32_t *rows;  // [n][W32]
+    long long n;
+    int W32, dim, kchunks;
+    const uint8_t *images;  // [qtiles][kchunks][32 KB]
+    int qtiles, nq;
+    const int *t2, *pb;
+    long long *buf;
+    int *cnt;
+    int cap;
+    long long id_base;
+};
+
+__global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams P)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *stage0 = smem;  // USTAGES x (A 16 KB | B 32 KB), 1024-byte aligned
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + USTAGES * STAGE_BYTES);
+    uint64_t *empty = full + USTAGES;
+    uint64_t *tmem_full = empty + USTAGES;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long row_tiles = (P.n + UM - 1) / UM;
+    const long long tiles = row_tiles * P.qtiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < USTAGES; s++) {
+            mbar_init(&full[s], N_A_PRODUCERS + 1);  // 128 row producers + the bulk copy's arrive.expect_tx
+            mbar_init(&empty[s], 1);                 // one tcgen05.commit
+        }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== B producer: one bulk copy of the query image chunk per stage =====
+        if (lane == 0) {
+            int stage = 0;
+            unsigned phase = 0;
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int qt = (int)(tile / row_tiles);
+                for (int kc = 0; kc < P.kchunks; kc++) {
+                    mbar_wait_bounded(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], B_STAGE_BYTES);
+                    bulk_g2s(stage0 + stage * STAGE_BYTES + A_STAGE_BYTES, P.images + ((size_t)qt * P.kchunks + kc) * B_STAGE_BYTES, B_STAGE_BYTES, &full[stage]);
+                    if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            unsigned phase = 0, acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                mbar_wait_bounded(&tmem_empty[acc], acc_phase ^ 1);  // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(acc * UN);
+                for (int kc = 0; kc < P.kchunks; kc++) {
+                    mbar_wait_bounded(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(stage0 + stage * STAGE_BYTES), b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < UKC / 32; k++)
+                        umma_i8(d, umma_desc(a_addr + 32 * k), umma_desc(b_addr + 32 * k), UMMA_IDESC, (kc | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty[stage]);  // frees the stage when these MMAs have read it
+                    if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);    // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== epilogue: thread = one row of the tile = one TMEM lane =====
+        const int ltid = (warp - 4) * 32 + lane;
+        int acc = 0;
+        unsigned acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int qt = (int)(tile / row_tiles);
+            const long long rr = (tile % row_tiles) * UM + ltid;
+            int par = 0;
+            if (rr < P.n) {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(P.rows + (size_t)rr * P.W32);
+                for (int c = 0; c < (P.W32 >> 2); c++) {
+                    const uint4 v = __ldg(rp + c);
+                    par += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+                }
+            }
+            mbar_wait_bounded(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + (uint32_t)(acc * UN);
+#pragma unroll 1
+            for (int g = 0; g < UN / 32; g++) {
+                uint32_t v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                      "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                      "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                      "=r"(v[31])
+                    : "r"(taddr + (uint32_t)(g * 32)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (rr < P.n) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const int q = qt * UN + g * 32 + c;
+                        if (q < P.nq) {
+                            const int dot = (int)v[c];
+                            if (par - 2 * dot <= __ldg(P.t2 + q)) {
+                                const int hd = par + __ldg(P.pb + q) - 2 * dot;
+                                const long long key = topk_key(bq_score_from_hd(hd, P.dim), (int32_t)(rr + P.id_base));
+                                const int pos = atomicAdd(&P.cnt[q], 1);
+                                if (pos < P.cap) P.buf[(size_t)q * P.cap + pos] = key;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 8) {
+        // ===== A producers: thread = one row; 128 bits -> 128 bytes per stage, swizzled 16-byte chunks =====
+        const int r = (warp - 8) * 32 + lane;
+        int stage = 0;
+        unsigned phase = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const long long rr = (tile % row_tiles) * UM + r;
+            const uint4 *rp = reinterpret_cast<const uint4 *>(P.rows + (size_t)(rr < P.n ? rr : 0) * P.W32);
+            for (int kc = 0; kc < P.kchunks; kc++) {
+                uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                if (rr < P.n) w = __ldg(rp + kc);
+                mbar_wait_bounded(&empty[stage], phase ^ 1);
+                unsigned char *dst = stage0 + stage * STAGE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+                const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t bits = (j & 1) ? (ws[j >> 1] >> 16) : (ws[j >> 1] & 0xffffu);
+                    uint4 v;
+                    v.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
+                    v.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+                    v.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+                    v.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+                    *reinterpret_cast<uint4 *>(dst + ((j ^ (r & 7)) << 4)) = v;
+                }
+                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                mbar_arrive(&full[stage]);
+                if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    }
+    // teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+}  // namespace
+
+size_t bq_umma_image_bytes(int nq, int W)
+{
+    const int qtiles = (nq + UN - 1) / UN, kchunks = (2 * W) / 4;
+    return (size_t)qtiles * kchunks * B_STAGE_BYTES + 1024;
+}
+
+bool bq_umma_supported(const DataDesc &d)
+{
+    return d.kind == KIND_BQ && (d.W % 2) == 0 && d.W <= 32;
+}
+
+// the filter pass over queries [0, nq) (identity list): pairs with hd <= thr[q] append their keys to buf / cnt
+cudaError_t launch_bq_umma_filter(const DataDesc &d, const uint32_t *qbits_dev, int nq, int nq_pad, const int *t2_dev, const int *pb_dev, long long *buf_dev,
+                                  int *cnt_dev, int cap, long long id_base, uint8_t *images_dev, int sm_count, cudaStream_t s)
+{
+    const int W32 = 2 * d.W, kchunks = W32 / 4, qtiles = (nq + UN - 1) / UN;
+    cudaError_t e;
+    // padding queries of the last tile need defined (zero) bits: qbits rows [nq, nq_pad) are zero; rows past nq_pad are not read
+    const int q_img = qtiles * UN;
+    if (q_img > nq_pad) return cudaErrorInvalidValue;  // callers pad nq_pad to a multiple of 256
+    {
+        const long long total = (long long)q_img * kchunks * 8;
+        bq_query_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(qbits_dev, q_img, W32, kchunks, images_dev);
+        g_launches++;
+    }
+    UmmaParams P;
+    P.rows = reinterpret_cast<const uint32_t *>(d.words);
+    P.n = d.n; P.W32 = W32; P.dim = d.dim; P.kchunks = kchunks; P.images = images_dev; P.qtiles = qtiles; P.nq = nq; P.t2 = t2_dev; P.pb = pb_dev;
+    P.buf = buf_dev; P.cnt = cnt_dev; P.cap = cap; P.id_base = id_base;
+    const size_t smem = (size_t)USTAGES * STAGE_BYTES + 256;
+    if ((e = cudaFuncSetAttribute(bq_umma_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    const long long tiles = ((d.n + UM - 1) / UM) * qtiles;
+    const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    bq_umma_filter_kernel<<<grid, UTHREADS, smem, s>>>(P);
+    g_launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace jv

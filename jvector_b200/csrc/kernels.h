@@ -76,7 +76,12 @@ size_t bq_imma_scratch_bytes(long long n, int nq, int W);
 // fully asynchronous on `s`: keys_out_dev [nq][k] best first with GLOBAL ids (row + id_base); *unresolved_dev = number of queries
 // the integer-threshold path could not resolve (a Hamming bin wider than the buffer) — the caller falls back for those batches
 cudaError_t launch_bq_topk_imma(const DataDesc &d, const float *queries_dev, int nq, int k, long long id_base, void *scratch_dev,
-                                long long *keys_out_dev, int *unresolved_dev, cudaStream_t s);
+                                long long *keys_out_dev, int *unresolved_dev, int sm_count, cudaStream_t s);
+// ---- bq_umma.cu: the filter pass of the same pipeline on tcgen05 (kind::i8, TMEM accumulators) ----
+bool bq_umma_supported(const DataDesc &d);
+size_t bq_umma_image_bytes(int nq, int W);
+cudaError_t launch_bq_umma_filter(const DataDesc &d, const uint32_t *qbits_dev, int nq, int nq_pad, const int *t2_dev, const int *pb_dev, long long *buf_dev,
+                                  int *cnt_dev, int cap, long long id_base, uint8_t *images_dev, int sm_count, cudaStream_t s);
 
 // FusedPQ.writeInline (FusedPQ.java:122-141) for every node: records[node] = ids + the neighbours' code rows in neighbour order
 cudaError_t launch_fuse_pq(const GraphDesc &g, const DataDesc &pq, uint8_t *records_dev, int rec_bytes, cudaStream_t s);

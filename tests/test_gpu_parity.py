@@ -262,6 +262,16 @@ def test_bq_bruteforce_tensor_core_contraction_exact(jv, oracle, dim, n, nq, k):
     bqv.close()
 
 
+def test_bq_bruteforce_tcgen05_filter_exact(jv):
+    # the same top-k with the filter pass on tcgen05 (kind::i8, TMEM accumulators, csrc/bq_umma.cu), in its own process
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, "umma_check.py")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "UMMA_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_bq_bruteforce_giant_tie_bin_falls_back_exactly(jv, oracle):
     # 11 000 copies of one row: for the query equal to that row, Hamming bin 0 alone is wider than the capture buffer, the
     # integer-threshold path reports the query unresolved and the key-threshold kernels must produce the exact answer
