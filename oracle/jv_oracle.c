@@ -1503,7 +1503,12 @@ typedef struct { int32_t *nodes; float *scores; int size; int diverseBefore; } n
 
 static float pair_score(int metric, const float *base, int dim, int a, int b)
 {
-    return jvo_compare_f32(metric, base + (size_t)a * dim, base + (size_t)b * dim, dim);
+    const float *x = base + (size_t)a * dim, *y = base + (size_t)b * dim;
+    if (REF.h) { /* after jvo_use_ref: the reference's compiled kernels (build-quality comparisons at 100k+ nodes) */
+        float raw = metric == JVO_EUCLIDEAN ? REF.l2(x, 0, y, 0, (size_t)dim) : metric == JVO_DOT_PRODUCT ? REF.dot(x, 0, y, 0, (size_t)dim) : REF.cos(x, 0, y, 0, (size_t)dim);
+        return jvo_score_from_raw(metric, raw);
+    }
+    return jvo_compare_f32(metric, x, y, dim);
 }
 
 /* retainDiverse over a sorted candidate list, evaluating diversity scores lazily */
