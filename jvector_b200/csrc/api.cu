@@ -113,7 +113,7 @@ struct ThreadCtx {
 thread_local ThreadCtx t_ctxs[MAX_DEVICES];
 thread_local ThreadCtx *t_ctx_override = nullptr;  // worker threads of the multi-device entry points run on the shard's own context
 #define t_ctx (*(t_ctx_override ? t_ctx_override : &t_ctxs[t_active]))
-thread_local BuildStats t_build_stats = {0, 0, 0, 0};
+thread_local BuildStats t_build_stats = {0, 0, 0, 0, 0};
 
 int round4(int v) { return (v + 3) & ~3; }
 
@@ -1148,6 +1148,7 @@ static int make_filter(const jv_search_options *opts, jv_graph g, int nq, bool b
     if (opts->threshold < 0.f || opts->rerank_floor < 0.f || opts->accept_stride_words < 0) return fail(JV_ERR_INVALID, "graph_search: negative threshold / rerankFloor / stride");
     f->threshold = opts->threshold;
     f->rerank_floor = opts->rerank_floor;
+    f->lenient = 0;
     f->accept_stride_words = opts->accept_stride_words;
     if (opts->accept_bits) {
         const size_t words = ((size_t)g->g.n + 31) / 32;

@@ -634,7 +634,7 @@ struct GraphBuilder {
     int32_t *own_rp_rows = nullptr;
     int *own_rp_deg = nullptr;
     size_t own_rp_cap = 0;
-    BuildStats st = {0, 0, 0, 0};
+    BuildStats st = {0, 0, 0, 0, 0};
     size_t psmem = 0;
     int prune_grid = 0;
 };
@@ -753,8 +753,11 @@ cudaError_t builder_insert_slice(GraphBuilder *B, int first, int count, int lo, 
         JV_TRY(cudaMalloc(&B->scratch, need));
         B->scratch_bytes = need;
     }
+    SearchFilter lenient;
+    memset(&lenient, 0, sizeof(lenient));
+    lenient.lenient = 1;  // an insert search never fails the build: see SearchParams::lenient
     JV_TRY(launch_search(g, B->d, nullptr, B->metric, B->d.rows + (size_t)(first + lo) * B->d.stride, m, B->beam, B->beam, plan, B->scratch, B->work_counter,
-                         B->res_nodes, B->res_scores, B->counters, B->overflow, nullptr, B->d.stride, nullptr, s));
+                         B->res_nodes, B->res_scores, B->counters, B->overflow, nullptr, B->d.stride, &lenient, s));
     PruneParams P = prune_params(B);
     P.mode = 0; P.node_base = first + lo; P.count = m; P.cand = B->res_nodes; P.cand_stride = B->beam;
     P.window = B->window; P.batch_first = first; P.batch_count = count;
@@ -843,10 +846,9 @@ cudaError_t builder_finish(GraphBuilder *B, int32_t *adj_out_dev, BuildStats *st
     JV_TRY(cudaStreamSynchronize(s));
     B->st.searched = (long long)hc.visited;
     B->st.dropped_backlinks = (long long)hd;
+    B->st.truncated_searches = (long long)hc.overflowed;
     if (stats) *stats = B->st;
-    // an insert search that overflowed its visited table left its node without neighbours; the graph is still valid (the node is
-    // reachable through later back-links) but the caller is told
-    return hc.overflowed ? cudaErrorLaunchOutOfResources : cudaSuccess;
+    return cudaSuccess;
 }
 
 int builder_row_cap(const GraphBuilder *B) { return B->row_cap; }

@@ -107,6 +107,7 @@ struct SearchFilter {
     long long accept_stride_words;  // words between the bitsets of two queries; 0 = one bitset shared by the whole batch
     float threshold;                // minimum approximate score of a result; 0 = none
     float rerank_floor;             // NodeQueue.rerank's rerankFloor; 0 = none
+    int lenient;                    // builder only: overflowing walks are cut short and counted instead of failing
 };
 cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const GraphDesc &g, int topK, int rerankK, int nq,
                         int visited_cap_hint, int list_cap_hint, int sm_count, SearchPlan *plan);
@@ -125,6 +126,7 @@ struct BuildParams {
 };
 struct BuildStats {
     long long searched, pruned, dropped_backlinks, batches;
+    long long truncated_searches;  // insert searches cut short by a full visited table / an oversized tie tail (pathological inputs)
 };
 // flat Vamana graph over rows [0, n) of an f32 data set; adj_out_dev [n][degree] (-1 padded); entry node is 0
 cudaError_t build_graph_flat(const DataDesc &f32, int metric, const BuildParams &bp, int32_t *adj_out_dev, int sm_count,

@@ -54,6 +54,8 @@ struct SearchParams {
     long long accept_stride;      // words between two queries' bitsets (0 = one bitset shared by the batch)
     float threshold, rerank_floor;
     int filtered;                 // accept_bits != nullptr || threshold > 0
+    int lenient;                  // insert searches of the builder: a full visited table ends the walk with what it has, a tie tail
+                                  // that does not fit is dropped — counted in counters->overflowed, never an error (build.cu)
     unsigned long long *dbg;  // JV_SEARCH_PROFILE builds only: per-phase cycle totals
 };
 
@@ -238,9 +240,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
         int table_cnt = 1;
         unsigned visited = 0, expanded = 0, expanded_base = 0;
         int failed = 0;  // 1: visited table full, 2: candidate list too short for a tie tail
+        bool truncated = false, inexact = false;  // lenient mode: the walk was cut short / a tie tail was dropped
         __syncthreads();
 
-        for (int lvl = P.g.entry_level; lvl >= 0 && !failed; --lvl) {
+        for (int lvl = P.g.entry_level; lvl >= 0 && !failed && !truncated; --lvl) {
             const int K = lvl > 0 ? 1 : L;
             // a new level: results + evicted are candidates again (setEntryPointsFromPreviousLayer), the result heap is empty
             for (int i = tid; i < size; i += SEARCH_THREADS) fcur[i] &= F_ACCEPTED;
@@ -339,7 +342,11 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                 if (tid == 0) { s_drop = INT_MIN; s_cnt = 0; }
                 const int n = s_n;
                 table_cnt += n;
-                if (table_cnt * 2 > P.visited_cap) { failed = 1; break; }
+                if (table_cnt * 2 > P.visited_cap) {
+                    if (P.lenient) truncated = true;
+                    else failed = 1;
+                    break;
+                }
                 if (KIND == KIND_F32) {
                     // two rows per warp at a time: twice the loads in flight, query fragment read once
                     for (int i = group; i < n; i += 2 * NG) {
@@ -446,7 +453,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                         __syncthreads();
                         ok = s_cnt >= L;
                     }
-                    if (!ok) { failed = 2; break; }
+                    if (!ok) {
+                        if (P.lenient) inexact = true;  // keep walking: only the exactness of tie handling is lost
+                        else { failed = 2; break; }
+                    }
                 }
                 { long long *t = cur; cur = nxt; nxt = t; }
                 { uint8_t *t = fcur; fcur = fnxt; fnxt = t; }
@@ -464,7 +474,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
             for (int i = tid; i < P.topK; i += SEARCH_THREADS) { no[i] = -1; so[i] = 0.f; }
             if (tid == 0) { P.overflow[qi] = (uint8_t)failed; atomicAdd(&P.counters->overflowed, 1ull); }
         } else {
-            if (tid == 0) P.overflow[qi] = 0;
+            if (tid == 0) {
+                P.overflow[qi] = 0;
+                if (truncated || inexact) atomicAdd(&P.counters->overflowed, 1ull);
+            }
             const int hs = s_hsize;  // the results: heap[1 .. hs]
             if (P.has_rerank) {
                 // NodeQueue.rerank (NodeQueue.java:168-230): rescore, in HEAP-ARRAY order, the results whose approximate score
@@ -744,6 +757,7 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
     P.threshold = filter ? filter->threshold : 0.f;
     P.rerank_floor = filter ? filter->rerank_floor : 0.f;
     P.filtered = (P.accept_bits != nullptr || P.threshold > 0.f) ? 1 : 0;
+    P.lenient = filter ? filter->lenient : 0;
     P.query_stride = query_stride > 0 ? query_stride : approx.dim;
     P.g = g;
     if (!(approx.kind == KIND_PQ && g.fused && g.fused_codes_of == approx.codes && g.fused_code_stride == approx.code_stride)) P.g.fused = nullptr;
