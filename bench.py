@@ -692,7 +692,7 @@ def bench_c5(cx):
     n, dim, nsub = a.c5_n, a.dim, 2
     t0 = time.time()
     base = gen_unit_rows_device(torch, SEED + 50, n, dim, a.dist)
-    qd = gen_unit_rows_device(torch, SEED + 51, 500, dim, a.dist)
+    qd = gen_unit_rows_device(torch, SEED + 51, 200, dim, a.dist)
     queries = qd.cpu().numpy()
     vec = cx.adopt(base)
     mean_d = base.mean(0)
@@ -820,7 +820,9 @@ def main():
         base, gh = w.base_host(), w.graph_host()
         ncpu = os.cpu_count() or 1
         probe = cpu_search(base, gh, w.queries[:max(64, 2 * ncpu)], topK, rerankK, int(VSF.DOT_PRODUCT), None)
-        nqs = int(min(args.nq, max(200, probe["qps"] * args.cpu_budget)))  # a bounded sample of the step per timed step
+        # a bounded sample of the step per timed step: the whole K + W run stays within ~2 minutes of CPU time
+        per_step = min(args.cpu_budget, 120.0 / (args.steps + args.warmup))
+        nqs = int(min(args.nq, max(200, probe["qps"] * per_step)))
         for _ in range(args.warmup):
             cpu_search(base, gh, w.queries[:max(64, nqs // 10)], topK, rerankK, int(VSF.DOT_PRODUCT), None)
         secs, scored, last = 0.0, 0, None
