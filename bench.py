@@ -455,13 +455,18 @@ def host_driven_seam(cx, w):
     out = {"single_hop_32_candidates_us": hop_us}
     # persistent query handles: blobs stay in HBM across steps, a step uploads ids + offsets only
     qb = jv.QueryBatch(w.vec, w.queries[:mq], VSF.DOT_PRODUCT)
-    qb.score_step(mids, off)
+    sc_out = np.empty(len(mids), np.float32)
+    for x in (mids, sc_out):  # the caller's hop buffers are pinned once, as a JVM would keep them off-heap
+        cx.lib.jv_host_register(x.ctypes.data, x.nbytes)
+    qb.score_step(mids, off, out=sc_out)
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(10):
-        _, ms = qb.score_step(mids, off, return_ms=True)
+        _, ms = qb.score_step(mids, off, return_ms=True, out=sc_out)
         dev_ms += ms
     step_s = (time.perf_counter() - t0) / 10
+    for x in (mids, sc_out):
+        cx.lib.jv_host_unregister(x.ctypes.data)
     peak, _ = measured_peaks()
     out["multi_query_step"] = {"queries": mq, "candidates_per_query": 32, "e2e_ms": 1e3 * step_s, "scored_vectors_per_sec_e2e": mq * 32 / step_s,
                                "device_ms": dev_ms / 10, "score_ragged_kernel_GBps": mq * 32 * (a.dim * 4 + 8) / (dev_ms / 10 / 1e3) / 1e9,

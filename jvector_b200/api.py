@@ -178,11 +178,13 @@ class QueryBatch:
         self._h = C.c_void_p()
         check(lib.jv_query_batch_begin(vectors._h, int(vsf), fp(queries), self.nq, C.byref(self._h)))
 
-    def score_step(self, ids, offsets, return_ms=False):
-        """one step of all searches: query i scores ids[offsets[i]:offsets[i+1]] (one launch)"""
+    def score_step(self, ids, offsets, return_ms=False, out=None):
+        """one step of all searches: query i scores ids[offsets[i]:offsets[i+1]] (one launch). `ids` / `out` that were pinned with
+        jv_host_register are used in place (no staging copy)."""
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         offsets = np.ascontiguousarray(offsets, dtype=np.int32)
-        out = np.empty(len(ids), dtype=np.float32)
+        if out is None:
+            out = np.empty(len(ids), dtype=np.float32)
         ms = C.c_double()
         check(nat.load().jv_query_batch_score(self._h, ip(ids), ip(offsets), fp(out), C.byref(ms)))
         return (out, ms.value) if return_ms else out

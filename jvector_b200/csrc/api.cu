@@ -1572,17 +1572,25 @@ int jv_query_batch_score(jv_query_batch b, const int32_t *ids, const int32_t *of
     if (total <= 0) return JV_OK;
     int rc = query_batch_staging(b, (size_t)total, (size_t)nq + 1);
     if (rc) return rc;
-    memcpy(b->h_ids, ids, (size_t)total * 4);
+    // caller buffers that are already pinned (jv_host_register / cudaHostAlloc) are copied from / to directly; pageable ones go
+    // through the batch's own pinned staging so that the copies stay asynchronous and full speed
+    auto pinned = [](const void *p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool ids_pinned = pinned(ids), out_pinned = pinned(scores_out);
+    if (!ids_pinned) memcpy(b->h_ids, ids, (size_t)total * 4);
     memcpy(b->h_off, offsets, ((size_t)nq + 1) * 4);
     cudaStream_t s = b->stream;
-    CK(cudaMemcpyAsync(b->d_ids, b->h_ids, (size_t)total * 4, cudaMemcpyHostToDevice, s), "H2D ids");
+    CK(cudaMemcpyAsync(b->d_ids, ids_pinned ? ids : b->h_ids, (size_t)total * 4, cudaMemcpyHostToDevice, s), "H2D ids");
     CK(cudaMemcpyAsync(b->d_off, b->h_off, ((size_t)nq + 1) * 4, cudaMemcpyHostToDevice, s), "H2D offsets");
     CK(cudaEventRecord(b->ev0, s), "event");
     CK(launch_score_ragged(b->ds->d, b->metric, b->blobs, nq, b->d_ids, b->d_off, 0, maxc, b->d_scores, s), "score_ragged");
     CK(cudaEventRecord(b->ev1, s), "event");
-    CK(cudaMemcpyAsync(b->h_scores, b->d_scores, (size_t)total * 4, cudaMemcpyDeviceToHost, s), "D2H scores");
+    CK(cudaMemcpyAsync(out_pinned ? scores_out : b->h_scores, b->d_scores, (size_t)total * 4, cudaMemcpyDeviceToHost, s), "D2H scores");
     CK(cudaStreamSynchronize(s), "sync");
-    memcpy(scores_out, b->h_scores, (size_t)total * 4);
+    if (!out_pinned) memcpy(scores_out, b->h_scores, (size_t)total * 4);
     if (device_ms) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, b->ev0, b->ev1);
