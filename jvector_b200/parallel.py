@@ -125,6 +125,47 @@ def gpu_sharded_bruteforce(dist, vectors, vsf, id_base):
     return sb
 
 
+class SliceExchange:
+    """The exchange step of the sharded build: `count` items of `width` int32 each (+ one int32 per item) are produced slice-wise —
+    rank r fills positions [r * chunk, (r + 1) * chunk) with chunk = ceil(count / world) — and all-gathered so that every rank
+    holds positions 0 .. count-1 in order. produce(lo, hi, rows_ptr, deg_ptr) receives pointers to a VIRTUAL [count][width] /
+    [count] array of which only rows lo .. hi-1 exist (they are rows 0 .. of this rank's send buffer), which is the contract of
+    jv_builder_insert_slice / jv_builder_reprune_slice."""
+
+    def __init__(self, dist, device):
+        self.dist = dist
+        self.device = device
+        self.world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.bufs = {}
+        self.exchanged_bytes = 0
+
+    def _buf(self, name, rows, width):
+        import torch
+        t = self.bufs.get(name)
+        if t is None or t.shape[0] < rows:
+            t = torch.empty((max(rows, 1) + max(rows, 1) // 4, width), dtype=torch.int32, device=self.device)
+            self.bufs[name] = t
+        return t
+
+    def run(self, count, width, produce):
+        import ctypes as C
+
+        from . import _native as nat
+        world, rank = self.world, self.rank
+        chunk = (count + world - 1) // world
+        lo, hi = min(count, rank * chunk), min(count, (rank + 1) * chunk)
+        send, sdeg = self._buf("send%d" % width, chunk, width), self._buf("sdeg", chunk, 1)
+        nat.check(produce(lo, hi, C.c_void_p(send.data_ptr() - lo * width * 4), C.c_void_p(sdeg.data_ptr() - lo * 4)))
+        if world == 1:
+            return send, sdeg
+        allr, alld = self._buf("all%d" % width, world * chunk, width), self._buf("alld", world * chunk, 1)
+        self.dist.all_gather_into_tensor(allr[:world * chunk], send[:chunk])
+        self.dist.all_gather_into_tensor(alld[:world * chunk], sdeg[:chunk])
+        self.exchanged_bytes += world * chunk * (width + 1) * 4
+        return allr, alld
+
+
 def sharded_build(dist, vectors, vsf, M=32, beamWidth=100, neighborOverflow=1.2, alpha=1.2, addHierarchy=True, seed=0, max_batch=0, concurrent_window=-1):
     """GraphIndexBuilder.build with the insert scoring SHARDED over the ranks of `dist` (BASELINE config 5).
 
@@ -149,30 +190,10 @@ def sharded_build(dist, vectors, vsf, M=32, beamWidth=100, neighborOverflow=1.2,
     deg_, cap_, mb_ = C.c_int(), C.c_int(), C.c_int()
     nat.check(lib.jv_builder_info(b, C.byref(deg_), C.byref(cap_), C.byref(mb_)))
     degree, row_cap, mb = deg_.value, cap_.value, mb_.value
-    exchanged = [0]
-    bufs = {}
-
-    def buf(name, rows, width):
-        t = bufs.get(name)
-        if t is None or t.shape[0] < rows:
-            t = torch.empty((max(rows, 1) + max(rows, 1) // 4, width), dtype=torch.int32, device="cuda")
-            bufs[name] = t
-        return t
+    ex = SliceExchange(dist, "cuda")
 
     def exchange(count, width, produce):
-        """slice-wise produce(lo, hi, rows_ptr, deg_ptr) on this rank, all-gather, return (rows_all, deg_all) holding positions 0..count-1"""
-        chunk = (count + world - 1) // world
-        lo, hi = min(count, rank * chunk), min(count, (rank + 1) * chunk)
-        send, sdeg = buf("send%d" % width, chunk, width), buf("sdeg", chunk, 1)
-        # the C call writes batch positions lo..hi-1 of a [count][width] array: point it so that position lo is row 0 of the send buffer
-        nat.check(produce(lo, hi, C.c_void_p(send.data_ptr() - lo * width * 4), C.c_void_p(sdeg.data_ptr() - lo * 4)))
-        if world == 1:
-            return send, sdeg
-        allr, alld = buf("all%d" % width, world * chunk, width), buf("alld", world * chunk, 1)
-        dist.all_gather_into_tensor(allr[:world * chunk], send[:chunk])
-        dist.all_gather_into_tensor(alld[:world * chunk], sdeg[:chunk])
-        exchanged[0] += world * chunk * (width + 1) * 4
-        return allr, alld
+        return ex.run(count, width, produce)
 
     def reprune_round(L):
         if L <= 0:
@@ -197,4 +218,4 @@ def sharded_build(dist, vectors, vsf, M=32, beamWidth=100, neighborOverflow=1.2,
         nat.check(lib.jv_builder_finish(b, C.byref(g), C.byref(ms)))
     finally:
         lib.jv_builder_free(b)
-    return GraphIndex(_handle=g), ms.value, exchanged[0]
+    return GraphIndex(_handle=g), ms.value, ex.exchanged_bytes

@@ -75,3 +75,46 @@ def test_shard_ranges_and_rebase():
     m = par.merge_keys_host(g, 3)
     nodes, scores = par.keys_to_nodes_scores(m)
     assert nodes.tolist() == [[4, 9, 2]] and scores[0, 0] == np.float32(0.5)
+
+
+def _exchange_worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from jvector_b200 import parallel as par
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ex = par.SliceExchange(dist, "cpu")
+    ok = True
+    for count, width in ((1, 3), (2, 3), (5, 4), (8, 4), (7, 64), (16384, 32)):
+        def produce(lo, hi, rows_ptr, deg_ptr):
+            # what jv_builder_insert_slice does: write rows lo .. hi-1 of a virtual [count][width] array and of a [count] array
+            rows = (C.c_int32 * (count * width)).from_address(rows_ptr.value) if lo == 0 else None
+            for pos in range(lo, hi):
+                row = (C.c_int32 * width).from_address(rows_ptr.value + pos * width * 4)
+                for j in range(width):
+                    row[j] = pos * 1000 + j
+                C.c_int32.from_address(deg_ptr.value + pos * 4).value = pos + 7
+            return 0
+        rows, deg = ex.run(count, width, produce)
+        want_rows = (torch.arange(count)[:, None] * 1000 + torch.arange(width)[None, :]).to(torch.int32)
+        ok = ok and bool(torch.equal(rows[:count], want_rows)) and bool(torch.equal(deg[:count, 0], (torch.arange(count) + 7).to(torch.int32)))
+    with open(os.path.join(tmp, "ex%d.ok" % rank), "w") as f:
+        f.write("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slice_exchange_gloo_world2(tmp_path):
+    # the exchange step of the sharded build (jvector_b200/parallel.py SliceExchange): every rank produces its slice through the
+    # pointer contract of jv_builder_insert_slice, after the all-gather every rank holds all positions in order — including
+    # counts that do not divide by the world size and counts smaller than it
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_exchange_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(tmp_path / ("ex%d.ok" % r)).read() == "1"
