@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
     uint8_t *flags0 = cand_slot + MAX_DEGREE;
     uint8_t *flags1 = flags0 + P.list_alloc;
     __shared__ float red[36];
-    __shared__ int s_q, s_n, s_hsize, s_drop, s_cnt;
+    __shared__ int s_q, s_n, s_m, s_hsize, s_cnt;
+    __shared__ int s_drop[2];  // best sortable score that fell off the list, double-buffered like s_posv
     __shared__ int s_posv[2];
 
     const int tid = threadIdx.x;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
             // a new level: results + evicted are candidates again (setEntryPointsFromPreviousLayer), the result heap is empty
             for (int i = tid; i < size; i += SEARCH_THREADS) fcur[i] &= F_ACCEPTED;
             int sel = 0;
-            if (tid == 0) { s_posv[0] = 0; s_posv[1] = INT_MAX; s_n = 0; s_hsize = 0; s_drop = INT_MIN; s_cnt = 0; }
+            if (tid == 0) { s_posv[0] = 0; s_posv[1] = INT_MAX; s_n = 0; s_m = 0; s_hsize = 0; s_drop[0] = INT_MIN; s_drop[1] = INT_MIN; s_cnt = 0; }
             __syncthreads();
             for (;;) {
                 const int p = s_posv[sel];  // first unexpanded entry = the top of the candidate queue
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                 int action = 0;
                 if (lvl > 0 || (fcur[p] & F_ACCEPTED)) action = hs < K ? 1 : (csc > wsc ? 2 : 3);
                 const int dead = (lvl > 0 && action == 3) ? p : -1;
-                if (tid == 0) { fcur[p] |= F_EXPANDED; s_posv[sel ^ 1] = INT_MAX; }
+                if (tid == 0) { fcur[p] |= F_EXPANDED; s_posv[sel ^ 1] = INT_MAX; s_m = 0; }
                 expanded++;
                 if (lvl == 0) expanded_base++;
                 const int32_t *nb;
@@ -277,7 +278,14 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                 // expanded node's own record
                 const bool fused = KIND == KIND_PQ && lvl == 0 && P.g.fused != nullptr;
                 const uint8_t *rec = fused ? P.g.fused + (size_t)node * P.g.fused_rec : nullptr;
-                if (fused) nb = reinterpret_cast<const int32_t *>(rec);
+                if (fused) {
+                    nb = reinterpret_cast<const int32_t *>(rec);
+                    // the code rows of this record are needed one barrier from now: pull the whole record towards L2 at once
+                    if (tid >= 64) {
+                        const int o = (tid - 64) * 128;
+                        if (o < P.g.fused_rec) prefetch_l2(rec + o);
+                    }
+                }
                 // processNeighbors: score a neighbour only if visited.add() says it is new (OnHeapGraphIndex.java:478)
                 if (nb)
                     for (int t = tid; t < degree; t += SEARCH_THREADS) {
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                         heap_down(heap, hs, 1);
                     }
                 }
-                if (tid == 0) { s_drop = INT_MIN; s_cnt = 0; }
+                if (tid == 0) { s_drop[sel ^ 1] = INT_MIN; s_cnt = 0; }
                 const int n = s_n;
                 table_cnt += n;
                 if (table_cnt * 2 > P.visited_cap) {
@@ -347,6 +355,20 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                     else failed = 1;
                     break;
                 }
+                // A candidate that scores under the last entry of a FULL list is dropped by the merge whatever the other candidates do, so
+                // it is dropped here and the merge only ranks the survivors (late in a walk that is most of them).
+                // (the list's last key is re-read from shared memory by the one lane that needs it: nothing extra lives in registers
+                // across the scoring loop)
+#define JV_EMIT(sc_, f_)                                                                                                            \
+    do {                                                                                                                            \
+        const long long key_ = topk_key((sc_), (f_));                                                                               \
+        if (dead < 0 && size == LC && key_ < cur[LC - 1]) atomicMax(&s_drop[sel], float_to_sortable(sc_));                          \
+        else {                                                                                                                      \
+            const int m_ = atomicAdd(&s_m, 1);                                                                                      \
+            cand_keys[m_] = key_;                                                                                                   \
+            if (P.filtered) cand_acc[m_] = ((!acc || ((acc[(f_) >> 5] >> ((f_) & 31)) & 1u)) && (sc_) >= P.threshold) ? F_ACCEPTED : 0; \
+        }                                                                                                                           \
+    } while (0)
                 if (KIND == KIND_F32) {
                     // two rows per warp at a time: twice the loads in flight, query fragment read once
                     for (int i = group; i < n; i += 2 * NG) {
@@ -356,12 +378,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                         float sa, sb;
                         score_f32_pair<METRIC>(P.approx, blobA, fa, fb, lane, sa, sb);
                         if (lane == 0) {
-                            cand_keys[i] = topk_key(sa, fa);
-                            if (two) cand_keys[i + NG] = topk_key(sb, fb);
-                            if (P.filtered) {
-                                cand_acc[i] = ((!acc || ((acc[fa >> 5] >> (fa & 31)) & 1u)) && sa >= P.threshold) ? F_ACCEPTED : 0;
-                                if (two) cand_acc[i + NG] = ((!acc || ((acc[fb >> 5] >> (fb & 31)) & 1u)) && sb >= P.threshold) ? F_ACCEPTED : 0;
-                            }
+                            JV_EMIT(sa, fa);
+                            if (two) JV_EMIT(sb, fb);
                         }
                     }
                 } else if (KIND == KIND_PQ && fused) {
@@ -370,41 +388,37 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                     for (int i = group; i < n; i += NG) {
                         const int32_t f = cand_ids[i];
                         const float sc = score_pq_codes<METRIC>(P.approx, blobA, codes0 + (size_t)cand_slot[i] * P.g.fused_code_stride, lane, blobH, splitm);
-                        if (lane == 0) {
-                            cand_keys[i] = topk_key(sc, f);
-                            if (P.filtered) cand_acc[i] = ((!acc || ((acc[f >> 5] >> (f & 31)) & 1u)) && sc >= P.threshold) ? F_ACCEPTED : 0;
-                        }
+                        if (lane == 0) JV_EMIT(sc, f);
                     }
                 } else {
                     for (int i = group; i < n; i += NG) {
                         const int32_t f = cand_ids[i];
                         const float sc = KIND == KIND_PQ ? score_pq<METRIC>(P.approx, blobA, f, lane, blobH, splitm) : score_row<KIND, METRIC>(P.approx, blobA, f, lane);
-                        if (lane == 0) {
-                            cand_keys[i] = topk_key(sc, f);
-                            if (P.filtered) cand_acc[i] = ((!acc || ((acc[f >> 5] >> (f & 31)) & 1u)) && sc >= P.threshold) ? F_ACCEPTED : 0;
-                        }
+                        if (lane == 0) JV_EMIT(sc, f);
                     }
                 }
+#undef JV_EMIT
                 __syncthreads();
                 JV_T(t_i2);
                 JV_ACC(2, t_i1, t_i2);
                 visited += n;
+                const int nm = s_m;  // candidates that survived the pre-filter
                 // rank-merge (old list is sorted; candidates are few): every element computes its slot directly and the
                 // first unexpanded slot of the next list falls out of the same pass. The entry at `dead` (refused on an
                 // upper level) leaves the list.
                 const int live = size - (dead >= 0 ? 1 : 0);
-                const int newsize = min(LC, live + n);
+                const int newsize = min(LC, live + nm);
                 const long long dead_key = dead >= 0 ? cur[dead] : KEY_MIN;
                 int mypos = INT_MAX, mydrop = INT_MIN;
                 // one work item per thread: items [0, size) are old entries, [size, size + n) the new candidates, so the
                 // two kinds run on different warps instead of back to back on warp 0
-                for (int it = tid; it < size + n; it += SEARCH_THREADS) {
+                for (int it = tid; it < size + nm; it += SEARCH_THREADS) {
                     if (it < size) {
                         if (it == dead) continue;
                         const long long k = cur[it];
                         int c = 0;
 #pragma unroll 8
-                        for (int j = 0; j < n; j++) c += (cand_keys[j] > k);
+                        for (int j = 0; j < nm; j++) c += (cand_keys[j] > k);
                         const int np = it + c - ((dead >= 0 && it > dead) ? 1 : 0);
                         const uint8_t fl = fcur[it];
                         if (np < LC) {
@@ -416,7 +430,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                         const long long k = cand_keys[it - size];
                         int c = count_greater_desc(cur, size, k) - ((dead >= 0 && dead_key > k) ? 1 : 0);
 #pragma unroll 8
-                        for (int jj = 0; jj < n; jj++) c += (cand_keys[jj] > k);
+                        for (int jj = 0; jj < nm; jj++) c += (cand_keys[jj] > k);
                         if (c < LC) {
                             nxt[c] = k;
                             fnxt[c] = P.filtered ? cand_acc[it - size] : F_ACCEPTED;
@@ -431,7 +445,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                     }
                 }
                 if (mypos != INT_MAX) atomicMin(&s_posv[sel ^ 1], mypos);
-                if (mydrop != INT_MIN) atomicMax(&s_drop, mydrop);
+                if (mydrop != INT_MIN) atomicMax(&s_drop[sel], mydrop);
                 if (tid == 0) s_n = 0;
                 __syncthreads();
                 JV_T(t_i3);
@@ -441,7 +455,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
 #endif
                 // something fell off the end of the list: that is exact only if at least rerankK accepted entries score strictly
                 // higher than everything dropped (then none of it can be popped before stopSearch fires)
-                const int dm = s_drop;
+                const int dm = s_drop[sel];
                 if (dm != INT_MIN) {
                     bool ok;
                     if (!P.filtered) ok = float_to_sortable(key_score(nxt[L - 1])) > dm;  // newsize == LC >= L here
@@ -645,7 +659,11 @@ static cudaError_t occupancy_of(size_t smem, int *blocks_per_sm)
 
 #define JV_SEARCH_DISPATCH(kind, metric, pq_wide, CALL)                                                  \
     do {                                                                                        \
-        if ((kind) == KIND_F32) {                                                               \
+        if ((kind) == KIND_F32 && (pq_wide)) {                                                  \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN, MINB_PQ_WIDE); } \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT, MINB_PQ_WIDE); } \
+            else { CALL(KIND_F32, JV_METRIC_COSINE, MINB_PQ_WIDE); }                            \
+        } else if ((kind) == KIND_F32) {                                                        \
             if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN, MINB_DEFAULT); }       \
             else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT, MINB_DEFAULT); }              \
             else { CALL(KIND_F32, JV_METRIC_COSINE, MINB_DEFAULT); }                                          \
@@ -727,6 +745,14 @@ cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const Gr
         bw = bps;
         if (e == cudaSuccess && bw >= lite) plan->pq_wide = 1;
         else bps = lite;
+    }
+    if (e == cudaSuccess && approx.kind == KIND_F32) {
+        // JV_SEARCH_WIDE=1: the 64-register build of the fp32 walk (4 resident CTAs per SM instead of 5, no spills) — a tuning knob
+        const char *w = getenv("JV_SEARCH_WIDE");
+        if (w && w[0] == '1') {
+            plan->pq_wide = 1;
+            JV_SEARCH_DISPATCH(approx.kind, metric_for_occ, true, CALL);
+        }
     }
 #undef CALL
     if (e != cudaSuccess) return e;

@@ -51,7 +51,11 @@ def run(approx, rr, label):
 
 
 if a.sweep or a.workload == "c2":
-    run(w.vec, None, "c2 fp32 walk")
+    run(w.vec, None, "c2 fp32 walk (48 registers, 5 CTAs/SM)")
+    if a.sweep:
+        os.environ["JV_SEARCH_WIDE"] = "1"
+        run(w.vec, None, "c2 fp32 walk (64 registers, 4 CTAs/SM)")
+        del os.environ["JV_SEARCH_WIDE"]
 if a.sweep or a.workload == "c3":
     import oracle_lib as o
     rs = np.random.default_rng(bench.SEED + 99)
