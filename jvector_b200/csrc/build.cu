@@ -464,7 +464,17 @@ __global__ void __launch_bounds__(256) apply_rows_kernel(int32_t *adj, int *deg,
     const int32_t t = j < degree ? rows[(size_t)i * degree + j] : -1;
     adj[(size_t)u * row_cap + j] = t;
     if (j == 0) deg[u] = rdeg[i];
-    if (j < degree) pairs[(size_t)i * degree + j] = t >= 0 ? (((unsigned long long)(unsigned)t << 32) | (unsigned)u) : ~0ull;  // ~0 sorts last
+    if (j < degree) {
+        bool link = t >= 0;
+        if (link && t >= first && t < first + count) {
+            // t was inserted in this very batch and may have chosen u itself (both sit in each other's in-progress window): then u is
+            // already in t's row and the back-link would duplicate it (NodeArray.insertSorted refuses duplicates)
+            const int32_t *trow = rows + (size_t)(t - first) * degree;
+            for (int x = 0; x < degree; x++)
+                if (trow[x] == u) { link = false; break; }
+        }
+        pairs[(size_t)i * degree + j] = link ? (((unsigned long long)(unsigned)t << 32) | (unsigned)u) : ~0ull;  // ~0 sorts last
+    }
 }
 
 __device__ __forceinline__ int lower_bound_u64(const unsigned long long *a, int n, unsigned long long key)
