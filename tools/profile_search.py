@@ -20,7 +20,7 @@ import bench  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--sweep", action="store_true")
-ap.add_argument("--workload", default="c3", choices=["c2", "c3"])
+ap.add_argument("--workload", default="c3", choices=["c2", "c3", "seam"])
 ap.add_argument("--n", type=int, default=1_000_000)
 ap.add_argument("--nq", type=int, default=10_000)
 ap.add_argument("--reps", type=int, default=3)
@@ -50,6 +50,21 @@ def run(approx, rr, label):
     return best
 
 
+if a.workload == "seam":
+    # the host-driven multi-query step (jv_query_batch_score -> score_ragged_kernel): 10 000 searches x 32 candidates
+    rs = np.random.default_rng(bench.SEED + 3)
+    mq = min(a.nq, 10000)
+    off = np.arange(mq + 1, dtype=np.int32) * 32
+    mids = rs.integers(0, a.n, mq * 32).astype(np.int32)
+    qb = jv.QueryBatch(w.vec, w.queries[:mq], VSF.DOT_PRODUCT)
+    qb.score_step(mids, off)
+    if a.ncu:
+        cx.torch.cuda.cudart().cudaProfilerStart()
+    _, ms = qb.score_step(mids, off, return_ms=True)
+    if a.ncu:
+        cx.torch.cuda.cudart().cudaProfilerStop()
+    print("score_ragged_kernel: %.3f ms for %d x 32 rows = %.1f GB/s" % (ms, mq, mq * 32 * 3080 / ms / 1e6))
+    sys.exit(0)
 if a.sweep or a.workload == "c2":
     run(w.vec, None, "c2 fp32 walk (48 registers, 5 CTAs/SM)")
     if a.sweep:
