@@ -54,7 +54,9 @@ IMMA_PEAK_TOPS = 917.0  # tools/micro/imma_rate.cu on B200: legacy IMMA.16832 is
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed `ncu --set full` captures
 # under profiles/ ; key = (workload, n, nq, rerankK)
-NCU_TRAFFIC = {("c2", 1_000_000, 10_000, 100): 94.728e9}
+NCU_TRAFFIC = {("c2", 1_000_000, 10_000, 100): 95.311e9,   # profiles/r2_ncu_search_c2.md
+               ("c3", 1_000_000, 10_000, 100): 26.292e9,   # profiles/r2_ncu_search_c3.md
+               ("c4", 1_000_000, 1000, 100): 0.211e9}      # profiles/r2_ncu_bq_imma.md (the filter launch)
 
 
 def log(*a):
@@ -472,14 +474,23 @@ def host_driven_seam(cx, w):
                                "device_ms": dev_ms / 10, "score_ragged_kernel_GBps": mq * 32 * (a.dim * 4 + 8) / (dev_ms / 10 / 1e3) / 1e9,
                                "score_ragged_kernel_frac_of_hbm_peak": mq * 32 * (a.dim * 4 + 8) / (dev_ms / 10 / 1e3) / 1e9 / peak,
                                "note": "jv_query_batch_score: prepared queries persist in HBM; H2D ids+offsets from pinned memory, D2H scores"}
-    h1 = qb.single(0)
-    for _ in range(50):
-        qb.score_one(0, ids32)
-    t0 = time.perf_counter()
-    for _ in range(500):
-        qb.score_one(0, ids32)
-    out["single_hop_32_candidates_pooled_handle_us"] = (time.perf_counter() - t0) / 500 * 1e6
-    del h1
+    # one hop of one search on the persistent handle, called the way a Panama / JNI binding calls it (raw pointers, no per-call
+    # array conversion): the library spins on a completion word in mapped memory instead of synchronising the stream
+    import ctypes as C
+    fn = cx.lib.jv_query_batch_score_one
+    hop_out = np.empty(32, np.float32)
+    idp, outp = ids32.ctypes.data_as(C.POINTER(C.c_int32)), hop_out.ctypes.data_as(C.POINTER(C.c_float))
+    for _ in range(200):
+        fn(qb._h, 0, idp, 32, outp)
+    lat = []
+    for _ in range(2000):
+        t0 = time.perf_counter_ns()
+        rc = fn(qb._h, 0, idp, 32, outp)
+        lat.append(time.perf_counter_ns() - t0)
+    lat = np.sort(np.array(lat, np.float64)) / 1e3
+    out["single_hop_32_candidates_pooled_handle_us"] = float(lat.mean())
+    out["single_hop_32_candidates_pooled_handle_us_p50_p99"] = [float(lat[len(lat) // 2]), float(lat[int(len(lat) * 0.99)])]
+    out["single_hop_matches_score_step"] = bool(rc == 0 and np.array_equal(hop_out, qb.score_one(0, ids32)))
     qb.close()
     return out
 
@@ -525,7 +536,7 @@ def bench_c3(cx, w, steps):
            "e2e": {"value": total_q / r["e2e_s"], "unit": "queries/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
            "gpu_launches": r["launches"],
            "roofline": {"kernel": "graph_search_kernel<PQ> (fused records)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "peak_source": peak_src, "adc_frac_of_code_stream_roofline": adc / (r["dev_ms"] / 1e3) / adc_roof,
+                        "traffic": NCU_TRAFFIC.get(("c3", a.n, a.nq, rerankK)), "peak_source": peak_src, "adc_frac_of_code_stream_roofline": adc / (r["dev_ms"] / 1e3) / adc_roof,
                         "note": "latency chain per hop (record -> visited CAS -> LUT gathers -> merge), not bandwidth bound; code-stream roofline = peak / M = %.1f G vec/s" % (adc_roof / 1e9)}}
     if cx.rank == 0 and not a.no_cpu:
         pq = {"codebooks": cb, "codes": codes, "M": M}
@@ -656,7 +667,8 @@ def bench_c4(cx, steps):
            "e2e": {"value": steps * nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(queries.nbytes), "d2h_bytes_per_step": int(nq * k * 8)},
            "gpu_launches": launches,
            "roofline": {"kernel": "bq_imma_kernel (IMMA.16832 u8)", "bound": "tensor", "achieved": ops / cx.world / dev_s / 1e12, "peak": IMMA_PEAK_TOPS, "unit": "TOP/s",
-                        "frac": ops / cx.world / dev_s / 1e12 / IMMA_PEAK_TOPS, "traffic": None,
+                        "frac": ops / cx.world / dev_s / 1e12 / IMMA_PEAK_TOPS,
+                        "traffic": NCU_TRAFFIC.get(("c4", n, nq, k)) if cx.world == 1 else None,
                         "peak_source": "measured issue rate of the legacy IMMA.16832 path on B200 (tools/micro/imma_rate.cu, profiles/r2_imma_rate.md); MEASURED_PEAKS.json has no integer entry",
                         "hbm_unique_GBps": float(steps) * (hi - lo) * W * 8 / dev_s / 1e9}}
     if cx.rank == 0 and not a.no_cpu:

@@ -1492,6 +1492,12 @@ struct jv_query_batch_s {
     size_t dcap = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // single-hop path: mapped pinned ids / scores / completion flag the kernel reads and writes directly, a device-side CTA counter
+    int32_t *hop_ids = nullptr, *hop_ids_dev = nullptr;
+    float *hop_scores = nullptr, *hop_scores_dev = nullptr;
+    int *hop_flag = nullptr, *hop_flag_dev = nullptr, *hop_done = nullptr;
+    size_t hop_cap = 0;
+    int hop_seq = 0;
 };
 
 static void query_batch_release(jv_query_batch_s *b)
@@ -1501,6 +1507,7 @@ static void query_batch_release(jv_query_batch_s *b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->blobs); cudaFree(b->d_ids); cudaFree(b->d_off); cudaFree(b->d_scores);
     cudaFreeHost(b->h_ids); cudaFreeHost(b->h_off); cudaFreeHost(b->h_scores);
+    cudaFreeHost(b->hop_ids); cudaFreeHost(b->hop_scores); cudaFreeHost(b->hop_flag); cudaFree(b->hop_done);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -1599,23 +1606,80 @@ int jv_query_batch_score(jv_query_batch b, const int32_t *ids, const int32_t *of
     return JV_OK;
 }
 
-// one hop of ONE search of the batch: the kernel reads the ids from, and writes the scores to, mapped pinned memory — one launch
-// and one stream synchronisation, no separate copies
+// one hop of ONE search of the batch. Latency path: the kernel reads the ids from, and writes the scores and a completion
+// sequence number to, mapped pinned memory; the host spins on that word instead of synchronising the stream (a blocking
+// cudaStreamSynchronize costs more than the launch and the kernel together), and polls the stream only to notice a failed launch.
 int jv_query_batch_score_one(jv_query_batch b, int query_index, const int32_t *ids, int n, float *scores_out)
 {
     ON_DEVICE_OF(b);
     if (query_index < 0 || query_index >= b->nq || n < 0 || (n > 0 && (!ids || !scores_out))) return fail(JV_ERR_INVALID, "query_batch_score_one: bad arguments");
     if (n == 0) return JV_OK;
-    int rc = query_batch_staging(b, (size_t)n, 2);
-    if (rc) return rc;
-    memcpy(b->h_ids, ids, (size_t)n * 4);
-    int32_t *dids = nullptr;
-    float *dsc = nullptr;
-    CK(cudaHostGetDevicePointer((void **)&dids, b->h_ids, 0), "cudaHostGetDevicePointer");
-    CK(cudaHostGetDevicePointer((void **)&dsc, b->h_scores, 0), "cudaHostGetDevicePointer");
-    CK(launch_score_ragged(b->ds->d, b->metric, b->blobs + (size_t)query_index * b->blob_floats, 1, dids, nullptr, n, n, dsc, b->stream), "score_ragged");
-    CK(cudaStreamSynchronize(b->stream), "sync");
-    memcpy(scores_out, b->h_scores, (size_t)n * 4);
+    if ((size_t)n > b->hop_cap) {
+        CK(cudaStreamSynchronize(b->stream), "sync");
+        cudaFreeHost(b->hop_ids); cudaFreeHost(b->hop_scores);
+        b->hop_ids = nullptr; b->hop_scores = nullptr; b->hop_cap = 0;
+        const size_t want = (size_t)n + 1024;
+        CK(cudaHostAlloc((void **)&b->hop_ids, want * 4, cudaHostAllocMapped), "cudaHostAlloc(hop ids)");
+        CK(cudaHostAlloc((void **)&b->hop_scores, want * 4, cudaHostAllocMapped), "cudaHostAlloc(hop scores)");
+        CK(cudaHostGetDevicePointer((void **)&b->hop_ids_dev, b->hop_ids, 0), "cudaHostGetDevicePointer");
+        CK(cudaHostGetDevicePointer((void **)&b->hop_scores_dev, b->hop_scores, 0), "cudaHostGetDevicePointer");
+        if (!b->hop_flag) {
+            CK(cudaHostAlloc((void **)&b->hop_flag, 64, cudaHostAllocMapped), "cudaHostAlloc(hop flag)");
+            CK(cudaHostGetDevicePointer((void **)&b->hop_flag_dev, b->hop_flag, 0), "cudaHostGetDevicePointer");
+            *b->hop_flag = 0;
+            CK(cudaMalloc((void **)&b->hop_done, 64), "cudaMalloc(hop counter)");
+            CK(cudaMemset(b->hop_done, 0, 64), "memset");
+        }
+        b->hop_cap = want;
+    }
+    const float *blob = b->blobs + (size_t)query_index * b->blob_floats;
+    if (n <= HOP_MAX_IDS) {
+        // ids in the kernel parameters, every score word pre-set to a pattern no score can have and polled until it is overwritten
+        volatile uint32_t *sc = reinterpret_cast<volatile uint32_t *>(b->hop_scores);
+        for (int i = 0; i < n; i++) sc[i] = 0xffffffffu;
+        __atomic_thread_fence(__ATOMIC_SEQ_CST);
+        CK(launch_score_hop(b->ds->d, b->metric, blob, ids, n, b->hop_scores_dev, b->stream), "score_hop");
+        unsigned spins = 0;
+        for (int i = 0; i < n; i++) {
+            while (sc[i] == 0xffffffffu) {
+                if ((++spins & 0x3fffu) == 0) {
+                    const cudaError_t e = cudaStreamQuery(b->stream);
+                    if (e == cudaSuccess) {
+                        if (sc[i] != 0xffffffffu) break;
+                        return fail(JV_ERR_CUDA, "query_batch_score_one: the kernel finished without writing its scores");
+                    }
+                    if (e != cudaErrorNotReady) return cuda_fail(e, "query_batch_score_one");
+                }
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        memcpy(scores_out, b->hop_scores, (size_t)n * 4);
+        return JV_OK;
+    }
+    memcpy(b->hop_ids, ids, (size_t)n * 4);
+    const int seq = ++b->hop_seq == 0 ? ++b->hop_seq : b->hop_seq;
+    // one lane group per id and 4 ids per CTA: the hop's rows are fetched in one wave instead of one CTA walking them in turn
+    CK(launch_score_ragged(b->ds->d, b->metric, blob, 1, b->hop_ids_dev, nullptr, n, n, b->hop_scores_dev, b->stream, 4, b->hop_done, b->hop_flag_dev, seq),
+       "score_ragged");
+    volatile int *flag = b->hop_flag;
+    for (unsigned spins = 1; *flag != seq; spins++) {
+        if ((spins & 0x3fffu) == 0) {
+            const cudaError_t e = cudaStreamQuery(b->stream);
+            if (e == cudaSuccess) {
+                if (*flag == seq) break;
+                return fail(JV_ERR_CUDA, "query_batch_score_one: the kernel finished without its completion signal");
+            }
+            if (e != cudaErrorNotReady) return cuda_fail(e, "query_batch_score_one");
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    memcpy(scores_out, b->hop_scores, (size_t)n * 4);
     return JV_OK;
 }
 

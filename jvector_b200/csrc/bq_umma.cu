@@ -8,10 +8,13 @@
 // warp tile; here the row tile is expanded ONCE per CTA tile into shared memory (producer warps), the query tile arrives as a
 // pre-expanded, pre-swizzled 32 KB image by one bulk copy, and one elected thread issues 128 x 256 x 32 MMAs.
 //
-// Roles (384 threads): warp 0 = B producer (cp.async.bulk of the query image chunk), warp 1 = MMA issuer + TMEM owner,
-// warps 4-7 = epilogue (tcgen05.ld: warp w may touch TMEM lanes 32 (w % 4) ..), warps 8-11 = A producers (bits -> bytes, swizzled
-// 128-bit stores, fence.proxy.async, arrive). Pipelines: full[s] / empty[s] over 4 operand stages of 48 KB, tmem_full[a] /
-// tmem_empty[a] over two 256-column accumulators, so the epilogue of one tile overlaps the MMAs of the next.
+// Roles (512 threads): warp 0 = B producer (cp.async.bulk of the query image chunk), warp 1 = MMA issuer + TMEM owner,
+// warps 4-7 = epilogue (tcgen05.ld: warp w may touch TMEM lanes 32 (w % 4) ..), warps 8-15 = A producers (two threads per row:
+// 64 bits -> 64 bytes each, swizzled 128-bit stores, fence.proxy.async, arrive). Pipelines: full[s] / empty[s] over 4 operand
+// stages of 48 KB, tmem_full[a] / tmem_empty[a] over two 256-column accumulators, so the epilogue of one tile overlaps the MMAs
+// of the next. The epilogue is branch-light: thresholds of the query tile sit in shared memory, a column costs LEA + ISETP, the
+// rare survivors (about 0.3 %) go to a shared-memory queue that the 128 epilogue threads flush together (one global atomic each)
+// — round-2 profile (profiles/r2_ncu_bq_umma.md): a per-element LDG + branch epilogue kept the MMA thread waiting half its time.
 // Every spin-wait is bounded and traps: a wrong barrier count aborts the launch instead of hanging the device.
 #include <limits.h>
 
@@ -25,11 +28,12 @@ constexpr int UM = 128;           // rows per tile (MMA M)
 constexpr int UN = 256;           // queries per tile (MMA N)
 constexpr int UKC = 128;          // K bytes per stage (one 128-byte swizzle atom wide)
 constexpr int USTAGES = 4;
-constexpr int UTHREADS = 384;
+constexpr int UTHREADS = 512;
 constexpr int A_STAGE_BYTES = UM * UKC;  // 16 KB
 constexpr int B_STAGE_BYTES = UN * UKC;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int N_A_PRODUCERS = 128;
+constexpr int N_A_PRODUCERS = 256;  // two threads per row
+constexpr int HIT_CAP = 1024;         // survivor queue of one tile (expected ~90 entries); overflow appends directly
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
@@ -120,6 +124,9 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
     uint64_t *tmem_full = empty + USTAGES;
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    int *s_nhits = reinterpret_cast<int *>(tmem_base_slot + 1);
+    int *s_t2 = reinterpret_cast<int *>(smem + USTAGES * STAGE_BYTES + 256);  // [UN] thresholds of the current query tile
+    int2 *s_hits = reinterpret_cast<int2 *>(s_t2 + UN);                       // [HIT_CAP] (row << 16 | column, par - 2 dot)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long row_tiles = (P.n + UM - 1) / UM;
@@ -127,7 +134,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
 
     if (tid == 0) {
         for (int s = 0; s < USTAGES; s++) {
-            mbar_init(&full[s], N_A_PRODUCERS + 1);  // 128 row producers + the bulk copy's arrive.expect_tx
+            mbar_init(&full[s], N_A_PRODUCERS + 1);  // 256 row producers + the bulk copy's arrive.expect_tx
             mbar_init(&empty[s], 1);                 // one tcgen05.commit
         }
         for (int a = 0; a < 2; a++) {
@@ -186,14 +193,31 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
     } else if (warp >= 4 && warp < 8) {
         // ===== epilogue: thread = one row of the tile = one TMEM lane =====
         const int ltid = (warp - 4) * 32 + lane;
-        int acc = 0;
+        int acc = 0, cur_qt = -1;
         unsigned acc_phase = 0;
+        auto append = [&](int q, long long rr, int x) {  // x = par - 2 dot
+            const int hd = x + __ldg(P.pb + q);
+            const long long key = topk_key(bq_score_from_hd(hd, P.dim), (int32_t)(rr + P.id_base));
+            const int pos = atomicAdd(&P.cnt[q], 1);
+            if (pos < P.cap) P.buf[(size_t)q * P.cap + pos] = key;
+        };
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int qt = (int)(tile / row_tiles);
-            const long long rr = (tile % row_tiles) * UM + ltid;
-            int par = 0;
+            const long long row0 = (tile % row_tiles) * UM, rr = row0 + ltid;
+            if (qt != cur_qt) {  // the thresholds of this query tile (padding queries never pass)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int c = ltid; c < UN; c += 128) {
+                    const int q = qt * UN + c;
+                    s_t2[c] = q < P.nq ? __ldg(P.t2 + q) : INT_MIN;
+                }
+                if (ltid == 0) *s_nhits = 0;
+                cur_qt = qt;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            int par = INT_MAX;  // rows past the end never pass
             if (rr < P.n) {
                 const uint4 *rp = reinterpret_cast<const uint4 *>(P.rows + (size_t)rr * P.W32);
+                par = 0;
                 for (int c = 0; c < (P.W32 >> 2); c++) {
                     const uint4 v = __ldg(rp + c);
                     par += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
@@ -215,43 +239,61 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                       "=r"(v[31])
                     : "r"(taddr + (uint32_t)(g * 32)));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (rr < P.n) {
+                const int4 *tp = reinterpret_cast<const int4 *>(s_t2 + g * 32);
 #pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const int q = qt * UN + g * 32 + c;
-                        if (q < P.nq) {
-                            const int dot = (int)v[c];
-                            if (par - 2 * dot <= __ldg(P.t2 + q)) {
-                                const int hd = par + __ldg(P.pb + q) - 2 * dot;
-                                const long long key = topk_key(bq_score_from_hd(hd, P.dim), (int32_t)(rr + P.id_base));
-                                const int pos = atomicAdd(&P.cnt[q], 1);
-                                if (pos < P.cap) P.buf[(size_t)q * P.cap + pos] = key;
-                            }
+                for (int c4 = 0; c4 < 8; c4++) {
+                    const int4 t = tp[c4];  // one broadcast LDS.128 per four columns
+                    const int tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int c = c4 * 4 + e;
+                        // hd - pb = par - 2 dot <= t2   <=>   2 dot + t2 >= par
+                        if (2 * (int)v[c] + tt[e] >= par) {
+                            const int slot = atomicAdd(s_nhits, 1);
+                            if (slot < HIT_CAP) s_hits[slot] = make_int2((ltid << 16) | (g * 32 + c), par - 2 * (int)v[c]);
+                            else append(qt * UN + g * 32 + c, rr, par - 2 * (int)v[c]);
                         }
                     }
                 }
             }
+            // the accumulator is drained: hand it back before the (slower) global flush of the queue
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int nh = min(*s_nhits, HIT_CAP);
+            for (int i = ltid; i < nh; i += 128) {
+                const int2 h = s_hits[i];
+                append(qt * UN + (h.x & 0xffff), row0 + (h.x >> 16), h.y);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (ltid == 0) *s_nhits = 0;
+            // (the next tile's first push happens after its tmem_full wait and at least one more bar.sync-free stretch; the reset
+            // is ordered before any push of the same thread, and other threads' pushes are atomics on the reset value: make the
+            // reset visible to them with one more barrier only when a query-tile change does not already provide it)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
     } else if (warp >= 8) {
-        // ===== A producers: thread = one row; 128 bits -> 128 bytes per stage, swizzled 16-byte chunks =====
-        const int r = (warp - 8) * 32 + lane;
+        // ===== A producers: two threads per row; 64 bits -> 64 bytes per stage and thread, swizzled 16-byte chunks =====
+        const int t = (warp - 8) * 32 + lane, r = t & 127, half = t >> 7;
         int stage = 0;
         unsigned phase = 0;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const long long rr = (tile % row_tiles) * UM + r;
-            const uint4 *rp = reinterpret_cast<const uint4 *>(P.rows + (size_t)(rr < P.n ? rr : 0) * P.W32);
+            const bool live = rr < P.n;
+            const uint2 *rp = reinterpret_cast<const uint2 *>(P.rows + (size_t)(live ? rr : 0) * P.W32) + half;
+            uint2 w = make_uint2(0u, 0u);
+            if (live) w = __ldg(rp);
             for (int kc = 0; kc < P.kchunks; kc++) {
-                uint4 w = make_uint4(0u, 0u, 0u, 0u);
-                if (rr < P.n) w = __ldg(rp + kc);
+                uint2 wn = make_uint2(0u, 0u);
+                if (live && kc + 1 < P.kchunks) wn = __ldg(rp + 2 * (kc + 1));  // the next chunk's words are in flight during this one
                 mbar_wait_bounded(&empty[stage], phase ^ 1);
                 unsigned char *dst = stage0 + stage * STAGE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
-                const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+                const uint32_t ws[2] = {w.x, w.y};
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint32_t bits = (j & 1) ? (ws[j >> 1] >> 16) : (ws[j >> 1] & 0xffffu);
+                for (int jj = 0; jj < 4; jj++) {
+                    const int j = half * 4 + jj;
+                    const uint32_t bits = (jj & 1) ? (ws[jj >> 1] >> 16) : (ws[jj >> 1] & 0xffffu);
                     uint4 v;
                     v.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
                     v.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
@@ -262,6 +304,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 mbar_arrive(&full[stage]);
                 if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+                w = wn;
             }
         }
     }
@@ -302,7 +345,7 @@ cudaError_t launch_bq_umma_filter(const DataDesc &d, const uint32_t *qbits_dev, 
     P.rows = reinterpret_cast<const uint32_t *>(d.words);
     P.n = d.n; P.W32 = W32; P.dim = d.dim; P.kchunks = kchunks; P.images = images_dev; P.qtiles = qtiles; P.nq = nq; P.t2 = t2_dev; P.pb = pb_dev;
     P.buf = buf_dev; P.cnt = cnt_dev; P.cap = cap; P.id_base = id_base;
-    const size_t smem = (size_t)USTAGES * STAGE_BYTES + 256;
+    const size_t smem = (size_t)USTAGES * STAGE_BYTES + 256 + UN * sizeof(int) + HIT_CAP * sizeof(int2);
     if ((e = cudaFuncSetAttribute(bq_umma_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     const long long tiles = ((d.n + UM - 1) / UM) * qtiles;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);

@@ -628,7 +628,7 @@ struct GraphBuilder {
     DataDesc d;
     int metric = 0, sm_count = 0;
     BuildParams bp;
-    int n = 0, degree = 0, beam = 0, hard_max = 0, row_cap = 0, max_batch = 0, window = 0;
+    int n = 0, degree = 0, beam = 0, hard_max = 0, row_cap = 0, max_batch = 0, window = 0, batch_div = 2;
     int inserted = 1;  // node 0 is the entry point with an empty list
     int32_t *adj = nullptr, *res_nodes = nullptr, *list = nullptr, *head_target = nullptr, *iota = nullptr;
     int *deg = nullptr, *mark = nullptr, *list_count = nullptr, *work_counter = nullptr;
@@ -671,6 +671,7 @@ cudaError_t builder_create(const DataDesc &d, int metric, const BuildParams &bp,
     B->row_cap = std::max(2 * bp.degree, B->hard_max + 1);
     if (B->row_cap > MAX_DEGREE) { delete B; return cudaErrorInvalidValue; }
     B->max_batch = bp.max_batch > 0 ? bp.max_batch : 16384;
+    if (const char *e = getenv("JV_BUILD_BATCH_DIV")) B->batch_div = atoi(e) > 0 ? atoi(e) : 2;  // tuning knob (tools/build_quality.py)
     // in-progress window: as many concurrently inserting peers as still fit the 128-candidate Gram tile next to the beam
     B->window = bp.window >= 0 ? bp.window : std::max(0, std::min(32, 128 - bp.beam));
     B->psmem = prune_smem_bytes(d);
@@ -726,7 +727,7 @@ cudaError_t builder_create(const DataDesc &d, int metric, const BuildParams &bp,
 bool builder_next_batch(GraphBuilder *B, int *first, int *count)
 {
     if (B->inserted >= B->n) return false;
-    int batch = B->inserted / 2;
+    int batch = B->inserted / B->batch_div;
     if (batch < 1) batch = 1;
     if (batch > B->max_batch) batch = B->max_batch;
     if (batch > B->n - B->inserted) batch = B->n - B->inserted;

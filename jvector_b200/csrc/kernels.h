@@ -36,8 +36,13 @@ struct SearchCounters {  // device-side totals
 // ---- kernels_batch.cu ----
 cudaError_t launch_prepare(const DataDesc &d, int metric, const float *queries_dev, int nq, float *blobs_dev, cudaStream_t s);
 // ragged: query qi scores ids[offsets[qi]..offsets[qi+1]); offsets == nullptr: every query scores ids[0..n) -> scores[qi*n + i]
+constexpr int HOP_MAX_IDS = 64;
+struct HopIds { int32_t ids[HOP_MAX_IDS]; };
+// one hop of one search with the ids in the kernel parameters and the scores stored to mapped host memory (latency path)
+cudaError_t launch_score_hop(const DataDesc &d, int metric, const float *blob_dev, const int32_t *ids_host, int n, float *scores_mapped, cudaStream_t s);
 cudaError_t launch_score_ragged(const DataDesc &d, int metric, const float *blobs_dev, int nq, const int32_t *ids_dev,
-                                const int32_t *offsets_dev, int n_shared, int max_per_query, float *scores_dev, cudaStream_t s);
+                                const int32_t *offsets_dev, int n_shared, int max_per_query, float *scores_dev, cudaStream_t s, int chunk = 0,
+                                int *done_counter = nullptr, int *host_flag = nullptr, int seq = 0);
 cudaError_t launch_score_pairs(const DataDesc &d, int metric, const int32_t *a_dev, const int32_t *b_dev, int n, float *out_dev, cudaStream_t s);
 
 struct TopkScratch {

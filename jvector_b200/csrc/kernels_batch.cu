@@ -51,7 +51,8 @@ constexpr int RAGGED_CHUNK = 128;
 template <int KIND, int METRIC>
 __global__ void __launch_bounds__(RAGGED_THREADS) score_ragged_kernel(DataDesc d, const float *__restrict__ blobs, int blob_stride,
                                                                       const int32_t *__restrict__ ids, const int32_t *__restrict__ offsets,
-                                                                      int n_shared, float *__restrict__ scores)
+                                                                      int n_shared, float *__restrict__ scores, int chunk, int *done_counter,
+                                                                      int *host_flag, int seq)
 {
     constexpr int G = GroupOf<KIND>::value;
     const int q = blockIdx.y;
@@ -66,27 +67,79 @@ __global__ void __launch_bounds__(RAGGED_THREADS) score_ragged_kernel(DataDesc d
         count = n_shared;
         out_base = (size_t)q * n_shared;
     }
-    const int c0 = blockIdx.x * RAGGED_CHUNK;
-    if (c0 >= count) return;
-    const int c1 = min(count, c0 + RAGGED_CHUNK);
-    const float *blob = blobs + (size_t)q * blob_stride;
-    const int group = threadIdx.x / G, lane = threadIdx.x % G;
-    constexpr int NG = RAGGED_THREADS / G;
-    for (int i = c0 + group; i < c1; i += NG) {
-        const int node = ids[begin + i];
-        float sc = 0.f;
-        if (node >= 0 && node < d.n) sc = score_row<KIND, METRIC>(d, blob, node, lane);
-        if (lane == 0) scores[out_base + i] = sc;
+    const int c0 = blockIdx.x * chunk;
+    if (c0 < count) {
+        const int c1 = min(count, c0 + chunk);
+        const float *blob = blobs + (size_t)q * blob_stride;
+        const int group = threadIdx.x / G, lane = threadIdx.x % G;
+        constexpr int NG = RAGGED_THREADS / G;
+        for (int i = c0 + group; i < c1; i += NG) {
+            const int node = ids[begin + i];
+            float sc = 0.f;
+            if (node >= 0 && node < d.n) sc = score_row<KIND, METRIC>(d, blob, node, lane);
+            if (lane == 0) {
+                scores[out_base + i] = sc;
+                if (host_flag) __threadfence_system();
+            }
+        }
+    }
+    if (host_flag) {
+        // completion signal for a host that spins on mapped memory instead of synchronising the stream: the last CTA to finish
+        // publishes `seq` after every score (written to mapped host memory too) has been fenced to the system scope
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(done_counter, 1) == (int)(gridDim.x * gridDim.y) - 1) {
+                *done_counter = 0;
+                __threadfence_system();
+                *(volatile int *)host_flag = seq;
+            }
+        }
     }
 }
 
 cudaError_t launch_score_ragged(const DataDesc &d, int metric, const float *blobs_dev, int nq, const int32_t *ids_dev,
-                                const int32_t *offsets_dev, int n_shared, int max_per_query, float *scores_dev, cudaStream_t s)
+                                const int32_t *offsets_dev, int n_shared, int max_per_query, float *scores_dev, cudaStream_t s, int chunk,
+                                int *done_counter, int *host_flag, int seq)
 {
     if (nq <= 0 || max_per_query <= 0) return cudaSuccess;
-    dim3 grid((max_per_query + RAGGED_CHUNK - 1) / RAGGED_CHUNK, nq);
+    if (chunk <= 0) chunk = RAGGED_CHUNK;
+    dim3 grid((max_per_query + chunk - 1) / chunk, nq);
     if (grid.y > 65535u) return cudaErrorInvalidValue;
-#define CALL(K, M) score_ragged_kernel<K, M><<<grid, RAGGED_THREADS, 0, s>>>(d, blobs_dev, blob_floats(d), ids_dev, offsets_dev, n_shared, scores_dev)
+#define CALL(K, M) \
+    score_ragged_kernel<K, M><<<grid, RAGGED_THREADS, 0, s>>>(d, blobs_dev, blob_floats(d), ids_dev, offsets_dev, n_shared, scores_dev, chunk, done_counter, host_flag, seq)
+    JV_DISPATCH_KIND_METRIC(d.kind, metric, CALL);
+#undef CALL
+    g_launches++;
+    return cudaGetLastError();
+}
+
+// one hop of one search, latency path: the candidate ids travel in the kernel parameters (no PCIe read before the rows can be
+// fetched), one lane group per id, and every score is stored straight into mapped host memory, where the host polls for the
+// sentinel it left there to disappear (no fence / counter / flag chain at the end of the kernel).
+template <int KIND, int METRIC>
+__global__ void __launch_bounds__(RAGGED_THREADS) score_hop_kernel(DataDesc d, const float *__restrict__ blob, HopIds h, int n, float *__restrict__ scores)
+{
+    constexpr int G = GroupOf<KIND>::value;
+    constexpr int NG = RAGGED_THREADS / G;
+    const int i = blockIdx.x * NG + threadIdx.x / G, lane = threadIdx.x % G;
+    if (i >= n) return;
+    const int node = h.ids[i];
+    float sc = 0.f;
+    if (node >= 0 && node < d.n) sc = score_row<KIND, METRIC>(d, blob, node, lane);
+    if (lane == 0) scores[i] = sc;
+}
+
+cudaError_t launch_score_hop(const DataDesc &d, int metric, const float *blob_dev, const int32_t *ids_host, int n, float *scores_mapped, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    if (n > HOP_MAX_IDS) return cudaErrorInvalidValue;
+    HopIds h;
+    memcpy(h.ids, ids_host, (size_t)n * 4);
+    const int G = d.kind == KIND_F32 ? GroupOf<KIND_F32>::value : d.kind == KIND_PQ ? GroupOf<KIND_PQ>::value : d.kind == KIND_BQ ? GroupOf<KIND_BQ>::value : GroupOf<KIND_NVQ>::value;
+    const int per_cta = RAGGED_THREADS / G;
+    const int grid = (n + per_cta - 1) / per_cta;
+#define CALL(K, M) score_hop_kernel<K, M><<<grid, RAGGED_THREADS, 0, s>>>(d, blob_dev, h, n, scores_mapped)
     JV_DISPATCH_KIND_METRIC(d.kind, metric, CALL);
 #undef CALL
     g_launches++;

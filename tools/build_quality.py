@@ -20,6 +20,8 @@ import oracle_lib as o  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=100_000)
 ap.add_argument("--nq", type=int, default=2000)
+ap.add_argument("--no-oracle", action="store_true", help="skip the (slow) reference-order build")
+ap.add_argument("--batch-div", default="", help="comma list of JV_BUILD_BATCH_DIV settings to compare (batch = inserted / div)")
 a = ap.parse_args()
 args = argparse.Namespace(impl="b200", n=a.n, dim=768, nq=a.nq, dist="latent", topk=10, gt_queries=a.nq)
 cx = bench.Ctx(args)
@@ -29,17 +31,21 @@ q = bench.gen_unit_rows_device(torch, bench.SEED + 1, a.nq, 768).cpu().numpy()
 base = base_d.cpu().numpy()
 vec = cx.adopt(base_d)
 gt, _, _ = jv.topk_bruteforce(vec, VSF.DOT_PRODUCT, q, 10)
-L = o.load()
-kind = "reference kernels" if (os.path.exists(o.REF_SO) and L.jvo_use_ref(o.REF_SO.encode()) == 0) else "scalar port"
-t0 = time.time()
-adj = np.empty((a.n, 32), np.int32)
-entry = L.jvo_graph_build_f32(o.DOT_PRODUCT, o.fp(base), a.n, 768, 32, 100, 1.2, 1.2, o.ip(adj))
-L.jvo_use_ref(None)
-t_ref = time.time() - t0
-g_ref = jv.GraphIndex(adj, entry)
 rows = []
-for name, g, secs in (("reference-order builder (oracle, %s)" % kind, g_ref, t_ref),):
-    rows.append((name, g, secs))
+if not a.no_oracle:
+    L = o.load()
+    kind = "reference kernels" if (os.path.exists(o.REF_SO) and L.jvo_use_ref(o.REF_SO.encode()) == 0) else "scalar port"
+    t0 = time.time()
+    adj = np.empty((a.n, 32), np.int32)
+    entry = L.jvo_graph_build_f32(o.DOT_PRODUCT, o.fp(base), a.n, 768, 32, 100, 1.2, 1.2, o.ip(adj))
+    L.jvo_use_ref(None)
+    rows.append(("reference-order builder (oracle, %s)" % kind, jv.GraphIndex(adj, entry), time.time() - t0))
+for div in [x for x in a.batch_div.split(",") if x]:
+    os.environ["JV_BUILD_BATCH_DIV"] = div
+    b = jv.GraphIndexBuilder(VSF.DOT_PRODUCT, M=32, beamWidth=100, neighborOverflow=1.2, alpha=1.2, addHierarchy=False, seed=bench.SEED)
+    g = b.build(vec)
+    rows.append(("device builder (batch = inserted / %s)" % div, g, b.device_ms / 1e3))
+    del os.environ["JV_BUILD_BATCH_DIV"]
 for window in (-1, 0):
     b = jv.GraphIndexBuilder(VSF.DOT_PRODUCT, M=32, beamWidth=100, neighborOverflow=1.2, alpha=1.2, addHierarchy=False, seed=bench.SEED, concurrent_window=window)
     g = b.build(vec)

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (raw page + SASS source page) into markdown for profiles/.
-usage: tools/ncu_summary.py <rep> <title> [algorithmic_bytes]"""
+usage: tools/ncu_summary.py <rep> <title> [algorithmic_bytes]   (NCU_INDEX=i picks the i-th profiled launch of the report, default 0)"""
 import csv
 import io
+import os
 import subprocess
 import sys
 
@@ -10,7 +11,8 @@ rep, title = sys.argv[1], sys.argv[2]
 algo = float(sys.argv[3]) if len(sys.argv) > 3 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+IDX = int(os.environ.get("NCU_INDEX", "0"))
+hdr, units, vals = rows[0], rows[1], rows[2 + IDX]
 m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
 
 
@@ -56,8 +58,10 @@ print("| L1 sector hit rate | %s %% |" % m.get("l1tex__t_sector_hit_rate.pct", (
 print("| SM throughput %% | %s |" % m.get("sm__throughput.avg.pct_of_peak_sustained_elapsed", ("?",))[0])
 print("| issue slots busy %% | %s |" % m.get("smsp__issue_active.avg.pct_of_peak_sustained_active", ("?",))[0])
 print("| shared-memory bank conflicts | %s |" % m.get("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", ("?",))[0])
+print("| L2 throughput %% (lts__throughput) | %s |" % m.get("lts__throughput.avg.pct_of_peak_sustained_elapsed", ("?",))[0])
+print("| tensor pipe active %% (sm__pipe_tensor_cycles_active_realtime) | %s |" % m.get("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", ("?",))[0])
 print()
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(IDX), "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]
 ci, cs = hdr.index("Source"), hdr.index("Warp Stall Sampling (All Samples)")
