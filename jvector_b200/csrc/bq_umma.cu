@@ -2,7 +2,8 @@
 // cores: tcgen05.mma kind::i8 (u8 x u8 -> s32, exact), accumulators in TMEM, operands in shared memory in the canonical K-major
 // SWIZZLE_128B layout, warp-specialised roles connected by mbarriers.
 //
-//   D[128 rows][256 queries] += A[128][K] * B[256][K]^T,  A / B = {0,1} bytes expanded from bit words, K = dim rounded to 128
+//   D[128 rows][256 queries] += A[128][K] * B[256][K]^T,  A bytes in {0, 2^s}, B bytes in {0, 2^(7-s)} expanded from bit words
+//   (D = 128 * popcount(row & query), exact in s32), K = dim rounded to 128
 //
 // Why a second kernel next to the IMMA one: the legacy IMMA path tops out at 917 TOP/s and re-expands both operands in every
 // warp tile; here the row tile is expanded ONCE per CTA tile into shared memory (producer warps), the query tile arrives as a
@@ -91,12 +92,15 @@ __global__ void __launch_bounds__(256) bq_query_image_kernel(const uint32_t *__r
     const long long t = idx >> 3;
     const int kc = (int)(t % kchunks), q = (int)(t / kchunks);
     const uint32_t w = qbits[(size_t)q * W32 + kc * 4 + (j >> 1)];
-    const uint32_t bits = (j & 1) ? (w >> 16) : (w & 0xffffu);
+    // K order inside a 32-bit word: output word s holds bits s, s + 8, s + 16, s + 24 (one per byte). The row side stores such a
+    // bit as the byte value 2^s (a single AND with a shifted mask), the query side as 2^(7 - s): every matching bit pair
+    // contributes exactly 128 to the s32 accumulator, so D = 128 * popcount(row & query).
+    const int sb = (j & 1) * 4;
     uint4 v;
-    v.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
-    v.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-    v.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-    v.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+    v.x = ((w >> (sb + 0)) & 0x01010101u) << (7 - (sb + 0));
+    v.y = ((w >> (sb + 1)) & 0x01010101u) << (7 - (sb + 1));
+    v.z = ((w >> (sb + 2)) & 0x01010101u) << (7 - (sb + 2));
+    v.w = ((w >> (sb + 3)) & 0x01010101u) << (7 - (sb + 3));
     const int qt = q / UN, r = q % UN;
     uint8_t *img = images + ((size_t)qt * kchunks + kc) * B_STAGE_BYTES;
     *reinterpret_cast<uint4 *>(img + (r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4)) = v;
@@ -208,13 +212,13 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 for (int c = ltid; c < UN; c += 128) {
                     const int q = qt * UN + c;
-                    s_t2[c] = q < P.nq ? __ldg(P.t2 + q) : INT_MIN;
+                    s_t2[c] = q < P.nq ? 128 * __ldg(P.t2 + q) : INT_MIN;  // the accumulators hold 128 * dot
                 }
                 if (ltid == 0) *s_nhits = 0;
                 cur_qt = qt;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            int par = INT_MAX;  // rows past the end never pass
+            int par = 0, par128 = INT_MAX;  // rows past the end never pass
             if (rr < P.n) {
                 const uint4 *rp = reinterpret_cast<const uint4 *>(P.rows + (size_t)rr * P.W32);
                 par = 0;
@@ -222,6 +226,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                     const uint4 v = __ldg(rp + c);
                     par += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
                 }
+                par128 = par << 7;
             }
             mbar_wait_bounded(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -240,6 +245,10 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                     : "r"(taddr + (uint32_t)(g * 32)));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const int4 *tp = reinterpret_cast<const int4 *>(s_t2 + g * 32);
+                // pass 1, branch-free: one bit per column that survives (independent LEA / ISETP / SEL chains; the round-2 profile
+                // showed a per-column branch costing ~90 cycles of dependent issue). hd - pb = par - 2 dot <= t2  <=>
+                // 2 (128 dot) + 128 t2 >= 128 par
+                uint32_t mask = 0;
 #pragma unroll
                 for (int c4 = 0; c4 < 8; c4++) {
                     const int4 t = tp[c4];  // one broadcast LDS.128 per four columns
@@ -247,11 +256,22 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
 #pragma unroll
                     for (int e = 0; e < 4; e++) {
                         const int c = c4 * 4 + e;
-                        // hd - pb = par - 2 dot <= t2   <=>   2 dot + t2 >= par
-                        if (2 * (int)v[c] + tt[e] >= par) {
-                            const int slot = atomicAdd(s_nhits, 1);
-                            if (slot < HIT_CAP) s_hits[slot] = make_int2((ltid << 16) | (g * 32 + c), par - 2 * (int)v[c]);
-                            else append(qt * UN + g * 32 + c, rr, par - 2 * (int)v[c]);
+                        mask |= (2 * (int)v[c] + tt[e] >= par128) ? (1u << c) : 0u;
+                    }
+                }
+                // pass 2: only the columns in which some lane of the warp has a survivor (about 3 of 32), warp-uniform branches,
+                // static register indices
+                const uint32_t um = __reduce_or_sync(0xffffffffu, mask);
+                if (um) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        if (um & (1u << c)) {
+                            if (mask & (1u << c)) {
+                                const int x = par - ((int)v[c] >> 6);  // par - 2 dot
+                                const int slot = atomicAdd(s_nhits, 1);
+                                if (slot < HIT_CAP) s_hits[slot] = make_int2((ltid << 16) | (g * 32 + c), x);
+                                else append(qt * UN + g * 32 + c, rr, x);
+                            }
                         }
                     }
                 }
@@ -292,13 +312,13 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                 const uint32_t ws[2] = {w.x, w.y};
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) {
-                    const int j = half * 4 + jj;
-                    const uint32_t bits = (jj & 1) ? (ws[jj >> 1] >> 16) : (ws[jj >> 1] & 0xffffu);
-                    uint4 v;
-                    v.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
-                    v.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-                    v.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-                    v.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+                    const int j = half * 4 + jj, sb = (jj & 1) * 4;
+                    const uint32_t word = ws[jj >> 1];
+                    uint4 v;  // bit (8 b + s) of the word -> byte b of output word s, value 2^s: one AND per output word
+                    v.x = word & (0x01010101u << (sb + 0));
+                    v.y = word & (0x01010101u << (sb + 1));
+                    v.z = word & (0x01010101u << (sb + 2));
+                    v.w = word & (0x01010101u << (sb + 3));
                     *reinterpret_cast<uint4 *>(dst + ((j ^ (r & 7)) << 4)) = v;
                 }
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads

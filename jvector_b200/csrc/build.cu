@@ -12,7 +12,7 @@
 //             max-similarity per candidate, updated in bulk whenever a neighbour is selected (SURVEY §3.2 seam v)
 //   backlink: append u to adj[v] for every chosen v (atomic slot), then prune_kernel again over every v whose list
 //             passed overflow * M
-// Batches grow geometrically (x1.5) up to max_batch so early nodes see a connected graph. Neighbour lists in the
+// Batches grow geometrically (x 33/32, JV_BUILD_BATCH_DIV) up to max_batch so early nodes see a connected graph. Neighbour lists in the
 // reference are concurrency-order dependent, so parity is on scores and on the recall of the resulting graph
 // (SURVEY §8d C5), not on identical adjacency.
 #include <limits.h>
@@ -628,7 +628,7 @@ struct GraphBuilder {
     DataDesc d;
     int metric = 0, sm_count = 0;
     BuildParams bp;
-    int n = 0, degree = 0, beam = 0, hard_max = 0, row_cap = 0, max_batch = 0, window = 0, batch_div = 2;
+    int n = 0, degree = 0, beam = 0, hard_max = 0, row_cap = 0, max_batch = 0, window = 0, batch_div = 32;
     int inserted = 1;  // node 0 is the entry point with an empty list
     int32_t *adj = nullptr, *res_nodes = nullptr, *list = nullptr, *head_target = nullptr, *iota = nullptr;
     int *deg = nullptr, *mark = nullptr, *list_count = nullptr, *work_counter = nullptr;
@@ -671,7 +671,7 @@ cudaError_t builder_create(const DataDesc &d, int metric, const BuildParams &bp,
     B->row_cap = std::max(2 * bp.degree, B->hard_max + 1);
     if (B->row_cap > MAX_DEGREE) { delete B; return cudaErrorInvalidValue; }
     B->max_batch = bp.max_batch > 0 ? bp.max_batch : 16384;
-    if (const char *e = getenv("JV_BUILD_BATCH_DIV")) B->batch_div = atoi(e) > 0 ? atoi(e) : 2;  // tuning knob (tools/build_quality.py)
+    if (const char *e = getenv("JV_BUILD_BATCH_DIV")) B->batch_div = atoi(e) > 0 ? atoi(e) : 32;  // tuning knob (tools/build_quality.py)
     // in-progress window: as many concurrently inserting peers as still fit the 128-candidate Gram tile next to the beam
     B->window = bp.window >= 0 ? bp.window : std::max(0, std::min(32, 128 - bp.beam));
     B->psmem = prune_smem_bytes(d);
@@ -723,7 +723,9 @@ cudaError_t builder_create(const DataDesc &d, int metric, const BuildParams &bp,
     return cudaGetLastError();
 }
 
-// the next batch: half of what is already inserted (so early nodes see a connected graph), at most max_batch
+// the next batch: 1/32 of what is already inserted, at most max_batch — every batch searches a graph that already holds 97 % of the
+// nodes a sequential build would show it. Measured on 100k rows (profiles/r2_build_quality.md): recall@10 at rerankK 100 is 0.950
+// with inserted / 2, 0.9585 with / 8, 0.9624 with / 32, against 0.9631 for the reference-order (sequential) builder.
 bool builder_next_batch(GraphBuilder *B, int *first, int *count)
 {
     if (B->inserted >= B->n) return false;
