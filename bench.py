@@ -500,7 +500,7 @@ def cpu_baseline_search(cx, w, topK, rerankK, pq, gt=True):
     r, sweep, nqs = cpu_sweep(w.base_host(), w.graph_host(), w.queries, topK, rerankK, int(cx.VSF.DOT_PRODUCT), pq, a.cpu_budget)
     d = {"value": r["qps"], "unit": "queries/s", "cores": r["threads"], "kind": r["kind"], "isa": r["isa"],
          "scored_vectors_per_sec": r["scored"] / r["seconds"], "thread_sweep": sweep, "topology": cpu_topology(),
-         "memory": "base rows in NUMA-interleaved pages (mbind MPOL_INTERLEAVE), queries block-partitioned over the threads",
+         "memory": "base rows in NUMA-interleaved pages (mbind MPOL_INTERLEAVE), queries handed to the threads in chunks of 4 from a shared counter",
          "sample": "%d of the %d queries of one step, best thread count of the sweep (%d), %.1f s" % (nqs, a.nq, r["threads"], r["seconds"])}
     if gt:
         d["recall_at_10"] = recall_at_k(r["nodes"][:w.ngt], w.gt_nodes[:min(w.ngt, nqs)], topK)
@@ -836,15 +836,21 @@ def main():
         topK, rerankK = args.topk, args.topk * args.overquery
         base, gh = w.base_host(), w.graph_host()
         ncpu = os.cpu_count() or 1
-        probe = cpu_search(base, gh, w.queries[:max(64, 2 * ncpu)], topK, rerankK, int(VSF.DOT_PRODUCT), None)
+        cpu_search(base, gh, w.queries[:max(64, 2 * ncpu)], topK, rerankK, int(VSF.DOT_PRODUCT), None)  # page-in
+        # all the host threads the reference can use: the better of one thread per logical CPU and one per physical core
+        probe, nthreads = None, ncpu
+        for t in sorted({max(1, ncpu // 2), ncpu}):
+            p = cpu_search(base, gh, w.queries[:max(256, 8 * t)], topK, rerankK, int(VSF.DOT_PRODUCT), None, threads=t)
+            if probe is None or p["qps"] > probe["qps"]:
+                probe, nthreads = p, t
         # a bounded sample of the step per timed step: the whole K + W run stays within ~2 minutes of CPU time
         per_step = min(args.cpu_budget, 120.0 / (args.steps + args.warmup))
         nqs = int(min(args.nq, max(200, probe["qps"] * per_step)))
         for _ in range(args.warmup):
-            cpu_search(base, gh, w.queries[:max(64, nqs // 10)], topK, rerankK, int(VSF.DOT_PRODUCT), None)
+            cpu_search(base, gh, w.queries[:max(64, nqs // 10)], topK, rerankK, int(VSF.DOT_PRODUCT), None, threads=nthreads)
         secs, scored, last = 0.0, 0, None
         for _ in range(args.steps):
-            last = cpu_search(base, gh, w.queries[:nqs], topK, rerankK, int(VSF.DOT_PRODUCT), None)
+            last = cpu_search(base, gh, w.queries[:nqs], topK, rerankK, int(VSF.DOT_PRODUCT), None, threads=nthreads)
             secs += last["seconds"]
             scored += last["scored"]
         qps = args.steps * nqs / secs
@@ -852,11 +858,11 @@ def main():
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
                "config": {"workload": "c2: synthetic %dx%d float32 unit rows (%s, generated on the device), DOT_PRODUCT, graph M=32 ef=100 overflow=1.2 alpha=1.2 "
                                       "hierarchy, GraphSearcher top-%d rerankK=%d, %d queries/step/GPU" % (args.n, args.dim, args.dist, topK, rerankK, args.nq),
-                          "parallelism": "CPU: queries block-partitioned over the host threads"},
+                          "parallelism": "CPU: queries handed to the host threads in chunks of 4 from a shared counter"},
                "value": qps, "ms_per_step": 1e3 * secs / args.steps, "recall_at_10": recall_at_k(last["nodes"][:w.ngt], w.gt_nodes[:min(w.ngt, nqs)], topK),
                "scored_vectors_per_sec": scored / secs,
                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": last["threads"], "kind": last["kind"], "isa": last["isa"], "topology": cpu_topology(),
-                                "memory": "base rows in NUMA-interleaved pages", "sample": "%d of the %d queries per step, all host threads" % (nqs, args.nq)},
+                                "memory": "base rows in NUMA-interleaved pages", "sample": "%d of the %d queries per step, %d threads (the better of %d and %d on a probe)" % (nqs, args.nq, nthreads, max(1, ncpu // 2), ncpu)},
                "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0, "setup": "rows and graph produced on the device (untimed); the timed path is CPU only"}
         cx.sampler.stop()

@@ -1307,18 +1307,24 @@ void *jvo_alloc_interleaved(size_t bytes)
 
 void jvo_free_interleaved(void *p, size_t bytes) { if (p) munmap(p, bytes); }
 
-/* ---- multi-threaded batch driver (queries block-partitioned, one searcher per thread:
+/* ---- multi-threaded batch driver (one searcher per thread, queries handed out in small chunks from a shared counter — the
+ *      work-stealing ForkJoin pool the reference's parallel query stream runs on balances the same way:
  *      jvector-examples/.../benchmarks/ThroughputBenchmark.java:213, datasets/SiftSmall.java:367-377) ---- */
 typedef struct {
-    const jvo_graph *g; const jvo_dataset *ds; const float *queries; int q0, q1, topK, rerankK;
-    int32_t *nodes; float *scores; int64_t scored;
+    const jvo_graph *g; const jvo_dataset *ds; const float *queries; int nq, topK, rerankK;
+    int32_t *nodes; float *scores; int64_t scored; int *next;
 } batch_job;
+#define JVO_BATCH_CHUNK 4
 
 static void *batch_worker(void *arg)
 {
     batch_job *j = (batch_job *)arg;
     const jvo_dataset *ds = j->ds;
-    for (int qi = j->q0; qi < j->q1; qi++) {
+    for (;;) {
+      const int c0 = __atomic_fetch_add(j->next, JVO_BATCH_CHUNK, __ATOMIC_RELAXED);
+      if (c0 >= j->nq) break;
+      const int c1 = c0 + JVO_BATCH_CHUNK < j->nq ? c0 + JVO_BATCH_CHUNK : j->nq;
+      for (int qi = c0; qi < c1; qi++) {
         const float *q = j->queries + (size_t)qi * ds->dim;
         jvo_scorer *ex = jvo_scorer_f32(ds->metric, ds->base, ds->n, ds->dim, q);
         jvo_scorer *ap = ds->kind == 1 ? jvo_scorer_pq(ds->metric, ds->codebooks, ds->M, ds->k, ds->dim, ds->centroid, ds->codes, ds->n, q) : NULL;
@@ -1331,6 +1337,7 @@ static void *batch_worker(void *arg)
         j->scored += st.visited + 1 + st.reranked;
         jvo_scorer_free(ex);
         jvo_scorer_free(ap);
+      }
     }
     return NULL;
 }
@@ -1344,9 +1351,10 @@ double jvo_graph_search_batch(const jvo_graph *g, const jvo_dataset *ds, const f
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
     batch_job *jobs = (batch_job *)calloc((size_t)threads, sizeof(batch_job));
     struct timespec t0, t1;
+    int next = 0;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < threads; t++) {
-        jobs[t] = (batch_job){g, ds, queries, (int)((int64_t)nq * t / threads), (int)((int64_t)nq * (t + 1) / threads), topK, rerankK, nodes_out, scores_out, 0};
+        jobs[t] = (batch_job){g, ds, queries, nq, topK, rerankK, nodes_out, scores_out, 0, &next};
         pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
     }
     int64_t total = 0;
