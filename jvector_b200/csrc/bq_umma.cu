@@ -259,20 +259,21 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                         mask |= (2 * (int)v[c] + tt[e] >= par128) ? (1u << c) : 0u;
                     }
                 }
-                // pass 2: only the columns in which some lane of the warp has a survivor (about 3 of 32), warp-uniform branches,
-                // static register indices
-                const uint32_t um = __reduce_or_sync(0xffffffffu, mask);
-                if (um) {
-#pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        if (um & (1u << c)) {
-                            if (mask & (1u << c)) {
-                                const int x = par - ((int)v[c] >> 6);  // par - 2 dot
-                                const int slot = atomicAdd(s_nhits, 1);
-                                if (slot < HIT_CAP) s_hits[slot] = make_int2((ltid << 16) | (g * 32 + c), x);
-                                else append(qt * UN + g * 32 + c, rr, x);
-                            }
-                        }
+                // pass 2: only the columns in which some lane of the warp has a survivor (about 3 of 32). The loop is warp-uniform;
+                // the column's accumulator is read back from TMEM with a one-column load (the column index is warp-uniform, a
+                // register array could only be indexed statically), so no per-column branch is paid for the other 29 columns.
+                uint32_t um = __reduce_or_sync(0xffffffffu, mask);
+                while (um) {
+                    const int c = __ffs(um) - 1;
+                    um &= um - 1;
+                    uint32_t dcol;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(dcol) : "r"(taddr + (uint32_t)(g * 32 + c)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (mask & (1u << c)) {
+                        const int x = par - ((int)dcol >> 6);  // par - 2 dot
+                        const int slot = atomicAdd(s_nhits, 1);
+                        if (slot < HIT_CAP) s_hits[slot] = make_int2((ltid << 16) | (g * 32 + c), x);
+                        else append(qt * UN + g * 32 + c, rr, x);
                     }
                 }
             }
