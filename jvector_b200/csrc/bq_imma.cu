@@ -453,9 +453,10 @@ cudaError_t launch_bq_topk_imma(const DataDesc &d, const float *queries_dev, int
 {
     if (nq <= 0) return cudaSuccess;
     const int nq_pad = (nq + NQ_ALIGN - 1) / NQ_ALIGN * NQ_ALIGN, W32 = 2 * d.W;
-    // JV_BQ_FILTER=umma: the full filter pass on tcgen05 (bq_umma.cu); default: the IMMA kernel of this file
+    // the full filter pass runs on tcgen05 (bq_umma.cu: 2.4x the IMMA kernel of this file on c4) whenever the shape allows;
+    // JV_BQ_FILTER=imma forces the legacy-MMA kernel (the sample pass and the redo passes always use it)
     const char *fm = getenv("JV_BQ_FILTER");
-    const bool use_umma = fm && fm[0] == 'u' && bq_umma_supported(d);
+    const bool use_umma = !(fm && fm[0] == 'i') && bq_umma_supported(d);
     char *p = reinterpret_cast<char *>(scratch_dev);
     auto take = [&p](size_t bytes) { char *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
     uint32_t *qbits = reinterpret_cast<uint32_t *>(take((size_t)nq_pad * W32 * 4));

@@ -13,9 +13,11 @@
 // warps 4-7 = epilogue (tcgen05.ld: warp w may touch TMEM lanes 32 (w % 4) ..), warps 8-15 = A producers (two threads per row:
 // 64 bits -> 64 bytes each, swizzled 128-bit stores, fence.proxy.async, arrive). Pipelines: full[s] / empty[s] over 4 operand
 // stages of 48 KB, tmem_full[a] / tmem_empty[a] over two 256-column accumulators, so the epilogue of one tile overlaps the MMAs
-// of the next. The epilogue is branch-light: thresholds of the query tile sit in shared memory, a column costs LEA + ISETP, the
-// rare survivors (about 0.3 %) go to a shared-memory queue that the 128 epilogue threads flush together (one global atomic each)
-// — round-2 profile (profiles/r2_ncu_bq_umma.md): a per-element LDG + branch epilogue kept the MMA thread waiting half its time.
+// of the next. The epilogue is branch-free per column: thresholds of the query tile sit in shared memory, a column costs
+// IADD3 + ISETP + SEL into a survivor bit mask; the rare survivors (about 0.3 %) are re-read from TMEM in a warp-uniform loop and go
+// to a per-warp shared-memory queue (ballot slots, no atomics) that the warp flushes after handing the accumulator back. Row
+// popcounts come from the producers. Round-2 profiles (profiles/r2_ncu_bq_umma.md): the first version's per-element LDG + branch
+// epilogue kept the MMA thread waiting half its time (6.8 ms); this one runs the filter pass in 2 ms.
 // Every spin-wait is bounded and traps: a wrong barrier count aborts the launch instead of hanging the device.
 #include <limits.h>
 
@@ -34,7 +36,7 @@ constexpr int A_STAGE_BYTES = UM * UKC;  // 16 KB
 constexpr int B_STAGE_BYTES = UN * UKC;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int N_A_PRODUCERS = 256;  // two threads per row
-constexpr int HIT_CAP = 1024;         // survivor queue of one tile (expected ~90 entries); overflow appends directly
+constexpr int WQ_CAP = 256;           // survivor queue of one epilogue warp and tile (expected ~25 entries); overflow appends directly
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
@@ -128,9 +130,9 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
     uint64_t *tmem_full = empty + USTAGES;
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-    int *s_nhits = reinterpret_cast<int *>(tmem_base_slot + 1);
     int *s_t2 = reinterpret_cast<int *>(smem + USTAGES * STAGE_BYTES + 256);  // [UN] thresholds of the current query tile
-    int2 *s_hits = reinterpret_cast<int2 *>(s_t2 + UN);                       // [HIT_CAP] (row << 16 | column, par - 2 dot)
+    int *s_parh = s_t2 + UN;                                                  // [2 tiles][2 halves][UM] row popcounts from the producers
+    int2 *s_hits = reinterpret_cast<int2 *>(s_parh + 4 * UM);                 // [4 warps][WQ_CAP] (row << 16 | column, par - 2 dot)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long row_tiles = (P.n + UM - 1) / UM;
@@ -197,8 +199,10 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
     } else if (warp >= 4 && warp < 8) {
         // ===== epilogue: thread = one row of the tile = one TMEM lane =====
         const int ltid = (warp - 4) * 32 + lane;
-        int acc = 0, cur_qt = -1;
+        int acc = 0, cur_qt = -1, tbuf = 0;
         unsigned acc_phase = 0;
+        int2 *wq = s_hits + (warp - 4) * WQ_CAP;  // this warp's private survivor queue: no atomics, no cross-warp barrier
+        const uint32_t lt_mask = (1u << lane) - 1u;
         auto append = [&](int q, long long rr, int x) {  // x = par - 2 dot
             const int hd = x + __ldg(P.pb + q);
             const long long key = topk_key(bq_score_from_hd(hd, P.dim), (int32_t)(rr + P.id_base));
@@ -214,23 +218,18 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                     const int q = qt * UN + c;
                     s_t2[c] = q < P.nq ? 128 * __ldg(P.t2 + q) : INT_MIN;  // the accumulators hold 128 * dot
                 }
-                if (ltid == 0) *s_nhits = 0;
                 cur_qt = qt;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            int par = 0, par128 = INT_MAX;  // rows past the end never pass
-            if (rr < P.n) {
-                const uint4 *rp = reinterpret_cast<const uint4 *>(P.rows + (size_t)rr * P.W32);
-                par = 0;
-                for (int c = 0; c < (P.W32 >> 2); c++) {
-                    const uint4 v = __ldg(rp + c);
-                    par += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
-                }
-                par128 = par << 7;
-            }
             mbar_wait_bounded(&tmem_full[acc], acc_phase);
             tc_fence_after();
+            // the row's popcount, summed by the two producer threads of the row while they expanded it (ordered before the
+            // accumulator's completion through full[] -> MMA -> tmem_full[])
+            const int par = s_parh[(tbuf * 2 + 0) * UM + ltid] + s_parh[(tbuf * 2 + 1) * UM + ltid];
+            const int par128 = rr < P.n ? par << 7 : INT_MAX;  // rows past the end never pass
+            tbuf ^= 1;
             const uint32_t taddr = tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + (uint32_t)(acc * UN);
+            int wcount = 0;  // warp-uniform
 #pragma unroll 1
             for (int g = 0; g < UN / 32; g++) {
                 uint32_t v[32];
@@ -261,7 +260,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                 }
                 // pass 2: only the columns in which some lane of the warp has a survivor (about 3 of 32). The loop is warp-uniform;
                 // the column's accumulator is read back from TMEM with a one-column load (the column index is warp-uniform, a
-                // register array could only be indexed statically), so no per-column branch is paid for the other 29 columns.
+                // register array could only be indexed statically); slots in the warp's queue come from a ballot.
                 uint32_t um = __reduce_or_sync(0xffffffffu, mask);
                 while (um) {
                     const int c = __ffs(um) - 1;
@@ -269,35 +268,33 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                     uint32_t dcol;
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(dcol) : "r"(taddr + (uint32_t)(g * 32 + c)));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (mask & (1u << c)) {
+                    const bool hit = (mask >> c) & 1u;
+                    const uint32_t b = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
                         const int x = par - ((int)dcol >> 6);  // par - 2 dot
-                        const int slot = atomicAdd(s_nhits, 1);
-                        if (slot < HIT_CAP) s_hits[slot] = make_int2((ltid << 16) | (g * 32 + c), x);
+                        const int slot = wcount + __popc(b & lt_mask);
+                        if (slot < WQ_CAP) wq[slot] = make_int2((ltid << 16) | (g * 32 + c), x);
                         else append(qt * UN + g * 32 + c, rr, x);
                     }
+                    wcount += __popc(b);
                 }
             }
             // the accumulator is drained: hand it back before the (slower) global flush of the queue
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int nh = min(*s_nhits, HIT_CAP);
-            for (int i = ltid; i < nh; i += 128) {
-                const int2 h = s_hits[i];
+            __syncwarp();
+            const int nh = min(wcount, WQ_CAP);
+            for (int i = lane; i < nh; i += 32) {
+                const int2 h = wq[i];
                 append(qt * UN + (h.x & 0xffff), row0 + (h.x >> 16), h.y);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (ltid == 0) *s_nhits = 0;
-            // (the next tile's first push happens after its tmem_full wait and at least one more bar.sync-free stretch; the reset
-            // is ordered before any push of the same thread, and other threads' pushes are atomics on the reset value: make the
-            // reset visible to them with one more barrier only when a query-tile change does not already provide it)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            __syncwarp();
         }
     } else if (warp >= 8) {
         // ===== A producers: two threads per row; 64 bits -> 64 bytes per stage and thread, swizzled 16-byte chunks =====
         const int t = (warp - 8) * 32 + lane, r = t & 127, half = t >> 7;
-        int stage = 0;
+        int stage = 0, tbuf = 0;
         unsigned phase = 0;
         for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const long long rr = (tile % row_tiles) * UM + r;
@@ -305,6 +302,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
             const uint2 *rp = reinterpret_cast<const uint2 *>(P.rows + (size_t)(live ? rr : 0) * P.W32) + half;
             uint2 w = make_uint2(0u, 0u);
             if (live) w = __ldg(rp);
+            int pc = 0;
             for (int kc = 0; kc < P.kchunks; kc++) {
                 uint2 wn = make_uint2(0u, 0u);
                 if (live && kc + 1 < P.kchunks) wn = __ldg(rp + 2 * (kc + 1));  // the next chunk's words are in flight during this one
@@ -322,11 +320,14 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                     v.w = word & (0x01010101u << (sb + 3));
                     *reinterpret_cast<uint4 *>(dst + ((j ^ (r & 7)) << 4)) = v;
                 }
+                pc += __popc(w.x) + __popc(w.y);
+                if (kc + 1 == P.kchunks) s_parh[(tbuf * 2 + half) * UM + r] = pc;  // this half row's popcount, for the epilogue
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 mbar_arrive(&full[stage]);
                 if (++stage == USTAGES) { stage = 0; phase ^= 1; }
                 w = wn;
             }
+            tbuf ^= 1;
         }
     }
     // teardown
@@ -366,7 +367,7 @@ cudaError_t launch_bq_umma_filter(const DataDesc &d, const uint32_t *qbits_dev, 
     P.rows = reinterpret_cast<const uint32_t *>(d.words);
     P.n = d.n; P.W32 = W32; P.dim = d.dim; P.kchunks = kchunks; P.images = images_dev; P.qtiles = qtiles; P.nq = nq; P.t2 = t2_dev; P.pb = pb_dev;
     P.buf = buf_dev; P.cnt = cnt_dev; P.cap = cap; P.id_base = id_base;
-    const size_t smem = (size_t)USTAGES * STAGE_BYTES + 256 + UN * sizeof(int) + HIT_CAP * sizeof(int2);
+    const size_t smem = (size_t)USTAGES * STAGE_BYTES + 256 + UN * sizeof(int) + 4 * UM * sizeof(int) + 4 * WQ_CAP * sizeof(int2);
     if ((e = cudaFuncSetAttribute(bq_umma_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     const long long tiles = ((d.n + UM - 1) / UM) * qtiles;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);

@@ -262,13 +262,15 @@ def test_bq_bruteforce_tensor_core_contraction_exact(jv, oracle, dim, n, nq, k):
     bqv.close()
 
 
-def test_bq_bruteforce_tcgen05_filter_exact(jv):
-    # the same top-k with the filter pass on tcgen05 (kind::i8, TMEM accumulators, csrc/bq_umma.cu), in its own process
+@pytest.mark.parametrize("filter_kernel", ["umma", "imma"])
+def test_bq_bruteforce_filter_kernels_exact(jv, filter_kernel):
+    # the same top-k with the filter pass forced onto tcgen05 (kind::i8, TMEM accumulators, csrc/bq_umma.cu: the default where the
+    # shape allows) and onto the legacy-MMA kernel (csrc/bq_imma.cu: the fallback), each in its own process
     import os
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
-    out = subprocess.run([sys.executable, os.path.join(here, "umma_check.py")], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([sys.executable, os.path.join(here, "umma_check.py"), filter_kernel], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "UMMA_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 

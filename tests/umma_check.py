@@ -1,4 +1,4 @@
-"""Run by tests/test_gpu_parity.py::test_bq_bruteforce_tcgen05_filter_exact in a SUBPROCESS (a faulting tcgen05 pipeline traps and
+"""Run by tests/test_gpu_parity.py::test_bq_bruteforce_filter_kernels_exact (argument: umma | imma) in a SUBPROCESS (a faulting tcgen05 pipeline traps and
 poisons the CUDA context; it must not take the other tests with it): BQ top-k with the filter pass on tcgen05 (JV_BQ_FILTER=umma)
 against the oracle's scalar popcount restatement, bit for bit."""
 import os
@@ -10,7 +10,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-os.environ["JV_BQ_FILTER"] = "umma"
+os.environ["JV_BQ_FILTER"] = sys.argv[1] if len(sys.argv) > 1 else "umma"
 import jvector_b200 as jv  # noqa: E402
 import oracle_lib as o  # noqa: E402
 from oracle_lib import fp, lp, wp  # noqa: E402
