@@ -50,7 +50,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 SEED = 20260922
 LATENT = 32      # intrinsic dimensionality of the synthetic embedding model
 NOISE = 0.25     # isotropic noise relative to the per-coordinate signal
-IMMA_PEAK_TOPS = 917.0  # tools/micro/imma_rate.cu on B200: legacy IMMA.16832 issue rate, 2*16*8*32 ops each (profiles/r2_imma_rate.md)
+IMMA_PEAK_TOPS = 917.0   # tools/micro/imma_rate.cu on B200: legacy IMMA.16832 issue rate, 2*16*8*32 ops each (profiles/r2_imma_rate.md)
+UMMA_I8_PEAK_TOPS = 4559.0  # tools/micro/umma_rate.cu on B200: tcgen05.mma kind::i8 128x256x32 at 128 cycles each on all 148 SMs
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed `ncu --set full` captures
 # under profiles/ ; key = (workload, n, nq, rerankK)
@@ -658,6 +659,8 @@ def bench_c4(cx, steps):
     launches = int(cx.sum_over_ranks([launches])[0])
     pairs = float(steps) * nq * n
     ops = pairs * 2.0 * (W * 64)  # u8 multiply-adds of the contraction, both counted
+    umma = os.environ.get("JV_BQ_FILTER", "u")[0] != "i" and W % 2 == 0 and W <= 32
+    tpeak = UMMA_I8_PEAK_TOPS if umma else IMMA_PEAK_TOPS
     out = {"metric": "queries_per_sec_bq_bruteforce", "unit": "queries/s", "n_gpus": cx.world, "steps": steps, "warmup": 33, "higher_is_better": True,
            "scaling": "strong", "dtype": "u8 x u8 -> s32 (exact)", "data": "synthetic",
            "config": {"workload": "c4: synthetic %dx%d BQ (sign bits of N(0,1) rows), Hamming top-%d, %d queries/step, base range-sharded over %d GPU(s)" % (n, dim, k, nq, cx.world),
@@ -666,10 +669,14 @@ def bench_c4(cx, steps):
            "value": steps * nq / dev_s, "ms_per_step": 1e3 * dev_s / steps, "pairs_per_sec": pairs / dev_s, "unresolved_queries": unresolved,
            "e2e": {"value": steps * nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(queries.nbytes), "d2h_bytes_per_step": int(nq * k * 8)},
            "gpu_launches": launches,
-           "roofline": {"kernel": "bq_imma_kernel (IMMA.16832 u8)", "bound": "tensor", "achieved": ops / cx.world / dev_s / 1e12, "peak": IMMA_PEAK_TOPS, "unit": "TOP/s",
-                        "frac": ops / cx.world / dev_s / 1e12 / IMMA_PEAK_TOPS,
+           "roofline": {"kernel": "bq_umma_filter_kernel (tcgen05.mma kind::i8, TMEM accumulators)" if umma else "bq_imma_kernel (IMMA.16832 u8)",
+                        "bound": "tensor", "achieved": ops / cx.world / dev_s / 1e12, "peak": tpeak, "unit": "TOP/s",
+                        "frac": ops / cx.world / dev_s / 1e12 / tpeak,
                         "traffic": NCU_TRAFFIC.get(("c4", n, nq, k)) if cx.world == 1 else None,
-                        "peak_source": "measured issue rate of the legacy IMMA.16832 path on B200 (tools/micro/imma_rate.cu, profiles/r2_imma_rate.md); MEASURED_PEAKS.json has no integer entry",
+                        "peak_source": ("measured issue rate of tcgen05.mma kind::i8 on B200 (tools/micro/umma_rate.cu, profiles/r2_umma_rate.md)" if umma else
+                                        "measured issue rate of the legacy IMMA.16832 path on B200 (tools/micro/imma_rate.cu, profiles/r2_imma_rate.md)") +
+                                       "; MEASURED_PEAKS.json has no integer entry",
+                        "note": "whole step in the denominator (sample pass + thresholds + filter pass + select)",
                         "hbm_unique_GBps": float(steps) * (hi - lo) * W * 8 / dev_s / 1e9}}
     if cx.rank == 0 and not a.no_cpu:
         import oracle_lib as o

@@ -9,8 +9,9 @@
 // warp tile; here the row tile is expanded ONCE per CTA tile into shared memory (producer warps), the query tile arrives as a
 // pre-expanded, pre-swizzled 32 KB image by one bulk copy, and one elected thread issues 128 x 256 x 32 MMAs.
 //
-// Roles (512 threads): warp 0 = B producer (cp.async.bulk of the query image chunk), warp 1 = MMA issuer + TMEM owner,
-// warps 4-7 = epilogue (tcgen05.ld: warp w may touch TMEM lanes 32 (w % 4) ..), warps 8-15 = A producers (two threads per row:
+// Roles (640 threads): warp 0 = B producer (cp.async.bulk of the query image chunk), warp 1 = MMA issuer + TMEM owner,
+// warps 4-7 and 16-19 = two epilogue groups, one per accumulator buffer, so each has two tiles' worth of MMA time to drain its
+// tile (tcgen05.ld: warp w may touch TMEM lanes 32 (w % 4) ..), warps 8-15 = A producers (two threads per row:
 // 64 bits -> 64 bytes each, swizzled 128-bit stores, fence.proxy.async, arrive). Pipelines: full[s] / empty[s] over 4 operand
 // stages of 48 KB, tmem_full[a] / tmem_empty[a] over two 256-column accumulators, so the epilogue of one tile overlaps the MMAs
 // of the next. The epilogue is branch-free per column: thresholds of the query tile sit in shared memory, a column costs
@@ -31,11 +32,13 @@ constexpr int UM = 128;           // rows per tile (MMA M)
 constexpr int UN = 256;           // queries per tile (MMA N)
 constexpr int UKC = 128;          // K bytes per stage (one 128-byte swizzle atom wide)
 constexpr int USTAGES = 4;
-constexpr int UTHREADS = 512;
+constexpr int UTHREADS = 640;
 constexpr int A_STAGE_BYTES = UM * UKC;  // 16 KB
 constexpr int B_STAGE_BYTES = UN * UKC;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int N_A_PRODUCERS = 256;  // two threads per row
+constexpr int NPAR = 8;               // ring of row-popcount buffers: the producers run up to USTAGES stages (= tiles when K is one
+                                      // chunk) ahead of the MMA, which runs up to 2 tiles ahead of the epilogue
 constexpr int WQ_CAP = 256;           // survivor queue of one epilogue warp and tile (expected ~25 entries); overflow appends directly
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -130,9 +133,9 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
     uint64_t *tmem_full = empty + USTAGES;
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-    int *s_t2 = reinterpret_cast<int *>(smem + USTAGES * STAGE_BYTES + 256);  // [UN] thresholds of the current query tile
-    int *s_parh = s_t2 + UN;                                                  // [2 tiles][2 halves][UM] row popcounts from the producers
-    int2 *s_hits = reinterpret_cast<int2 *>(s_parh + 4 * UM);                 // [4 warps][WQ_CAP] (row << 16 | column, par - 2 dot)
+    int *s_t2 = reinterpret_cast<int *>(smem + USTAGES * STAGE_BYTES + 256);  // [2 groups][UN] thresholds of the group's query tile
+    int *s_parh = s_t2 + 2 * UN;                                                  // [NPAR tiles][2 halves][UM] row popcounts from the producers
+    int2 *s_hits = reinterpret_cast<int2 *>(s_parh + NPAR * 2 * UM);                 // [8 warps][WQ_CAP] (row << 16 | column, par - 2 dot)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long row_tiles = (P.n + UM - 1) / UM;
@@ -196,12 +199,15 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===== epilogue: thread = one row of the tile = one TMEM lane =====
-        const int ltid = (warp - 4) * 32 + lane;
-        int acc = 0, cur_qt = -1, tbuf = 0;
+    } else if ((warp >= 4 && warp < 8) || warp >= 16) {
+        // ===== epilogue: thread = one row of the tile = one TMEM lane; group g drains accumulator buffer g (every other tile) =====
+        const int grp = warp >= 16 ? 1 : 0, wq4 = warp & 3;
+        const int ltid = wq4 * 32 + lane;
+        const int acc = grp;
+        int cur_qt = -1;
         unsigned acc_phase = 0;
-        int2 *wq = s_hits + (warp - 4) * WQ_CAP;  // this warp's private survivor queue: no atomics, no cross-warp barrier
+        int *my_t2 = s_t2 + grp * UN;
+        int2 *wq = s_hits + (grp * 4 + wq4) * WQ_CAP;  // this warp's private survivor queue: no atomics, no cross-warp barrier
         const uint32_t lt_mask = (1u << lane) - 1u;
         auto append = [&](int q, long long rr, int x) {  // x = par - 2 dot
             const int hd = x + __ldg(P.pb + q);
@@ -209,17 +215,21 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
             const int pos = atomicAdd(&P.cnt[q], 1);
             if (pos < P.cap) P.buf[(size_t)q * P.cap + pos] = key;
         };
-        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int qt = (int)(tile / row_tiles);
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+            if ((it & 1) != grp) continue;
+            const int qt = (int)(tile / row_tiles), tbuf = it & (NPAR - 1);
             const long long row0 = (tile % row_tiles) * UM, rr = row0 + ltid;
             if (qt != cur_qt) {  // the thresholds of this query tile (padding queries never pass)
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                else asm volatile("bar.sync 2, 128;" ::: "memory");
                 for (int c = ltid; c < UN; c += 128) {
                     const int q = qt * UN + c;
-                    s_t2[c] = q < P.nq ? 128 * __ldg(P.t2 + q) : INT_MIN;  // the accumulators hold 128 * dot
+                    my_t2[c] = q < P.nq ? 128 * __ldg(P.t2 + q) : INT_MIN;  // the accumulators hold 128 * dot
                 }
                 cur_qt = qt;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                else asm volatile("bar.sync 2, 128;" ::: "memory");
             }
             mbar_wait_bounded(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -227,8 +237,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
             // accumulator's completion through full[] -> MMA -> tmem_full[])
             const int par = s_parh[(tbuf * 2 + 0) * UM + ltid] + s_parh[(tbuf * 2 + 1) * UM + ltid];
             const int par128 = rr < P.n ? par << 7 : INT_MAX;  // rows past the end never pass
-            tbuf ^= 1;
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + (uint32_t)(acc * UN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq4 * 32) << 16) + (uint32_t)(acc * UN);
             int wcount = 0;  // warp-uniform
 #pragma unroll 1
             for (int g = 0; g < UN / 32; g++) {
@@ -243,7 +252,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                       "=r"(v[31])
                     : "r"(taddr + (uint32_t)(g * 32)));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int4 *tp = reinterpret_cast<const int4 *>(s_t2 + g * 32);
+                const int4 *tp = reinterpret_cast<const int4 *>(my_t2 + g * 32);
                 // pass 1, branch-free: one bit per column that survives (independent LEA / ISETP / SEL chains; the round-2 profile
                 // showed a per-column branch costing ~90 cycles of dependent issue). hd - pb = par - 2 dot <= t2  <=>
                 // 2 (128 dot) + 128 t2 >= 128 par
@@ -282,7 +291,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
             // the accumulator is drained: hand it back before the (slower) global flush of the queue
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            acc_phase ^= 1;
             __syncwarp();
             const int nh = min(wcount, WQ_CAP);
             for (int i = lane; i < nh; i += 32) {
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
             }
             __syncwarp();
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 16) {
         // ===== A producers: two threads per row; 64 bits -> 64 bytes per stage and thread, swizzled 16-byte chunks =====
         const int t = (warp - 8) * 32 + lane, r = t & 127, half = t >> 7;
         int stage = 0, tbuf = 0;
@@ -327,7 +336,7 @@ __global__ void __launch_bounds__(UTHREADS, 1) bq_umma_filter_kernel(UmmaParams 
                 if (++stage == USTAGES) { stage = 0; phase ^= 1; }
                 w = wn;
             }
-            tbuf ^= 1;
+            tbuf = (tbuf + 1) & (NPAR - 1);
         }
     }
     // teardown
@@ -367,7 +376,7 @@ cudaError_t launch_bq_umma_filter(const DataDesc &d, const uint32_t *qbits_dev, 
     P.rows = reinterpret_cast<const uint32_t *>(d.words);
     P.n = d.n; P.W32 = W32; P.dim = d.dim; P.kchunks = kchunks; P.images = images_dev; P.qtiles = qtiles; P.nq = nq; P.t2 = t2_dev; P.pb = pb_dev;
     P.buf = buf_dev; P.cnt = cnt_dev; P.cap = cap; P.id_base = id_base;
-    const size_t smem = (size_t)USTAGES * STAGE_BYTES + 256 + UN * sizeof(int) + 4 * UM * sizeof(int) + 4 * WQ_CAP * sizeof(int2);
+    const size_t smem = (size_t)USTAGES * STAGE_BYTES + 256 + 2 * UN * sizeof(int) + NPAR * 2 * UM * sizeof(int) + 8 * WQ_CAP * sizeof(int2);
     if ((e = cudaFuncSetAttribute(bq_umma_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     const long long tiles = ((d.n + UM - 1) / UM) * qtiles;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
