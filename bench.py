@@ -57,7 +57,7 @@ UMMA_I8_PEAK_TOPS = 4559.0  # tools/micro/umma_rate.cu on B200: tcgen05.mma kind
 # under profiles/ ; key = (workload, n, nq, rerankK)
 NCU_TRAFFIC = {("c2", 1_000_000, 10_000, 100): 95.311e9,   # profiles/r2_ncu_search_c2.md
                ("c3", 1_000_000, 10_000, 100): 26.292e9,   # profiles/r2_ncu_search_c3.md
-               ("c4", 1_000_000, 1000, 100): 0.211e9}      # profiles/r2_ncu_bq_imma.md (the filter launch)
+               ("c4", 1_000_000, 1000, 100): 0.790e9}      # profiles/r2_ncu_bq_umma.md (the tcgen05 filter launch)
 
 
 def log(*a):
