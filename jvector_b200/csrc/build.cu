@@ -262,7 +262,7 @@ constexpr int GRAM_KC = 32;
 constexpr int GRAM_PITCH = 36;
 
 template <int METRIC, int TILE>
-__global__ void __launch_bounds__(PRUNE_THREADS) prune_gram_kernel(PruneParams P)
+__global__ void __launch_bounds__(PRUNE_THREADS, TILE == 128 ? 2 : 4) prune_gram_kernel(PruneParams P)
 {
     constexpr int NB = TILE / 16;       // rows / cols per thread
     constexpr int CP = TILE + 1;        // pitch of the similarity matrix
