@@ -262,7 +262,7 @@ constexpr int GRAM_KC = 32;
 constexpr int GRAM_PITCH = 36;
 
 template <int METRIC, int TILE>
-__global__ void __launch_bounds__(PRUNE_THREADS, TILE == 128 ? 2 : 4) prune_gram_kernel(PruneParams P)
+__global__ void __launch_bounds__(PRUNE_THREADS) prune_gram_kernel(PruneParams P)
 {
     constexpr int NB = TILE / 16;       // rows / cols per thread
     constexpr int CP = TILE + 1;        // pitch of the similarity matrix
@@ -441,6 +441,302 @@ __global__ void __launch_bounds__(PRUNE_THREADS, TILE == 128 ? 2 : 4) prune_gram
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// prune_gram_tc_kernel: the same kernel with the Gram product on the 5th-generation tensor cores. The candidate x candidate
+// matrix is GEMM-shaped work (X X^T, X = the candidate rows), 72 % of prune_gram_kernel<128>'s time on the CUDA cores
+// (profiles/r2_build_prune.md). fp32 products are kept by the 3xTF32 split: x = hi + lo with hi = x truncated to tf32's 10
+// mantissa bits and lo = x - hi (exact), D += hi hi^T + hi lo^T + lo hi^T (the dropped lo lo^T term is 2^-22 relative), fp32
+// accumulation in TMEM. Per 32-float K chunk all 256 threads stage the rows into two K-major SWIZZLE_128B tiles (hi | lo, TILE
+// rows x 128 B each; the same tile is the A and the B operand), double buffered, and one thread issues 12
+// tcgen05.mma.kind::tf32 (M = 128, N = TILE, K = 8); the next chunk's global loads are in flight while it does. The similarity
+// matrix C overlays the staging area once the last MMA has completed. The scores against v (the sort keys) stay exact fp32.
+// For TILE = 64 the A operand still spans 128 rows (M = 128): rows 64..127 read whatever follows the tile and produce
+// accumulator rows that are never read.
+// ------------------------------------------------------------------------------------------------
+namespace tc {
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void wait_bounded(uint64_t *bar, unsigned parity)
+{
+    for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 28)) __trap();
+}
+template <int TILE>
+struct Layout {
+    static constexpr int TILE_BYTES = TILE * 128;                  // one operand tile: TILE rows x 32 floats
+    static constexpr int STAGE_BYTES = 2 * TILE_BYTES;             // hi | lo
+    static constexpr int STAGES_END = 2 * STAGE_BYTES + (TILE < 128 ? (128 - TILE) * 128 : 0);  // + what an M = 128 A operand over-reads
+    static constexpr int C_BYTES = (TILE * (TILE + 1) * 4 + 15) & ~15;
+    static constexpr int AREA = ((STAGES_END > C_BYTES ? STAGES_END : C_BYTES) + 1023) & ~1023;
+};
+}  // namespace tc
+
+template <int TILE>
+static size_t gram_tc_smem_bytes(const DataDesc &d)
+{
+    size_t b = 1024 /* alignment slack */ + tc::Layout<TILE>::AREA + (size_t)(d.stride + 4) * 4 + (size_t)TILE * 8 + (size_t)TILE * 4 * 3 + TILE + 64;
+    return (b + 15) & ~(size_t)15;
+}
+
+template <int METRIC, int TILE>
+__global__ void __launch_bounds__(PRUNE_THREADS, TILE == 128 ? 3 : 4) prune_gram_tc_kernel(PruneParams P)
+{
+    using L = tc::Layout<TILE>;
+    constexpr int CP = TILE + 1;
+    constexpr int PASSES = TILE / 32;   // 256 threads stage 32 rows x 8 float4 per pass
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *area = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    float *C = reinterpret_cast<float *>(area);
+    float *blob = reinterpret_cast<float *>(area + L::AREA);                   // stride + 4
+    long long *keys = reinterpret_cast<long long *>(blob + ((P.d.stride + 4 + 1) & ~1));
+    float *maxsim = reinterpret_cast<float *>(keys + TILE);
+    float *diag = maxsim + TILE;
+    int32_t *ids = reinterpret_cast<int32_t *>(diag + TILE);
+    uint8_t *state = reinterpret_cast<uint8_t *>(ids + TILE);
+    __shared__ float red[36];
+    __shared__ int s_next;
+    __shared__ __align__(8) uint64_t mma_bar[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = PRUNE_THREADS / 32;
+    const int total = P.count_ptr ? *P.count_ptr : P.count;
+    float alpha_max = 1.0f;
+    for (float a = 1.0f; a <= P.alpha + 1e-6f; a += 0.2f) alpha_max = a;
+
+    if (tid == 0) {
+        mbar_init(&mma_bar[0], 1);
+        mbar_init(&mma_bar[1], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TILE) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    // c = F32 (1) at [4,6), a = b = TF32 (2) at [7,10) / [10,13), K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    unsigned commits0 = 0u, commits1 = 0u;  // commits issued per staging buffer so far (every thread keeps the same count)
+    const int nchunks = (P.d.stride + 31) / 32;
+    const int c4 = tid & 7, r0 = tid >> 3;
+
+    for (int it = blockIdx.x; it < total; it += gridDim.x) {
+        const int v = P.mode == 0 ? P.node_base + it : P.list[P.list_base + it];
+        const int32_t *cand;
+        int nc, ncs;
+        if (P.mode == 0) {
+            cand = P.cand + (size_t)it * P.cand_stride;
+            ncs = P.cand_stride;
+            nc = ncs + P.window;
+        } else {
+            cand = P.adj + (size_t)v * P.row_cap;
+            ncs = nc = min(P.deg[v], P.row_cap);
+        }
+        nc = min(nc, TILE);
+        prepare_blob(P.d, P.metric, P.d.rows + (size_t)v * P.d.stride, blob, red);
+        for (int i = warp; i < TILE; i += 2 * NW) {
+            const int i2 = i + NW;
+            const int32_t ca = i < nc ? prune_candidate(P, cand, ncs, v, i) : -1, cb = (i2 < TILE && i2 < nc) ? prune_candidate(P, cand, ncs, v, i2) : -1;
+            const bool va = ca >= 0 && ca != v, vb = cb >= 0 && cb != v;
+            long long ka = KEY_MIN, kb = KEY_MIN;
+            if (va || vb) {
+                float sa, sb;
+                score_f32_pair<METRIC>(P.d, blob, va ? ca : cb, vb ? cb : ca, lane, sa, sb);
+                if (va) ka = topk_key(sa, ca);
+                if (vb) kb = topk_key(sb, cb);
+            }
+            if (lane == 0) {
+                keys[i] = ka;
+                if (i2 < TILE) keys[i2] = kb;
+            }
+        }
+        __syncthreads();
+        bitonic_sort_desc_prune(keys, TILE);
+        int nvalid;
+        {
+            int lo = 0, hi = TILE;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (keys[mid] != KEY_MIN) lo = mid + 1;
+                else hi = mid;
+            }
+            nvalid = lo;
+        }
+        for (int i = tid; i < TILE; i += PRUNE_THREADS) {
+            maxsim[i] = -3.0e38f;
+            state[i] = (i < nvalid && !(i > 0 && keys[i - 1] == keys[i])) ? 0 : 2;
+            ids[i] = i < nvalid ? key_node(keys[i]) : -1;
+        }
+        __syncthreads();
+
+        // ---- Gram matrix of the candidate rows on the tensor cores (3xTF32) ----
+        const float *rowp[PASSES];
+#pragma unroll
+        for (int j = 0; j < PASSES; j++) {
+            const int32_t node = ids[r0 + 32 * j];
+            rowp[j] = node >= 0 ? P.d.rows + (size_t)node * P.d.stride + 4 * c4 : nullptr;
+        }
+        float4 pre[PASSES];
+#pragma unroll
+        for (int j = 0; j < PASSES; j++) pre[j] = (rowp[j] && 4 * c4 < P.d.stride) ? __ldg(reinterpret_cast<const float4 *>(rowp[j])) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < nchunks; c++) {
+            const int b = c & 1;
+            if (c >= 2) tc::wait_bounded(&mma_bar[b], ((b ? commits1 : commits0) - 1u) & 1u);  // the MMAs of chunk c - 2 have read this buffer
+            unsigned char *hi_t = area + b * L::STAGE_BYTES, *lo_t = hi_t + L::TILE_BYTES;
+#pragma unroll
+            for (int j = 0; j < PASSES; j++) {
+                const int r = r0 + 32 * j;
+                const float4 x = pre[j];
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = __fsub_rn(x.x, h.x);
+                h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = __fsub_rn(x.y, h.y);
+                h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = __fsub_rn(x.z, h.z);
+                h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = __fsub_rn(x.w, h.w);
+                const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((c4 ^ (r & 7)) << 4);
+                *reinterpret_cast<float4 *>(hi_t + off) = h;
+                *reinterpret_cast<float4 *>(lo_t + off) = l;
+            }
+            if (c + 1 < nchunks) {
+                const int k1 = (c + 1) * 32 + 4 * c4;
+#pragma unroll
+                for (int j = 0; j < PASSES; j++)
+                    pre[j] = (rowp[j] && k1 < P.d.stride) ? __ldg(reinterpret_cast<const float4 *>(rowp[j] + (c + 1) * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ah = smem_u32(hi_t), al = smem_u32(lo_t);
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    const uint64_t dh = tc::desc_sw128(ah + 32 * ks), dl = tc::desc_sw128(al + 32 * ks);
+                    tc::mma_tf32(tmem, dh, dh, IDESC, (c | ks) != 0 ? 1u : 0u);
+                    tc::mma_tf32(tmem, dh, dl, IDESC, 1u);
+                    tc::mma_tf32(tmem, dl, dh, IDESC, 1u);
+                }
+                tc::commit(&mma_bar[b]);
+            }
+            if (b) commits1++;
+            else commits0++;
+        }
+        if (commits0) tc::wait_bounded(&mma_bar[0], (commits0 - 1u) & 1u);
+        if (commits1) tc::wait_bounded(&mma_bar[1], (commits1 - 1u) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        __syncthreads();  // every thread is past its waits: the staging area may now be overwritten by C
+        {
+            // TMEM -> C: warp w reads lanes 32 (w % 4) .. (its quarter of the rows) and half of the columns
+            const int quarter = warp & 3, half = warp >> 2;
+            if (quarter * 32 < TILE) {
+                const int i = quarter * 32 + lane;
+#pragma unroll 1
+                for (int cg = 0; cg < TILE / 64; cg++) {
+                    const int col0 = half * (TILE / 2) + cg * 32;
+                    uint32_t t[32];
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9]), "=r"(t[10]),
+                          "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15]), "=r"(t[16]), "=r"(t[17]), "=r"(t[18]), "=r"(t[19]), "=r"(t[20]),
+                          "=r"(t[21]), "=r"(t[22]), "=r"(t[23]), "=r"(t[24]), "=r"(t[25]), "=r"(t[26]), "=r"(t[27]), "=r"(t[28]), "=r"(t[29]), "=r"(t[30]),
+                          "=r"(t[31])
+                        : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; j++) C[i * CP + col0 + j] = __uint_as_float(t[j]);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // raw dot products -> the reference's similarity scores (needs the diagonal for L2 / cosine)
+        if (METRIC != JV_METRIC_DOT) {
+            for (int i = tid; i < TILE; i += PRUNE_THREADS) diag[i] = C[i * CP + i];
+            __syncthreads();
+        }
+        for (int idx = tid; idx < TILE * TILE; idx += PRUNE_THREADS) {
+            const int i = idx / TILE, j = idx - i * TILE;
+            const float dotv = C[i * CP + j];
+            float raw;
+            if (METRIC == JV_METRIC_EUCLIDEAN) raw = fmaxf(0.f, __fadd_rn(__fadd_rn(diag[i], diag[j]), -2.0f * dotv));
+            else if (METRIC == JV_METRIC_COSINE) raw = __fdiv_rn(dotv, __fsqrt_rn(__fmul_rn(diag[i], diag[j])));
+            else raw = dotv;
+            C[i * CP + j] = score_map(METRIC, raw);
+        }
+        __syncthreads();
+
+        // ---- the sequential selection, over shared memory only ----
+        int nsel = 0;
+        float currentAlpha = 1.0f;
+        while (currentAlpha <= P.alpha + 1e-6f && nsel < P.degree) {
+            int cursor = 0;
+            while (nsel < P.degree) {
+                if (tid == 0) s_next = INT_MAX;
+                __syncthreads();
+                for (int i = cursor + tid; i < nvalid; i += PRUNE_THREADS)
+                    if (state[i] == 0 && !(maxsim[i] > __fmul_rn(key_score(keys[i]), currentAlpha))) { atomicMin(&s_next, i); break; }
+                __syncthreads();
+                const int pick = s_next;
+                if (pick == INT_MAX) break;
+                nsel++;
+                cursor = pick + 1;
+                for (int i = tid; i < nvalid; i += PRUNE_THREADS) {
+                    if (i == pick) state[i] = 1;
+                    else if (state[i] == 0) {
+                        const float m = fmaxf(maxsim[i], C[i * CP + pick]);
+                        maxsim[i] = m;
+                        if (m > __fmul_rn(key_score(keys[i]), alpha_max)) state[i] = 2;
+                    }
+                }
+                __syncthreads();
+            }
+            currentAlpha += 0.2f;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int w = 0;
+            int32_t *row = P.out_rows ? P.out_rows + (size_t)(P.out_base + it) * P.out_stride : P.adj + (size_t)v * P.row_cap;
+            const int width = P.out_rows ? P.out_stride : P.row_cap;
+            for (int i = 0; i < nvalid; i++)
+                if (state[i] == 1) row[w++] = ids[i];
+            for (int i = w; i < width; i++) row[i] = -1;
+            if (P.out_rows) P.out_deg[P.out_base + it] = w;
+            else P.deg[v] = w;
+            if (P.mode == 1 && P.mark) P.mark[v] = 0;
+        }
+        __syncthreads();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TILE) : "memory");
+}
+
 template <int TILE>
 static size_t gram_smem_bytes(const DataDesc &d)
 {
@@ -590,7 +886,17 @@ static cudaError_t launch_prune_t(const PruneParams &P, int grid, size_t smem, c
     // candidate sets that fit a tile go through the Gram-matrix kernel; anything larger keeps the incremental kernel
     const int ncmax = P.mode == 0 ? P.cand_stride + P.window : P.row_cap;
     cudaError_t e;
-    if (ncmax <= 64) {
+    // Gram products on the tensor cores (tcgen05, 3xTF32) unless JV_PRUNE_GRAM=ffma asks for the CUDA-core kernel
+    static const bool use_tc = !(getenv("JV_PRUNE_GRAM") && getenv("JV_PRUNE_GRAM")[0] == 'f');
+    if (ncmax <= 64 && use_tc) {
+        const size_t gs = gram_tc_smem_bytes<64>(P.d);
+        if ((e = cudaFuncSetAttribute(prune_gram_tc_kernel<METRIC, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs)) != cudaSuccess) return e;
+        prune_gram_tc_kernel<METRIC, 64><<<grid, PRUNE_THREADS, gs, s>>>(P);
+    } else if (ncmax <= 128 && use_tc) {
+        const size_t gs = gram_tc_smem_bytes<128>(P.d);
+        if ((e = cudaFuncSetAttribute(prune_gram_tc_kernel<METRIC, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs)) != cudaSuccess) return e;
+        prune_gram_tc_kernel<METRIC, 128><<<grid, PRUNE_THREADS, gs, s>>>(P);
+    } else if (ncmax <= 64) {
         const size_t gs = gram_smem_bytes<64>(P.d);
         if ((e = cudaFuncSetAttribute(prune_gram_kernel<METRIC, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs)) != cudaSuccess) return e;
         prune_gram_kernel<METRIC, 64><<<grid, PRUNE_THREADS, gs, s>>>(P);
