@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "lib", "libjvector_b200.so")
+# JV_B200_SO: load a tuning variant of the library (tools/) instead of the product build
+SO = os.environ.get("JV_B200_SO") or os.path.join(HERE, "lib", "libjvector_b200.so")
 
 f32p = C.POINTER(C.c_float)
 u8p = C.POINTER(C.c_uint8)

@@ -6,7 +6,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "lib")
+# JV_B200_LIBDIR: where a tuning variant (built with JV_NVCC_EXTRA) goes, next to the product library
+LIBDIR = os.environ.get("JV_B200_LIBDIR") or os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libjvector_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CU = ["kernels_batch.cu", "bq_imma.cu", "bq_umma.cu", "search.cu", "build.cu", "api.cu"]

@@ -105,6 +105,9 @@ struct SearchPlan {
     int pq_smem_m;       // PQ: LUT rows of sub-spaces [0, pq_smem_m) stay in shared memory
     int pq_wide;         // PQ: the 64-register build of the kernel (residency is limited by shared memory anyway)
     int blob_floats;
+    int vis_slots_log, vis_rlog;  // visited set in shared memory: log2(slots), log2(slots per region); 0 = per-CTA global table
+    unsigned vis_idmask;
+    int row_prefetch;             // fp32 / NVQ walks: bulk L2 prefetch of newly visited rows
 };
 // acceptOrds / threshold / rerankFloor of GraphSearcher.search (base:graph/GraphSearcher.java:166-181,427-431, NodeQueue.java:168-230)
 struct SearchFilter {

@@ -56,6 +56,12 @@ struct SearchParams {
     int filtered;                 // accept_bits != nullptr || threshold > 0
     int lenient;                  // insert searches of the builder: a full visited table ends the walk with what it has, a tie tail
                                   // that does not fit is dropped — counted in counters->overflowed, never an error (build.cu)
+    // visited set in shared memory (plan_search decides): 2^vis_slots_log 16-bit slots split into 2^(vis_bits-15) regions; 0 = the
+    // per-CTA global table
+    int vis_slots_log, vis_rlog;
+    unsigned vis_idmask;
+    int pq_thread;     // PQ walk: one thread scores one candidate (score_pq_codes_thread) instead of an 8-lane group
+    int row_prefetch;  // fp32 / NVQ walks: 1 = a bulk L2 prefetch of every newly visited row is issued by the thread that discovered it
     unsigned long long *dbg;  // JV_SEARCH_PROFILE builds only: per-phase cycle totals
 };
 
@@ -68,6 +74,28 @@ __device__ __forceinline__ bool visited_insert(int32_t *t, unsigned mask, int sh
         if (old == v) return false;
         h = (h + 1) & mask;
     }
+    return false;
+}
+
+// The same set in shared memory, 16 bits per slot. x = id * odd mod 2^bits is a bijection on [0, 2^bits) (bits = ceil(log2 n) >= 15);
+// its top (bits - 15) bits choose a REGION of the table, its low 15 bits are the tag stored there (bit 15 = occupied), and a probe
+// sequence never leaves its region — so (region, tag) identifies the id exactly and the set has no false positives. A full region
+// reports through *fail (the query is re-run on the global table, like any visited-table overflow).
+__device__ __forceinline__ bool visited_insert_smem(unsigned short *t, unsigned idmask, int rlog, int32_t v, int *fail)
+{
+    const unsigned x = ((unsigned)v * 0x9E3779B1u) & idmask;
+    const unsigned tag = x & 0x7fffu;
+    const unsigned short val = (unsigned short)(tag | 0x8000u);
+    const unsigned rmask = (1u << rlog) - 1u;
+    unsigned short *base = t + ((size_t)(x >> 15) << rlog);
+    unsigned h = (tag * 0x9E3779B1u) >> (32 - rlog);
+    for (unsigned probes = 0; probes <= rmask; ++probes) {
+        const unsigned short old = atomicCAS(&base[h], (unsigned short)0, val);
+        if (old == 0) return true;
+        if (old == val) return false;
+        h = (h + 1) & rmask;
+    }
+    *fail = 1;
     return false;
 }
 
@@ -169,7 +197,7 @@ constexpr uint8_t F_ACCEPTED = 2;  // acceptOrds.get(node) && score >= threshold
 //   (setEntryPointsFromPreviousLayer re-queues results + evicted only, GraphSearcher.java:316-323).
 // MINB: resident CTAs per SM the register allocation is capped for. PQ is compiled twice: 6 (40 registers; the L2-LUT mode, where
 // nothing else limits residency) and 4 (64 registers; the modes whose shared-memory LUT part allows at most 4-5 CTAs anyway).
-template <int KIND, int METRIC, int MINB>
+template <int KIND, int METRIC, int MINB, bool VSM>
 __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(SearchParams P)
 {
     constexpr int G = GroupOf<KIND>::value;
@@ -190,6 +218,9 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
     uint8_t *cand_slot = cand_acc + MAX_DEGREE;  // fused PQ: position of the candidate inside the expanded node's record
     uint8_t *flags0 = cand_slot + MAX_DEGREE;
     uint8_t *flags1 = flags0 + P.list_alloc;
+    unsigned short *vis = reinterpret_cast<unsigned short *>((reinterpret_cast<uintptr_t>(flags1 + P.list_alloc) + 15) & ~(uintptr_t)15);
+    constexpr bool vsm = VSM;  // visited set in shared memory (16-bit slots) instead of the per-CTA global table
+    __shared__ int s_vfail;
     __shared__ float red[36];
     __shared__ int s_q, s_n, s_m, s_hsize, s_cnt;
     __shared__ int s_drop[2];  // best sortable score that fell off the list, double-buffered like s_posv
@@ -199,6 +230,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
     const int group = tid / G, lane = tid % G;
     const int L = P.rerankK, LC = P.list_cap;
     const unsigned vmask = (unsigned)P.visited_cap - 1u;
+    const int vis_limit = 3 << (P.vis_slots_log > 2 ? P.vis_slots_log - 2 : 0);  // shared-memory table: at most 3/4 full
     int32_t *table = P.visited_tables + (size_t)blockIdx.x * P.visited_cap;
     const int degree = P.g.degree;
 
@@ -216,7 +248,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
         JV_T(t_q0);
         prepare_blob(P.approx, P.metric, q, blobA, red, blobH, splitm);
         if (P.has_rerank) prepare_blob(P.rerank, P.metric, q, blobR, red);
-        {
+        if (vsm) {
+            int4 *t4 = reinterpret_cast<int4 *>(vis);
+            const int4 z = make_int4(0, 0, 0, 0);
+            for (int i = tid; i < (1 << (P.vis_slots_log - 3)); i += SEARCH_THREADS) t4[i] = z;
+            if (tid == 0) s_vfail = 0;
+        } else {
             int4 *t4 = reinterpret_cast<int4 *>(table);
             const int4 m1 = make_int4(-1, -1, -1, -1);
             for (int i = tid; i < (P.visited_cap >> 2); i += SEARCH_THREADS) t4[i] = m1;
@@ -234,7 +271,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                 const int32_t en = P.g.entry_node;
                 cur[0] = topk_key(sc, en);
                 fcur[0] = ((!acc || ((acc[en >> 5] >> (en & 31)) & 1u)) && sc >= P.threshold) ? F_ACCEPTED : 0;
-                visited_insert(table, vmask, P.visited_shift, en);
+                if (vsm) visited_insert_smem(vis, P.vis_idmask, P.vis_rlog, en, &s_vfail);
+                else visited_insert(table, vmask, P.visited_shift, en);
             }
         }
         int size = 1;
@@ -290,10 +328,14 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                 if (nb)
                     for (int t = tid; t < degree; t += SEARCH_THREADS) {
                         const int32_t f = __ldg(nb + t);
-                        if (f >= 0 && visited_insert(table, vmask, P.visited_shift, f)) {
+                        if (f >= 0 && (vsm ? visited_insert_smem(vis, P.vis_idmask, P.vis_rlog, f, &s_vfail) : visited_insert(table, vmask, P.visited_shift, f))) {
                             const int slot = atomicAdd(&s_n, 1);
                             cand_ids[slot] = f;
                             if (KIND == KIND_PQ) cand_slot[slot] = (uint8_t)t;
+                            // the row is needed one barrier from now: start the DRAM -> L2 transfer of all of it at once (one
+                            // UBLKPF per row; bytes in flight that occupy no registers and no shared memory)
+                            if (KIND == KIND_F32 && P.row_prefetch == 1) bulk_prefetch_l2(P.approx.rows + (size_t)f * P.approx.stride, (unsigned)P.approx.stride * 4u);
+                            if (KIND == KIND_NVQ && P.row_prefetch == 1) bulk_prefetch_l2(P.approx.bytes + (size_t)f * P.approx.byte_stride, (unsigned)P.approx.byte_stride);
                         }
                     }
                 // Speculation by the otherwise idle warps (PQ / BQ only: their traversal is a latency chain and HBM is idle, while
@@ -350,7 +392,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                 if (tid == 0) { s_drop[sel ^ 1] = INT_MIN; s_cnt = 0; }
                 const int n = s_n;
                 table_cnt += n;
-                if (table_cnt * 2 > P.visited_cap) {
+                if (vsm ? (table_cnt > vis_limit || s_vfail) : (table_cnt * 2 > P.visited_cap)) {
                     if (P.lenient) truncated = true;
                     else failed = 1;
                     break;
@@ -381,6 +423,14 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                             JV_EMIT(sa, fa);
                             if (two) JV_EMIT(sb, fb);
                         }
+                    }
+                } else if (KIND == KIND_PQ && P.pq_thread) {
+                    // lane = candidate (score_pq_codes_thread): every gather instruction of the warp stays inside one LUT row
+                    for (int i = tid; i < n; i += SEARCH_THREADS) {
+                        const int32_t f = cand_ids[i];
+                        const uint8_t *c = fused ? rec + 4 * degree + (size_t)cand_slot[i] * P.g.fused_code_stride : P.approx.codes + (size_t)f * P.approx.code_stride;
+                        const float sc = score_pq_codes_thread<METRIC>(P.approx, blobA, c, blobH, splitm);
+                        JV_EMIT(sc, f);
                     }
                 } else if (KIND == KIND_PQ && fused) {
                     // FusedPQDecoder.similarityToNeighbor (FusedPQDecoder.java:107-114): the code row sits inside the record just read
@@ -635,7 +685,7 @@ static int search_smemA_floats(const DataDesc &approx, int pq_smem_m)
     return (pq_smem_m * approx.k + 3) & ~3;
 }
 
-static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, int rerankK, int list_alloc, int pq_smem_m)
+static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, int rerankK, int list_alloc, int pq_smem_m, int vis_slots_log = 0)
 {
     size_t b = (size_t)search_smemA_floats(approx, pq_smem_m) * 4;
     if (rerank) b += (size_t)blob_floats(*rerank) * 4;
@@ -644,46 +694,65 @@ static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, 
     b += (size_t)((rerankK + 2) & ~1) * 8;            // result heap (1-based)
     b += (size_t)MAX_DEGREE * 4 + (size_t)MAX_DEGREE * 2; // candidate ids + accept flags + record slots
     b += (size_t)list_alloc * 2;                      // entry flags of the two buffers
-    return (b + 15) & ~(size_t)15;
+    b = (b + 15) & ~(size_t)15;
+    if (vis_slots_log) b += (size_t)2 << vis_slots_log;  // visited set, 16 bits per slot
+    return b;
 }
 
-constexpr int MINB_DEFAULT = JV_SEARCH_MINB, MINB_PQ_LITE = JV_SEARCH_MINB_PQ, MINB_PQ_WIDE = 4;
+#ifndef JV_VISITED_SMEM_DEFAULT
+#define JV_VISITED_SMEM_DEFAULT true
+#endif
+#ifndef JV_PQ_THREAD_DEFAULT
+#define JV_PQ_THREAD_DEFAULT 0
+#endif
+#ifndef JV_SEARCH_MINB_PQ_WIDE
+#define JV_SEARCH_MINB_PQ_WIDE 4
+#endif
+#ifndef JV_ROW_PREFETCH_DEFAULT
+#define JV_ROW_PREFETCH_DEFAULT 1
+#endif
+constexpr int MINB_DEFAULT = JV_SEARCH_MINB, MINB_PQ_LITE = JV_SEARCH_MINB_PQ, MINB_PQ_WIDE = JV_SEARCH_MINB_PQ_WIDE;
 
-template <int KIND, int METRIC, int MINB>
+template <int KIND, int METRIC, int MINB, bool VSM>
 static cudaError_t occupancy_of(size_t smem, int *blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute(graph_search_kernel<KIND, METRIC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(graph_search_kernel<KIND, METRIC, MINB, VSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, graph_search_kernel<KIND, METRIC, MINB>, SEARCH_THREADS, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, graph_search_kernel<KIND, METRIC, MINB, VSM>, SEARCH_THREADS, smem);
 }
 
-#define JV_SEARCH_DISPATCH(kind, metric, pq_wide, CALL)                                                  \
+#define JV_SEARCH_DISPATCH_V(kind, metric, pq_wide, V, CALL)                                                  \
     do {                                                                                        \
         if ((kind) == KIND_F32 && (pq_wide)) {                                                  \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN, MINB_PQ_WIDE); } \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT, MINB_PQ_WIDE); } \
-            else { CALL(KIND_F32, JV_METRIC_COSINE, MINB_PQ_WIDE); }                            \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN, MINB_PQ_WIDE, V); } \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT, MINB_PQ_WIDE, V); } \
+            else { CALL(KIND_F32, JV_METRIC_COSINE, MINB_PQ_WIDE, V); }                            \
         } else if ((kind) == KIND_F32) {                                                        \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN, MINB_DEFAULT); }       \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT, MINB_DEFAULT); }              \
-            else { CALL(KIND_F32, JV_METRIC_COSINE, MINB_DEFAULT); }                                          \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN, MINB_DEFAULT, V); }       \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT, MINB_DEFAULT, V); }              \
+            else { CALL(KIND_F32, JV_METRIC_COSINE, MINB_DEFAULT, V); }                                          \
         } else if ((kind) == KIND_PQ && (pq_wide)) {                                            \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_PQ, JV_METRIC_EUCLIDEAN, MINB_PQ_WIDE); } \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_PQ, JV_METRIC_DOT, MINB_PQ_WIDE); } \
-            else { CALL(KIND_PQ, JV_METRIC_COSINE, MINB_PQ_WIDE); }                             \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_PQ, JV_METRIC_EUCLIDEAN, MINB_PQ_WIDE, V); } \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_PQ, JV_METRIC_DOT, MINB_PQ_WIDE, V); } \
+            else { CALL(KIND_PQ, JV_METRIC_COSINE, MINB_PQ_WIDE, V); }                             \
         } else if ((kind) == KIND_PQ) {                                                         \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_PQ, JV_METRIC_EUCLIDEAN, MINB_PQ_LITE); } \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_PQ, JV_METRIC_DOT, MINB_PQ_LITE); } \
-            else { CALL(KIND_PQ, JV_METRIC_COSINE, MINB_PQ_LITE); }                             \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_PQ, JV_METRIC_EUCLIDEAN, MINB_PQ_LITE, V); } \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_PQ, JV_METRIC_DOT, MINB_PQ_LITE, V); } \
+            else { CALL(KIND_PQ, JV_METRIC_COSINE, MINB_PQ_LITE, V); }                             \
         } else if ((kind) == KIND_BQ) {                                                         \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_BQ, JV_METRIC_EUCLIDEAN, MINB_DEFAULT); }        \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_BQ, JV_METRIC_DOT, MINB_DEFAULT); }               \
-            else { CALL(KIND_BQ, JV_METRIC_COSINE, MINB_DEFAULT); }                                           \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_BQ, JV_METRIC_EUCLIDEAN, MINB_DEFAULT, V); }        \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_BQ, JV_METRIC_DOT, MINB_DEFAULT, V); }               \
+            else { CALL(KIND_BQ, JV_METRIC_COSINE, MINB_DEFAULT, V); }                                           \
         } else {                                                                                \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_NVQ, JV_METRIC_EUCLIDEAN, MINB_DEFAULT); }       \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_NVQ, JV_METRIC_DOT, MINB_DEFAULT); }              \
-            else { CALL(KIND_NVQ, JV_METRIC_COSINE, MINB_DEFAULT); }                                          \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_NVQ, JV_METRIC_EUCLIDEAN, MINB_DEFAULT, V); }       \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_NVQ, JV_METRIC_DOT, MINB_DEFAULT, V); }              \
+            else { CALL(KIND_NVQ, JV_METRIC_COSINE, MINB_DEFAULT, V); }                                          \
         }                                                                                       \
+    } while (0)
+#define JV_SEARCH_DISPATCH(kind, metric, pq_wide, vsm, CALL)                    \
+    do {                                                                       \
+        if (vsm) JV_SEARCH_DISPATCH_V(kind, metric, pq_wide, true, CALL);      \
+        else JV_SEARCH_DISPATCH_V(kind, metric, pq_wide, false, CALL);         \
     } while (0)
 
 cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const GraphDesc &g, int topK, int rerankK, int nq,
@@ -731,19 +800,58 @@ cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const Gr
     if (vcap < 2048) vcap = 2048;
     if (vcap > (1 << 22)) vcap = 1 << 22;
     plan->visited_cap = next_pow2i(vcap);
+    // Visited set in shared memory (16-bit slots, see visited_insert_smem): no L2 round trip per neighbour, no 64 KB table to clear
+    // per query, nothing of it in L2. Taken on the first attempt when the table a walk of this effort needs fits 32 KB and every
+    // region keeps at least 32 slots; a query that outgrows it (or fills one region) is re-run on the global table
+    // (visited_cap_hint > 0).
+    // JV_VISITED=global|smem overrides, JV_VISITED_SMEM_SLOTS sets the slot count.
+    plan->vis_slots_log = 0;
+    plan->vis_rlog = 0;
+    plan->vis_idmask = 0;
+    {
+        const char *vm = getenv("JV_VISITED");
+        const char *vs = getenv("JV_VISITED_SMEM_SLOTS");
+        int bits = 15;
+        while ((1ll << bits) < g.n) bits++;
+        int slots = vs ? next_pow2i(atoi(vs)) : plan->visited_cap / 2;
+        int slog = 0;
+        while ((1 << slog) < slots) slog++;
+        // many regions (large n) want more slots each: grow the table up to 32 KB (10M nodes: 512 regions of 32 slots, ~6 expected
+        // entries each for a 3 200-node walk)
+        while (!vs && slog - (bits - 15) < 7 && slog < 14) slog++;
+        const int rlog = slog - (bits - 15);
+        const bool want = vm ? vm[0] == 's' : JV_VISITED_SMEM_DEFAULT;
+        if (want && visited_cap_hint <= 0 && slog >= 10 && slog <= 14 && rlog >= 5) {
+            const size_t sb = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, plan->pq_smem_m, slog);
+            if (sb <= 227 * 1024) {
+                plan->vis_slots_log = slog;
+                plan->vis_rlog = rlog;
+                plan->vis_idmask = (unsigned)((1ull << bits) - 1ull);
+                plan->smem_bytes = sb;
+            }
+        }
+    }
+    // JV_ROW_PREFETCH=0|1|2: L2 prefetch of the newly visited rows (fp32 / NVQ walks)
+    {
+        const char *rp = getenv("JV_ROW_PREFETCH");
+        plan->row_prefetch = rp ? atoi(rp) : JV_ROW_PREFETCH_DEFAULT;
+        if (approx.kind == KIND_NVQ && ((approx.byte_stride & 15) || plan->row_prefetch != 1)) plan->row_prefetch = 0;
+        if (approx.kind != KIND_F32 && approx.kind != KIND_NVQ) plan->row_prefetch = 0;
+    }
     int bps = 0;
     cudaError_t e = cudaSuccess;
     const int metric_for_occ = JV_METRIC_DOT;
-#define CALL(K, M, B) e = occupancy_of<K, M, B>(plan->smem_bytes, &bps)
-    JV_SEARCH_DISPATCH(approx.kind, metric_for_occ, false, CALL);
+#define CALL(K, M, B, V) e = occupancy_of<K, M, B, V>(plan->smem_bytes, &bps)
+    JV_SEARCH_DISPATCH(approx.kind, metric_for_occ, false, plan->vis_slots_log != 0, CALL);
     plan->pq_wide = 0;
     if (e == cudaSuccess && approx.kind == KIND_PQ) {
         // the 64-register build wherever shared memory (not registers) is what limits residency
         int bw = 0;
         const int lite = bps;
-        JV_SEARCH_DISPATCH(approx.kind, metric_for_occ, true, CALL);
+        JV_SEARCH_DISPATCH(approx.kind, metric_for_occ, true, plan->vis_slots_log != 0, CALL);
         bw = bps;
-        if (e == cudaSuccess && bw >= lite) plan->pq_wide = 1;
+        const char *pw = getenv("JV_PQ_WIDE");  // 0 | 1: force the register build (tuning)
+        if (e == cudaSuccess && (pw ? pw[0] == '1' : bw >= lite)) plan->pq_wide = 1;
         else bps = lite;
     }
     if (e == cudaSuccess && approx.kind == KIND_F32) {
@@ -751,7 +859,7 @@ cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const Gr
         const char *w = getenv("JV_SEARCH_WIDE");
         if (w && w[0] == '1') {
             plan->pq_wide = 1;
-            JV_SEARCH_DISPATCH(approx.kind, metric_for_occ, true, CALL);
+            JV_SEARCH_DISPATCH(approx.kind, metric_for_occ, true, plan->vis_slots_log != 0, CALL);
         }
     }
 #undef CALL
@@ -766,7 +874,7 @@ cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const Gr
 
 size_t search_scratch_bytes(const SearchPlan &p)
 {
-    size_t b = (size_t)p.ctas * p.visited_cap * sizeof(int32_t);
+    size_t b = p.vis_slots_log ? 256 : (size_t)p.ctas * p.visited_cap * sizeof(int32_t);
     if (p.blob_in_global) b += (size_t)p.ctas * p.blob_floats * sizeof(float) + 256;
     return b;
 }
@@ -818,8 +926,16 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
     P.smemA_floats = search_smemA_floats(approx, plan.pq_smem_m);
     P.blobR_floats = rerank ? blob_floats(*rerank) : 0;
     P.blob_global = nullptr;
+    P.vis_slots_log = plan.vis_slots_log;
+    P.vis_rlog = plan.vis_rlog;
+    P.vis_idmask = plan.vis_idmask;
+    P.row_prefetch = plan.row_prefetch;
+    {
+        const char *pt = getenv("JV_PQ_SCORE");  // thread | group
+        P.pq_thread = pt ? (pt[0] == 't') : JV_PQ_THREAD_DEFAULT;
+    }
     if (plan.blob_in_global) {
-        size_t off = ((size_t)plan.ctas * plan.visited_cap * sizeof(int32_t) + 255) & ~(size_t)255;
+        size_t off = ((plan.vis_slots_log ? 256 : (size_t)plan.ctas * plan.visited_cap * sizeof(int32_t)) + 255) & ~(size_t)255;
         P.blob_global = reinterpret_cast<float *>(reinterpret_cast<char *>(scratch_dev) + off);
     }
     P.dbg = nullptr;
@@ -831,12 +947,12 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
 #endif
     cudaError_t e = cudaMemsetAsync(work_counter_dev, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
-#define CALL(K, M, B)                                                                                                              \
-    do {                                                                                                                           \
-        e = cudaFuncSetAttribute(graph_search_kernel<K, M, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes); \
-        if (e == cudaSuccess) graph_search_kernel<K, M, B><<<plan.ctas, SEARCH_THREADS, plan.smem_bytes, s>>>(P);                  \
+#define CALL(K, M, B, V)                                                                                                              \
+    do {                                                                                                                              \
+        e = cudaFuncSetAttribute(graph_search_kernel<K, M, B, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes); \
+        if (e == cudaSuccess) graph_search_kernel<K, M, B, V><<<plan.ctas, SEARCH_THREADS, plan.smem_bytes, s>>>(P);                  \
     } while (0)
-    JV_SEARCH_DISPATCH(approx.kind, metric, plan.pq_wide != 0, CALL);
+    JV_SEARCH_DISPATCH(approx.kind, metric, plan.pq_wide != 0, plan.vis_slots_log != 0, CALL);
 #undef CALL
     if (e != cudaSuccess) return e;
     g_launches++;

@@ -25,6 +25,8 @@ ap.add_argument("--n", type=int, default=1_000_000)
 ap.add_argument("--nq", type=int, default=10_000)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--smem-m", default="0,24,32,48,64,96")
+ap.add_argument("--envs", default="", help="';'-separated settings, each 'A=1,B=2' (empty = defaults): every workload is timed under each")
+ap.add_argument("--workloads", default="", help="comma list of c2,c3 for --envs")
 ap.add_argument("--ncu", action="store_true", help="bracket the timed launches with cudaProfilerStart/Stop (ncu --profile-from-start off)")
 a = ap.parse_args()
 
@@ -50,6 +52,45 @@ def run(approx, rr, label):
     return best
 
 
+def with_env(setting, fn):
+    kv = [x.split("=", 1) for x in setting.split(",") if x]
+    old = {k: os.environ.get(k) for k, _ in kv}
+    for k, v in kv:
+        os.environ[k] = v
+    try:
+        return fn()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def make_pq():
+    import oracle_lib as o
+    rs = np.random.default_rng(bench.SEED + 99)
+    sel = np.sort(rs.choice(a.n, min(a.n, 20000), replace=False))
+    sample = w.base_dev[cx.torch.from_numpy(sel).cuda()].cpu().numpy()
+    cb, _, _ = o.train_pq_numpy(rs, sample, 96, 256, iters=6)
+    codes = jv.pq_encode_all(w.vec, cb, 96, 256)
+    pqv = jv.PQVectors(codes, cb, 768, 256)
+    w.gi.fuse_pq(pqv)
+    return pqv
+
+
+if a.envs:
+    wl = [x for x in (a.workloads or "c2,c3").split(",") if x]
+    pqv = make_pq() if "c3" in wl else None
+    refs = {}
+    for setting in a.envs.split(";"):
+        for k in wl:
+            r = with_env(setting, lambda: run(w.vec, None, "c2 [%s]" % setting) if k == "c2" else run(pqv, w.vec, "c3 [%s]" % setting))
+            if k not in refs:
+                refs[k] = r.nodes
+            elif not np.array_equal(refs[k], r.nodes):
+                print("   !! id lists differ from the first setting")
+    sys.exit(0)
 if a.workload == "seam":
     # the host-driven multi-query step (jv_query_batch_score -> score_ragged_kernel): 10 000 searches x 32 candidates
     rs = np.random.default_rng(bench.SEED + 3)
