@@ -108,6 +108,7 @@ struct SearchPlan {
     int vis_slots_log, vis_rlog;  // visited set in shared memory: log2(slots), log2(slots per region); 0 = per-CTA global table
     unsigned vis_idmask;
     int row_prefetch;             // fp32 / NVQ walks: bulk L2 prefetch of newly visited rows
+    int pq_rows;                  // PQ walk: lane = candidate, warp = partial sum
 };
 // acceptOrds / threshold / rerankFloor of GraphSearcher.search (base:graph/GraphSearcher.java:166-181,427-431, NodeQueue.java:168-230)
 struct SearchFilter {

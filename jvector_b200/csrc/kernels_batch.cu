@@ -73,13 +73,6 @@ __global__ void __launch_bounds__(RAGGED_THREADS) score_ragged_kernel(DataDesc d
         const float *blob = blobs + (size_t)q * blob_stride;
         const int group = threadIdx.x / G, lane = threadIdx.x % G;
         constexpr int NG = RAGGED_THREADS / G;
-        if (KIND == KIND_F32) {
-            // every row this CTA will score starts its DRAM -> L2 transfer now (one UBLKPF each), before the first dot product
-            for (int i = c0 + (int)threadIdx.x; i < c1; i += RAGGED_THREADS) {
-                const int node = ids[begin + i];
-                if (node >= 0 && node < d.n) bulk_prefetch_l2(d.rows + (size_t)node * d.stride, (unsigned)d.stride * 4u);
-            }
-        }
         for (int i = c0 + group; i < c1; i += NG) {
             const int node = ids[begin + i];
             float sc = 0.f;

@@ -296,64 +296,44 @@ __device__ __forceinline__ float score_pq_codes(const DataDesc &d, const float *
     return score_map(METRIC, s);
 }
 
-// The same score computed by ONE thread (search kernel: lane = candidate). The 8 lanes of score_pq_codes each keep one running
-// sum (lane g: words g, g + 8, ... in order, then tail element g) folded by a xor butterfly (4, 2, 1); here the 8 sums are 8
-// registers of one thread, filled in the same order and folded in the same tree, so the result is the same bits. What changes is
-// the memory pattern: the 32 lanes of a warp now look up the SAME sub-space at one time, so one gather instruction touches the
-// (at most) 8 lines of one 1 KB LUT row instead of 32 lines of 8 rows — the L1 tag stage takes a line per cycle, and 32-line
-// gathers were what bounded the PQ walk (profiles/r2_ncu_search_c3.md).
+// The same score split the way the butterfly of score_pq_codes splits it: lane g of the 8 keeps the running sum of words g, g + 8, ...
+// (then tail element g), and the 8 sums are folded by xor 4, 2, 1. score_pq_partial computes sum g alone (codes already in
+// shared memory), pq_fold8 folds eight of them in the same tree, so partial sums computed by eight different WARPS give the same
+// bits. The search kernel uses this to make every gather instruction of a warp stay inside one 1 KB LUT row (lane = candidate,
+// warp = partial sum): at most 8 lines per instruction instead of 32.
 template <int METRIC>
-__device__ __forceinline__ float score_pq_codes_thread(const DataDesc &d, const float *lut_lo, const uint8_t *__restrict__ c, const float *lut_hi = nullptr,
-                                                       int split_m = 1 << 30)
+__device__ __forceinline__ void score_pq_partial(const DataDesc &d, const float *lut_lo, const float *lut_hi, int split_m, const uint8_t *c, int g, float &s_out,
+                                                 float &a_out)
 {
-    if (!lut_hi) lut_hi = lut_lo;
-    const int k = d.k, M = d.M;
-    const int M4 = M >> 2;
-    float s[8], a[8];
-#pragma unroll
-    for (int g = 0; g < 8; g++) { s[g] = 0.f; a[g] = 0.f; }
+    const int k = d.k, M = d.M, M4 = M >> 2;
+    float s = 0.f, a = 0.f;
     const uint32_t *c4 = reinterpret_cast<const uint32_t *>(c);
-    for (int j0 = 0; j0 < M4; j0 += 8) {
-        uint32_t w[8];
-        if (j0 + 8 <= M4 && ((reinterpret_cast<uintptr_t>(c4 + j0) & 15) == 0)) {
-            const uint4 x = __ldg(reinterpret_cast<const uint4 *>(c4 + j0)), y = __ldg(reinterpret_cast<const uint4 *>(c4 + j0) + 1);
-            w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
-        } else {
-#pragma unroll
-            for (int g = 0; g < 8; g++) w[g] = j0 + g < M4 ? __ldg(c4 + j0 + g) : 0u;
-        }
-#pragma unroll
-        for (int g = 0; g < 8; g++) {
-            const int j = j0 + g;
-            if (j < M4) {
-                const int base = (4 * j) * k;
-                const float *lut = 4 * j < split_m ? lut_lo : lut_hi;
-                const int i0 = base + (int)(w[g] & 255u), i1 = base + k + (int)((w[g] >> 8) & 255u), i2 = base + 2 * k + (int)((w[g] >> 16) & 255u),
-                          i3 = base + 3 * k + (int)(w[g] >> 24);
-                s[g] = __fadd_rn(s[g], lut[i0]); s[g] = __fadd_rn(s[g], lut[i1]); s[g] = __fadd_rn(s[g], lut[i2]); s[g] = __fadd_rn(s[g], lut[i3]);
-                if (METRIC == JV_METRIC_COSINE) {
-                    a[g] = __fadd_rn(a[g], __ldg(d.mag + i0)); a[g] = __fadd_rn(a[g], __ldg(d.mag + i1));
-                    a[g] = __fadd_rn(a[g], __ldg(d.mag + i2)); a[g] = __fadd_rn(a[g], __ldg(d.mag + i3));
-                }
-            }
+    for (int j = g; j < M4; j += 8) {
+        const uint32_t w = c4[j];
+        const int base = (4 * j) * k;
+        const float *lut = 4 * j < split_m ? lut_lo : lut_hi;
+        const int i0 = base + (int)(w & 255u), i1 = base + k + (int)((w >> 8) & 255u), i2 = base + 2 * k + (int)((w >> 16) & 255u),
+                  i3 = base + 3 * k + (int)(w >> 24);
+        s = __fadd_rn(s, lut[i0]); s = __fadd_rn(s, lut[i1]); s = __fadd_rn(s, lut[i2]); s = __fadd_rn(s, lut[i3]);
+        if (METRIC == JV_METRIC_COSINE) {
+            a = __fadd_rn(a, __ldg(d.mag + i0)); a = __fadd_rn(a, __ldg(d.mag + i1));
+            a = __fadd_rn(a, __ldg(d.mag + i2)); a = __fadd_rn(a, __ldg(d.mag + i3));
         }
     }
-#pragma unroll
-    for (int g = 0; g < 3; g++) {
-        const int m = 4 * M4 + g;
-        if (m < M) {
-            const int idx = m * k + (int)c[m];
-            s[g] = __fadd_rn(s[g], (m < split_m ? lut_lo : lut_hi)[idx]);
-            if (METRIC == JV_METRIC_COSINE) a[g] = __fadd_rn(a[g], __ldg(d.mag + idx));
-        }
+    const int m = 4 * M4 + g;
+    if (m < M) {
+        const int idx = m * k + (int)c[m];
+        s = __fadd_rn(s, (m < split_m ? lut_lo : lut_hi)[idx]);
+        if (METRIC == JV_METRIC_COSINE) a = __fadd_rn(a, __ldg(d.mag + idx));
     }
-    // group_sum<8>: xor 4, xor 2, xor 1
-    float t = __fadd_rn(__fadd_rn(__fadd_rn(s[0], s[4]), __fadd_rn(s[2], s[6])), __fadd_rn(__fadd_rn(s[1], s[5]), __fadd_rn(s[3], s[7])));
-    if (METRIC == JV_METRIC_COSINE) {
-        const float u = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[4]), __fadd_rn(a[2], a[6])), __fadd_rn(__fadd_rn(a[1], a[5]), __fadd_rn(a[3], a[7])));
-        t = __fdiv_rn(t, __fsqrt_rn(__fmul_rn(u, lut_hi[M * k])));
-    }
-    return score_map(METRIC, t);
+    s_out = s;
+    a_out = a;
+}
+// p[g * stride], g = 0..7 -> group_sum<8>'s tree (xor 4, xor 2, xor 1)
+__device__ __forceinline__ float pq_fold8(const float *p, int stride)
+{
+    return __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[4 * stride]), __fadd_rn(p[2 * stride], p[6 * stride])),
+                     __fadd_rn(__fadd_rn(p[stride], p[5 * stride]), __fadd_rn(p[3 * stride], p[7 * stride])));
 }
 
 template <int METRIC>

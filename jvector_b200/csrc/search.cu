@@ -60,7 +60,8 @@ struct SearchParams {
     // per-CTA global table
     int vis_slots_log, vis_rlog;
     unsigned vis_idmask;
-    int pq_thread;     // PQ walk: one thread scores one candidate (score_pq_codes_thread) instead of an 8-lane group
+    int early_pf;      // request the adjacency / FusedPQ record of a new candidate that lands among the next two pops at score time
+    int pq_rows;       // PQ walk: lane = candidate, warp = partial sum (score_pq_partial) instead of an 8-lane group per candidate
     int row_prefetch;  // fp32 / NVQ walks: 1 = a bulk L2 prefetch of every newly visited row is issued by the thread that discovered it
     unsigned long long *dbg;  // JV_SEARCH_PROFILE builds only: per-phase cycle totals
 };
@@ -168,8 +169,17 @@ __device__ __forceinline__ void heap_down(long long *h, int size, int pos)
 #ifndef JV_SEARCH_MINB_PQ
 #define JV_SEARCH_MINB_PQ 6  // tools/sweep_pq_minb.sh: 5 -> 777k q/s, 6 -> 817k, 8 -> 592k (c3, LUT in L2)
 #endif
-constexpr int SEARCH_THREADS = JV_SEARCH_THREADS;
-constexpr int HEAP_TID = SEARCH_THREADS - 32;  // the thread that maintains the result heap (lane 0 of the last warp)
+// CTA width per walking scorer. fp32 / NVQ rows are scored a warp per row and, with every new row already on its way to L2
+// (bulk prefetch), the walk gains from MORE queries in flight rather than more warps per query: 128 threads, 10 CTAs per SM
+// (c2: 14.7 -> 14.2 ms). PQ / BQ score 8 lanes per candidate and want a hop's ~28 candidates in one pass: 256 threads.
+#ifndef JV_SEARCH_THREADS_ROWS
+#define JV_SEARCH_THREADS_ROWS 128
+#endif
+template <int KIND>
+struct SearchThreads {
+    static constexpr int value = (KIND == KIND_F32 || KIND == KIND_NVQ) ? JV_SEARCH_THREADS_ROWS : JV_SEARCH_THREADS;
+};
+static int search_threads_of(int kind) { return (kind == KIND_F32 || kind == KIND_NVQ) ? JV_SEARCH_THREADS_ROWS : JV_SEARCH_THREADS; }
 
 // optional phase timers (tools/: build with JV_NVCC_EXTRA=-DJV_SEARCH_PROFILE); compiled out of the product build
 #ifdef JV_SEARCH_PROFILE
@@ -198,8 +208,10 @@ constexpr uint8_t F_ACCEPTED = 2;  // acceptOrds.get(node) && score >= threshold
 // MINB: resident CTAs per SM the register allocation is capped for. PQ is compiled twice: 6 (40 registers; the L2-LUT mode, where
 // nothing else limits residency) and 4 (64 registers; the modes whose shared-memory LUT part allows at most 4-5 CTAs anyway).
 template <int KIND, int METRIC, int MINB, bool VSM>
-__global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(SearchParams P)
+__global__ void __launch_bounds__(SearchThreads<KIND>::value, MINB) graph_search_kernel(SearchParams P)
 {
+    constexpr int SEARCH_THREADS = SearchThreads<KIND>::value;
+    constexpr int HEAP_TID = SEARCH_THREADS - 32;  // the thread that maintains the result heap (lane 0 of the last warp)
     constexpr int G = GroupOf<KIND>::value;
     constexpr int NG = SEARCH_THREADS / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -220,7 +232,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
     uint8_t *flags1 = flags0 + P.list_alloc;
     unsigned short *vis = reinterpret_cast<unsigned short *>((reinterpret_cast<uintptr_t>(flags1 + P.list_alloc) + 15) & ~(uintptr_t)15);
     constexpr bool vsm = VSM;  // visited set in shared memory (16-bit slots) instead of the per-CTA global table
+    uint32_t *pq_stage = reinterpret_cast<uint32_t *>(vis + (VSM ? (1 << P.vis_slots_log) : 0));  // PQ row mode: the hop's code rows
+    float *pq_part = reinterpret_cast<float *>(pq_stage + P.g.degree * ((P.approx.code_stride >> 2) + 1));  // and its partial sums
     __shared__ int s_vfail;
+    __shared__ long long s_nk;  // key of the second unexpanded entry behind the one being expanded (see JV_EMIT)
     __shared__ float red[36];
     __shared__ int s_q, s_n, s_m, s_hsize, s_cnt;
     __shared__ int s_drop[2];  // best sortable score that fell off the list, double-buffered like s_posv
@@ -318,8 +333,18 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                 const uint8_t *rec = fused ? P.g.fused + (size_t)node * P.g.fused_rec : nullptr;
                 if (fused) {
                     nb = reinterpret_cast<const int32_t *>(rec);
-                    // the code rows of this record are needed one barrier from now: pull the whole record towards L2 at once
-                    if (tid >= 64) {
+                    if (P.pq_rows) {
+                        // the record's code rows do not depend on which neighbours turn out to be new: the warps that have no
+                        // neighbour to test copy ALL of them (degree x code_stride contiguous bytes) into shared memory while
+                        // warp 0 runs visited.add(); the scoring phase then finds candidate i's codes at slot cand_slot[i]
+                        const int cw = P.approx.code_stride >> 2, cws = cw + 1;
+                        const uint32_t *src = reinterpret_cast<const uint32_t *>(rec + 4 * degree);
+                        for (int t = tid - 64; t >= 0 && t < degree * cw; t += SEARCH_THREADS - 64) {
+                            const int i = t / cw;
+                            pq_stage[i * cws + (t - i * cw)] = __ldg(src + t);
+                        }
+                    } else if (tid >= 64) {
+                        // the code rows of this record are needed one barrier from now: pull the whole record towards L2 at once
                         const int o = (tid - 64) * 128;
                         if (o < P.g.fused_rec) prefetch_l2(rec + o);
                     }
@@ -335,7 +360,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                             // the row is needed one barrier from now: start the DRAM -> L2 transfer of all of it at once (one
                             // UBLKPF per row; bytes in flight that occupy no registers and no shared memory)
                             if (KIND == KIND_F32 && P.row_prefetch == 1) bulk_prefetch_l2(P.approx.rows + (size_t)f * P.approx.stride, (unsigned)P.approx.stride * 4u);
-                            if (KIND == KIND_NVQ && P.row_prefetch == 1) bulk_prefetch_l2(P.approx.bytes + (size_t)f * P.approx.byte_stride, (unsigned)P.approx.byte_stride);
+                            if (KIND == KIND_NVQ && P.row_prefetch == 1) {
+                                bulk_prefetch_l2(P.approx.bytes + (size_t)f * P.approx.byte_stride, (unsigned)P.approx.byte_stride);
+                                prefetch_l2(P.approx.params + (size_t)f * 4 * P.approx.nsub);  // {min, max, growthRate, midpoint} per sub-vector
+                            }
                         }
                     }
                 // Speculation by the otherwise idle warps (PQ / BQ only: their traversal is a latency chain and HBM is idle, while
@@ -349,6 +377,18 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                         const int pp = p + (tid - 31);
                         if (pp < size && !(fcur[pp] & F_EXPANDED)) prefetch_l2(P.g.adj0 + (size_t)key_node(cur[pp]) * degree);
                     }
+                }
+                if (lvl == 0 && P.early_pf && tid == 36) {
+                    // the next pop is the best of {unexpanded old entries, this hop's new candidates}: a new candidate that beats the
+                    // SECOND unexpanded old entry is among the next two pops, so its adjacency (or FusedPQ record) is requested the
+                    // moment its score is known (JV_EMIT) instead of after the merge
+                    int found = 0;
+                    const int end = min(size, p + 17);
+                    long long nk = end > p + 1 ? cur[end - 1] : KEY_MIN;
+                    for (int i = p + 1; i < end; i++)
+                        if (!(fcur[i] & F_EXPANDED) && ++found == 2) { nk = cur[i]; break; }
+                    if (found < 2 && end == size) nk = KEY_MIN;
+                    s_nk = nk;
                 }
                 if (lvl == 0 && (KIND == KIND_PQ || KIND == KIND_BQ)) {
                     const int w = tid >> 5;
@@ -404,6 +444,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
 #define JV_EMIT(sc_, f_)                                                                                                            \
     do {                                                                                                                            \
         const long long key_ = topk_key((sc_), (f_));                                                                               \
+        if (lvl == 0 && P.early_pf && key_ > s_nk) {                                                                                \
+            if (KIND == KIND_PQ && P.g.fused) bulk_prefetch_l2(P.g.fused + (size_t)(f_) * P.g.fused_rec, (unsigned)P.g.fused_rec);  \
+            else prefetch_l2(P.g.adj0 + (size_t)(f_) * degree);                                                                     \
+        }                                                                                                                           \
         if (dead < 0 && size == LC && key_ < cur[LC - 1]) atomicMax(&s_drop[sel], float_to_sortable(sc_));                          \
         else {                                                                                                                      \
             const int m_ = atomicAdd(&s_m, 1);                                                                                      \
@@ -424,12 +468,32 @@ __global__ void __launch_bounds__(SEARCH_THREADS, MINB) graph_search_kernel(Sear
                             if (two) JV_EMIT(sb, fb);
                         }
                     }
-                } else if (KIND == KIND_PQ && P.pq_thread) {
-                    // lane = candidate (score_pq_codes_thread): every gather instruction of the warp stays inside one LUT row
+                } else if (KIND == KIND_PQ && P.pq_rows) {
+                    // lane = candidate, warp = one of the 8 partial sums of the ADC score (score_pq_partial): the code rows of the
+                    // hop are staged in shared memory by one coalesced pass, then every gather instruction of a warp reads ONE LUT row
+                    const int cw = P.approx.code_stride >> 2, cws = cw + 1;  // odd word stride: no bank conflicts across candidates
+                    if (!fused) {
+                        for (int t = tid; t < n * cw; t += SEARCH_THREADS) {
+                            const int i = t / cw, wd = t - i * cw;
+                            pq_stage[i * cws + wd] = __ldg(reinterpret_cast<const uint32_t *>(P.approx.codes + (size_t)cand_ids[i] * P.approx.code_stride) + wd);
+                        }
+                        __syncthreads();
+                    }
+                    const int pstride = (degree + 31) & ~31;
+                    for (int g = tid >> 5; g < 8; g += SEARCH_THREADS / 32)
+                        for (int i = tid & 31; i < n; i += 32) {
+                            float ps, pa;
+                            score_pq_partial<METRIC>(P.approx, blobA, blobH, splitm, reinterpret_cast<const uint8_t *>(pq_stage + (fused ? (int)cand_slot[i] : i) * cws), g, ps, pa);
+                            pq_part[g * pstride + i] = ps;
+                            if (METRIC == JV_METRIC_COSINE) pq_part[(8 + g) * pstride + i] = pa;
+                        }
+                    __syncthreads();
                     for (int i = tid; i < n; i += SEARCH_THREADS) {
+                        float sraw = pq_fold8(pq_part + i, pstride);
+                        if (METRIC == JV_METRIC_COSINE)
+                            sraw = __fdiv_rn(sraw, __fsqrt_rn(__fmul_rn(pq_fold8(pq_part + 8 * pstride + i, pstride), blobH[P.approx.M * P.approx.k])));
+                        const float sc = score_map(METRIC, sraw);
                         const int32_t f = cand_ids[i];
-                        const uint8_t *c = fused ? rec + 4 * degree + (size_t)cand_slot[i] * P.g.fused_code_stride : P.approx.codes + (size_t)f * P.approx.code_stride;
-                        const float sc = score_pq_codes_thread<METRIC>(P.approx, blobA, c, blobH, splitm);
                         JV_EMIT(sc, f);
                     }
                 } else if (KIND == KIND_PQ && fused) {
@@ -685,7 +749,7 @@ static int search_smemA_floats(const DataDesc &approx, int pq_smem_m)
     return (pq_smem_m * approx.k + 3) & ~3;
 }
 
-static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, int rerankK, int list_alloc, int pq_smem_m, int vis_slots_log = 0)
+static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, int rerankK, int list_alloc, int pq_smem_m, int vis_slots_log = 0, int pq_rows_degree = 0)
 {
     size_t b = (size_t)search_smemA_floats(approx, pq_smem_m) * 4;
     if (rerank) b += (size_t)blob_floats(*rerank) * 4;
@@ -696,14 +760,15 @@ static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, 
     b += (size_t)list_alloc * 2;                      // entry flags of the two buffers
     b = (b + 15) & ~(size_t)15;
     if (vis_slots_log) b += (size_t)2 << vis_slots_log;  // visited set, 16 bits per slot
-    return b;
+    if (pq_rows_degree) b += (size_t)pq_rows_degree * ((approx.code_stride >> 2) + 1) * 4 + (size_t)16 * ((pq_rows_degree + 31) & ~31) * 4;  // staged codes + partial sums
+    return (b + 15) & ~(size_t)15;
 }
 
 #ifndef JV_VISITED_SMEM_DEFAULT
 #define JV_VISITED_SMEM_DEFAULT true
 #endif
-#ifndef JV_PQ_THREAD_DEFAULT
-#define JV_PQ_THREAD_DEFAULT 0
+#ifndef JV_PQ_ROWS_DEFAULT
+#define JV_PQ_ROWS_DEFAULT 1
 #endif
 #ifndef JV_SEARCH_MINB_PQ_WIDE
 #define JV_SEARCH_MINB_PQ_WIDE 4
@@ -711,26 +776,33 @@ static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, 
 #ifndef JV_ROW_PREFETCH_DEFAULT
 #define JV_ROW_PREFETCH_DEFAULT 1
 #endif
+#ifndef JV_SEARCH_MINB_ROWS
+#define JV_SEARCH_MINB_ROWS 8
+#endif
+#ifndef JV_SEARCH_MINB_ROWS_WIDE
+#define JV_SEARCH_MINB_ROWS_WIDE 8
+#endif
 constexpr int MINB_DEFAULT = JV_SEARCH_MINB, MINB_PQ_LITE = JV_SEARCH_MINB_PQ, MINB_PQ_WIDE = JV_SEARCH_MINB_PQ_WIDE;
+constexpr int MINB_ROWS = JV_SEARCH_MINB_ROWS, MINB_ROWS_WIDE = JV_SEARCH_MINB_ROWS_WIDE;  // fp32 / NVQ walks (64 registers at 128 threads: 8 CTAs per SM; measured 9 x 56 registers: 14.24 ms, 8 x 64: 13.84 ms on c2)
 
 template <int KIND, int METRIC, int MINB, bool VSM>
 static cudaError_t occupancy_of(size_t smem, int *blocks_per_sm)
 {
     cudaError_t e = cudaFuncSetAttribute(graph_search_kernel<KIND, METRIC, MINB, VSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, graph_search_kernel<KIND, METRIC, MINB, VSM>, SEARCH_THREADS, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, graph_search_kernel<KIND, METRIC, MINB, VSM>, SearchThreads<KIND>::value, smem);
 }
 
 #define JV_SEARCH_DISPATCH_V(kind, metric, pq_wide, V, CALL)                                                  \
     do {                                                                                        \
         if ((kind) == KIND_F32 && (pq_wide)) {                                                  \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN, MINB_PQ_WIDE, V); } \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT, MINB_PQ_WIDE, V); } \
-            else { CALL(KIND_F32, JV_METRIC_COSINE, MINB_PQ_WIDE, V); }                            \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN, MINB_ROWS_WIDE, V); } \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT, MINB_ROWS_WIDE, V); } \
+            else { CALL(KIND_F32, JV_METRIC_COSINE, MINB_ROWS_WIDE, V); }                            \
         } else if ((kind) == KIND_F32) {                                                        \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN, MINB_DEFAULT, V); }       \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT, MINB_DEFAULT, V); }              \
-            else { CALL(KIND_F32, JV_METRIC_COSINE, MINB_DEFAULT, V); }                                          \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_F32, JV_METRIC_EUCLIDEAN, MINB_ROWS, V); }       \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_F32, JV_METRIC_DOT, MINB_ROWS, V); }              \
+            else { CALL(KIND_F32, JV_METRIC_COSINE, MINB_ROWS, V); }                                          \
         } else if ((kind) == KIND_PQ && (pq_wide)) {                                            \
             if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_PQ, JV_METRIC_EUCLIDEAN, MINB_PQ_WIDE, V); } \
             else if ((metric) == JV_METRIC_DOT) { CALL(KIND_PQ, JV_METRIC_DOT, MINB_PQ_WIDE, V); } \
@@ -744,9 +816,9 @@ static cudaError_t occupancy_of(size_t smem, int *blocks_per_sm)
             else if ((metric) == JV_METRIC_DOT) { CALL(KIND_BQ, JV_METRIC_DOT, MINB_DEFAULT, V); }               \
             else { CALL(KIND_BQ, JV_METRIC_COSINE, MINB_DEFAULT, V); }                                           \
         } else {                                                                                \
-            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_NVQ, JV_METRIC_EUCLIDEAN, MINB_DEFAULT, V); }       \
-            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_NVQ, JV_METRIC_DOT, MINB_DEFAULT, V); }              \
-            else { CALL(KIND_NVQ, JV_METRIC_COSINE, MINB_DEFAULT, V); }                                          \
+            if ((metric) == JV_METRIC_EUCLIDEAN) { CALL(KIND_NVQ, JV_METRIC_EUCLIDEAN, MINB_ROWS, V); }       \
+            else if ((metric) == JV_METRIC_DOT) { CALL(KIND_NVQ, JV_METRIC_DOT, MINB_ROWS, V); }              \
+            else { CALL(KIND_NVQ, JV_METRIC_COSINE, MINB_ROWS, V); }                                          \
         }                                                                                       \
     } while (0)
 #define JV_SEARCH_DISPATCH(kind, metric, pq_wide, vsm, CALL)                    \
@@ -759,7 +831,7 @@ cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const Gr
                         int visited_cap_hint, int list_cap_hint, int sm_count, SearchPlan *plan)
 {
     if (g.degree > MAX_DEGREE || rerankK < 1 || topK < 1 || topK > rerankK) return cudaErrorInvalidValue;
-    plan->threads = SEARCH_THREADS;
+    plan->threads = search_threads_of(approx.kind);
     plan->sort_pow2 = next_pow2i(rerankK);
     // The list keeps rerankK entries plus a tie tail (see the kernel header). Continuous scores tie rarely: the slack that
     // rounds rerankK up to a multiple of 32 is enough; BQ scores take at most dim + 1 values, so whole groups tie at the
@@ -789,11 +861,18 @@ cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const Gr
         plan->blob_in_global = plan->pq_smem_m < approx.M ? 1 : 0;
     }
     plan->blob_floats = blob_floats(approx);
-    plan->smem_bytes = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, plan->pq_smem_m);
+    // PQ scoring layout of a hop: JV_PQ_SCORE=rows (lane = candidate, warp = partial sum) | group (8 lanes per candidate)
+    plan->pq_rows = 0;
+    if (approx.kind == KIND_PQ) {
+        const char *pt = getenv("JV_PQ_SCORE");
+        plan->pq_rows = pt ? (pt[0] == 'r') : JV_PQ_ROWS_DEFAULT;
+    }
+    const int prd = plan->pq_rows ? g.degree : 0;
+    plan->smem_bytes = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, plan->pq_smem_m, 0, prd);
     if (plan->smem_bytes > 227 * 1024 && approx.kind == KIND_PQ && plan->pq_smem_m > 0) {
         plan->pq_smem_m = 0;  // a long list next to a LUT: keep the list in shared memory, move the whole LUT to L2
         plan->blob_in_global = 1;
-        plan->smem_bytes = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, 0);
+        plan->smem_bytes = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, 0, 0, prd);
     }
     if (plan->smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
     int vcap = visited_cap_hint > 0 ? visited_cap_hint : next_pow2i(4 * rerankK * (g.degree > 16 ? g.degree : 16));
@@ -822,7 +901,7 @@ cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const Gr
         const int rlog = slog - (bits - 15);
         const bool want = vm ? vm[0] == 's' : JV_VISITED_SMEM_DEFAULT;
         if (want && visited_cap_hint <= 0 && slog >= 10 && slog <= 14 && rlog >= 5) {
-            const size_t sb = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, plan->pq_smem_m, slog);
+            const size_t sb = search_smem_bytes(approx, rerank, rerankK, plan->list_alloc, plan->pq_smem_m, slog, prd);
             if (sb <= 227 * 1024) {
                 plan->vis_slots_log = slog;
                 plan->vis_rlog = rlog;
@@ -930,9 +1009,12 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
     P.vis_rlog = plan.vis_rlog;
     P.vis_idmask = plan.vis_idmask;
     P.row_prefetch = plan.row_prefetch;
+    P.pq_rows = plan.pq_rows;
     {
-        const char *pt = getenv("JV_PQ_SCORE");  // thread | group
-        P.pq_thread = pt ? (pt[0] == 't') : JV_PQ_THREAD_DEFAULT;
+        // on for the latency-bound walks (PQ / BQ: c3 12.0 -> 11.5 ms); off where HBM is already saturated and a wasted adjacency
+        // line costs more than an early one saves (fp32 / NVQ: c2 13.8 vs 14.0 ms). JV_EARLY_PREFETCH=0|1 overrides.
+        const char *ep = getenv("JV_EARLY_PREFETCH");
+        P.early_pf = ep ? atoi(ep) : ((approx.kind == KIND_PQ || approx.kind == KIND_BQ) ? 1 : 0);
     }
     if (plan.blob_in_global) {
         size_t off = ((plan.vis_slots_log ? 256 : (size_t)plan.ctas * plan.visited_cap * sizeof(int32_t)) + 255) & ~(size_t)255;
@@ -950,7 +1032,7 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
 #define CALL(K, M, B, V)                                                                                                              \
     do {                                                                                                                              \
         e = cudaFuncSetAttribute(graph_search_kernel<K, M, B, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes); \
-        if (e == cudaSuccess) graph_search_kernel<K, M, B, V><<<plan.ctas, SEARCH_THREADS, plan.smem_bytes, s>>>(P);                  \
+        if (e == cudaSuccess) graph_search_kernel<K, M, B, V><<<plan.ctas, SearchThreads<K>::value, plan.smem_bytes, s>>>(P);               \
     } while (0)
     JV_SEARCH_DISPATCH(approx.kind, metric, plan.pq_wide != 0, plan.vis_slots_log != 0, CALL);
 #undef CALL

@@ -911,6 +911,49 @@ def test_search_visited_table_overflow_retry(jv, oracle):
     gi.close()
 
 
+def test_search_visited_set_in_shared_memory_is_exact(jv, oracle):
+    # The walk keeps its visited set in shared memory as 16-bit tags inside per-id-range regions (search.cu visited_insert_smem):
+    # it must behave exactly like a set. Same traversal as the oracle (i) on the default table, (ii) on the global-memory table,
+    # (iii) with a table so small (1024 slots) that every query outgrows it and is re-run on the global table, (iv) on a graph
+    # with many nodes (2^21 ids: 64 regions) where ids differ only in their high bits.
+    import os
+    rng = np.random.default_rng(77)
+    n, dim, degree = 30000, 24, 32
+    data = o.random_unit_vectors(rng, n, dim)
+    queries = o.random_unit_vectors(rng, 32, dim)
+    adj = rng.integers(0, n, (n, degree)).astype(np.int32)
+    adj[adj == np.arange(n)[:, None]] = 0
+    g = o.make_graph(adj, 7)
+    gi = jv.GraphIndex(adj, 7)
+    vec = jv.F32Vectors(data)
+    want = _oracle_search(oracle, g, lambda q: oracle.jvo_scorer_f32(o.DOT_PRODUCT, fp(data), n, dim, fp(q)), queries, 10, 60)
+    for env, must_retry in (({}, False), ({"JV_VISITED": "global"}, False), ({"JV_VISITED": "smem", "JV_VISITED_SMEM_SLOTS": "1024"}, True)):
+        os.environ.update(env)
+        try:
+            res = jv.GraphSearcher(gi).search(vec, queries, o.DOT_PRODUCT, 10, 60)
+        finally:
+            for k in env:
+                del os.environ[k]
+        _assert_same_search(res, want, "visited set %r" % (env,))
+        assert res.retried > 0 or not must_retry, (env, res.retried)
+    vec.close()
+    gi.close()
+    # (iv) 2^21 nodes, 8 dimensions: neighbours are id +- multiples of 2^15, 2^16 ... so tags collide unless the region bits work
+    n2, dim2 = 1 << 21, 8
+    data2 = o.random_unit_vectors(rng, n2, dim2)
+    strides = np.array([1 << 15, 1 << 16, 1 << 17, 3 << 15, 5 << 15, 1 << 20, 7, 1], np.int64)
+    adj2 = ((np.arange(n2, dtype=np.int64)[:, None] + np.concatenate([strides, -strides])[None, :]) % n2).astype(np.int32)
+    g2 = o.make_graph(adj2, 11)
+    gi2 = jv.GraphIndex(adj2, 11)
+    vec2 = jv.F32Vectors(data2)
+    q2 = o.random_unit_vectors(rng, 8, dim2)
+    res = jv.GraphSearcher(gi2).search(vec2, q2, o.DOT_PRODUCT, 10, 80)
+    want = _oracle_search(oracle, g2, lambda q: oracle.jvo_scorer_f32(o.DOT_PRODUCT, fp(data2), n2, dim2, fp(q)), q2, 10, 80)
+    _assert_same_search(res, want, "visited set, 2^21 ids")
+    vec2.close()
+    gi2.close()
+
+
 def test_topk_multipass_on_adversarial_layout(jv, oracle):
     # n > 16384 takes the sampled-threshold path. Put LOW scores exactly on the strided sample positions and near-equal HIGH
     # scores everywhere else: the sample thresholds are then far too low, the candidate buffer overflows, and the exact

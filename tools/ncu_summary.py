@@ -90,7 +90,7 @@ for r in rows[2:]:
     if len(r) > ci:
         op = r[ci].strip().split(" ")[0].lstrip("@!P0123456789 ").split(".")[0]
         s_ = r[ci]
-        for key in ("UBLKCP", "SYNCS", "POPC", "LDG", "ATOMG", "ATOMS", "SHFL", "UTMALDG", "CCTL"):
+        for key in ("UBLKPF", "UBLKCP", "SYNCS", "POPC", "LDG", "ATOMG", "ATOMS", "SHFL", "UTMALDG", "CCTL"):
             if key in s_:
                 mn.add(key)
 print("\nSASS mnemonics present: " + ", ".join(sorted(mn)))
