@@ -74,6 +74,19 @@ struct ThreadCtx {
     void *dbuf[SLOTS] = {};
     size_t dcap[SLOTS] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // host-pointer searches: a second stream carries the query chunks while the search kernel already runs (arrival watermark)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr;
+    int *marks_pinned = nullptr;  // pinned: the watermark values the copy stream writes behind each chunk
+    static constexpr int MARKS = 16;
+    int init_copy()
+    {
+        if (copy_stream) return JV_OK;
+        CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), "cudaStreamCreate(copy)");
+        CK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming), "cudaEventCreate(copy)");
+        CK(cudaHostAlloc((void **)&marks_pinned, MARKS * sizeof(int), cudaHostAllocDefault), "cudaHostAlloc(marks)");
+        return JV_OK;
+    }
     int init()
     {
         if (stream) return JV_OK;
@@ -106,6 +119,13 @@ struct ThreadCtx {
         cudaEventDestroy(ev0);
         cudaEventDestroy(ev1);
         cudaStreamDestroy(stream);
+        if (copy_stream) {
+            cudaStreamSynchronize(copy_stream);
+            cudaStreamDestroy(copy_stream);
+            cudaEventDestroy(ev_copy);
+            cudaFreeHost(marks_pinned);
+            copy_stream = nullptr;
+        }
         stream = nullptr;
         if (cur >= 0) cudaSetDevice(cur);
     }
@@ -1198,8 +1218,44 @@ int jv_graph_search_batch_ex(jv_graph g, jv_dataset approx, jv_dataset reranker,
     SearchFilter f;
     bool use;
     if ((rc = make_filter(opts, g, nq, false, &f, &use))) return rc;
-    CK(cudaMemcpyAsync(t_ctx.dbuf[0], queries, qb, cudaMemcpyHostToDevice, s), "H2D queries");
-    rc = search_device(g, approx, reranker, metric, (const float *)t_ctx.dbuf[0], nq, topK, rerankK, use ? &f : nullptr, (int32_t *)t_ctx.dbuf[1], (float *)t_ctx.dbuf[2], stats);
+    // Large batches: the queries travel in chunks on a second stream, each followed by a 4-byte watermark ("queries [0, w) have
+    // arrived"), and the search kernel — launched at once — takes query i only when the watermark has passed it. The H2D copy
+    // (30 MB at c2) hides behind the first wave of queries instead of preceding the kernel. JV_SEARCH_OVERLAP=0 disables.
+    const char *ov = getenv("JV_SEARCH_OVERLAP");
+    const bool overlap = qb >= ((size_t)1 << 20) && nq >= 64 && !(ov && ov[0] == '0');
+    if (overlap) {
+        if ((rc = t_ctx.init_copy()) || (rc = t_ctx.ensure(7, 256))) return rc;
+        int *arrived = (int *)t_ctx.dbuf[7];
+        CK(cudaMemsetAsync(arrived, 0, sizeof(int), s), "memset watermark");
+        CK(cudaEventRecord(t_ctx.ev_copy, s), "event");
+        cudaStream_t s2 = t_ctx.copy_stream;
+        CK(cudaStreamSynchronize(s2), "copy stream");  // the pinned watermark values of the previous call are free again
+        CK(cudaStreamWaitEvent(s2, t_ctx.ev_copy, 0), "wait");
+        const int chunks = ThreadCtx::MARKS;
+        const size_t row = (size_t)approx->d.dim * 4;
+        for (int c = 0; c < chunks; c++) {
+            // first chunk small (one kernel wave starts as early as possible), the rest equal. Boundaries are multiples of 32 queries:
+            // 32 rows of 4 * dim bytes end on a 128-byte line, so no cache line holds queries of two chunks (a kernel that has read
+            // the last query of a chunk can never hold a stale L1 copy of the first bytes of the next one)
+            auto bound = [&](int c_) -> long long {
+                if (c_ <= 0) return 0;
+                if (c_ >= chunks) return nq;
+                const long long rest = nq > 2048 ? nq - 2048 : 0;
+                const long long b = 2048 + rest * (c_ - 1) / (chunks - 1);
+                return std::min<long long>(nq, b & ~31ll);
+            };
+            const long long lo = bound(c), hi = bound(c + 1);
+            if (hi <= lo) continue;
+            CK(cudaMemcpyAsync((char *)t_ctx.dbuf[0] + (size_t)lo * row, (const char *)queries + (size_t)lo * row, (size_t)(hi - lo) * row, cudaMemcpyHostToDevice, s2), "H2D queries");
+            t_ctx.marks_pinned[c] = (int)hi;
+            CK(cudaMemcpyAsync(arrived, &t_ctx.marks_pinned[c], sizeof(int), cudaMemcpyHostToDevice, s2), "H2D watermark");
+        }
+        f.arrived = arrived;
+        rc = search_device(g, approx, reranker, metric, (const float *)t_ctx.dbuf[0], nq, topK, rerankK, &f, (int32_t *)t_ctx.dbuf[1], (float *)t_ctx.dbuf[2], stats);
+    } else {
+        CK(cudaMemcpyAsync(t_ctx.dbuf[0], queries, qb, cudaMemcpyHostToDevice, s), "H2D queries");
+        rc = search_device(g, approx, reranker, metric, (const float *)t_ctx.dbuf[0], nq, topK, rerankK, use ? &f : nullptr, (int32_t *)t_ctx.dbuf[1], (float *)t_ctx.dbuf[2], stats);
+    }
     if (rc) return rc;
     CK(cudaMemcpyAsync(nodes_out, t_ctx.dbuf[1], ob, cudaMemcpyDeviceToHost, s), "D2H nodes");
     CK(cudaMemcpyAsync(scores_out, t_ctx.dbuf[2], ob, cudaMemcpyDeviceToHost, s), "D2H scores");

@@ -117,6 +117,7 @@ struct SearchFilter {
     float threshold;                // minimum approximate score of a result; 0 = none
     float rerank_floor;             // NodeQueue.rerank's rerankFloor; 0 = none
     int lenient;                    // builder only: overflowing walks are cut short and counted instead of failing
+    const int *arrived;             // device int or nullptr: queries [0, *arrived) are in place (host-pointer searches overlap the H2D copy)
 };
 cudaError_t plan_search(const DataDesc &approx, const DataDesc *rerank, const GraphDesc &g, int topK, int rerankK, int nq,
                         int visited_cap_hint, int list_cap_hint, int sm_count, SearchPlan *plan);

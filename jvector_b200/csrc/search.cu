@@ -54,6 +54,7 @@ struct SearchParams {
     long long accept_stride;      // words between two queries' bitsets (0 = one bitset shared by the batch)
     float threshold, rerank_floor;
     int filtered;                 // accept_bits != nullptr || threshold > 0
+    const int *arrived;           // nullptr, or: query i may be read only once *arrived > i (the H2D copy is still running)
     int lenient;                  // insert searches of the builder: a full visited table ends the walk with what it has, a tie tail
                                   // that does not fit is dropped — counted in counters->overflowed, never an error (build.cu)
     // visited set in shared memory (plan_search decides): 2^vis_slots_log 16-bit slots split into 2^(vis_bits-15) regions; 0 = the
@@ -250,7 +251,15 @@ __global__ void __launch_bounds__(SearchThreads<KIND>::value, MINB) graph_search
     const int degree = P.g.degree;
 
     for (;;) {
-        if (tid == 0) s_q = atomicAdd(P.work_counter, 1);
+        if (tid == 0) {
+            const int w = atomicAdd(P.work_counter, 1);
+            if (P.arrived && w < P.nq) {
+                // the batch is still being copied in (api.cu jv_graph_search_batch_ex): wait until the watermark has passed this query
+                const int need = P.query_index ? P.query_index[w] : w;
+                while (*reinterpret_cast<const volatile int *>(P.arrived) <= need) __nanosleep(200);
+            }
+            s_q = w;
+        }
         __syncthreads();
         const int wq = s_q;
         if (wq >= P.nq) break;
@@ -971,6 +980,7 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
     P.rerank_floor = filter ? filter->rerank_floor : 0.f;
     P.filtered = (P.accept_bits != nullptr || P.threshold > 0.f) ? 1 : 0;
     P.lenient = filter ? filter->lenient : 0;
+    P.arrived = filter ? filter->arrived : nullptr;
     P.query_stride = query_stride > 0 ? query_stride : approx.dim;
     P.g = g;
     if (!(approx.kind == KIND_PQ && g.fused && g.fused_codes_of == approx.codes && g.fused_code_stride == approx.code_stride)) P.g.fused = nullptr;

@@ -954,6 +954,39 @@ def test_search_visited_set_in_shared_memory_is_exact(jv, oracle):
     gi2.close()
 
 
+def test_host_pointer_search_overlaps_the_query_copy(jv, oracle):
+    # jv_graph_search_batch with host buffers: batches of >= 1 MB travel in chunks behind an arrival watermark while the kernel
+    # already runs (api.cu). Same answers as the plain path (JV_SEARCH_OVERLAP=0) and as the oracle; dim = 100 makes adjacent
+    # queries share cache lines, nq is not a multiple of the chunk alignment.
+    import os
+    rng = np.random.default_rng(99)
+    n, dim, nq = 20000, 100, 4099
+    data = o.random_unit_vectors(rng, n, dim)
+    queries = o.random_unit_vectors(rng, nq, dim)
+    vec = jv.F32Vectors(data)
+    gi = jv.GraphIndexBuilder(o.DOT_PRODUCT, M=16, beamWidth=40).build(vec)
+    s = jv.GraphSearcher(gi)
+    a = s.search(vec, queries, o.DOT_PRODUCT, 10, 30)
+    os.environ["JV_SEARCH_OVERLAP"] = "0"
+    try:
+        b = s.search(vec, queries, o.DOT_PRODUCT, 10, 30)
+    finally:
+        del os.environ["JV_SEARCH_OVERLAP"]
+    assert np.array_equal(a.nodes, b.nodes) and np.array_equal(a.scores.view(np.int32), b.scores.view(np.int32))
+    assert a.visitedCount == b.visitedCount
+    for _ in range(3):  # repeated calls reuse the copy stream and the pinned watermark slots
+        c = s.search(vec, queries, o.DOT_PRODUCT, 10, 30)
+        assert np.array_equal(a.nodes, c.nodes)
+    _, adj = gi.level(0)
+    info = gi.info()
+    if info["levels"] == 1:
+        g = o.make_graph(adj, info["entry_node"])
+        want = _oracle_search(oracle, g, lambda q: oracle.jvo_scorer_f32(o.DOT_PRODUCT, fp(data), n, dim, fp(q)), queries[-16:], 10, 30)
+        assert np.array_equal(a.nodes[-16:], want[0])
+    vec.close()
+    gi.close()
+
+
 def test_topk_multipass_on_adversarial_layout(jv, oracle):
     # n > 16384 takes the sampled-threshold path. Put LOW scores exactly on the strided sample positions and near-equal HIGH
     # scores everywhere else: the sample thresholds are then far too low, the candidate buffer overflows, and the exact

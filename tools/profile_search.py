@@ -27,6 +27,7 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--smem-m", default="0,24,32,48,64,96")
 ap.add_argument("--envs", default="", help="';'-separated settings, each 'A=1,B=2' (empty = defaults): every workload is timed under each")
 ap.add_argument("--workloads", default="", help="comma list of c2,c3 for --envs")
+ap.add_argument("--sustain", type=float, default=0.0, help="seconds of back-to-back launches before the timed reps (power-capped steady state, like bench.py); reports the MEAN of the reps")
 ap.add_argument("--ncu", action="store_true", help="bracket the timed launches with cudaProfilerStart/Stop (ncu --profile-from-start off)")
 a = ap.parse_args()
 
@@ -42,6 +43,19 @@ def run(approx, rr, label):
     if a.ncu:
         s.search(approx, w.queries, VSF.DOT_PRODUCT, 10, 100, reranker=rr)  # warm-up outside the profiled range
         cx.torch.cuda.cudart().cudaProfilerStart()
+    if a.sustain > 0:
+        import subprocess
+        import time
+        t0 = time.time()
+        while time.time() - t0 < a.sustain:
+            s.search(approx, w.queries, VSF.DOT_PRODUCT, 10, 100, reranker=rr)
+        ms = []
+        for _ in range(a.reps):
+            best = s.search(approx, w.queries, VSF.DOT_PRODUCT, 10, 100, reranker=rr)
+            ms.append(best.device_ms)
+        smi = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.mem,power.draw", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+        print("%-44s sustained mean %8.3f ms (min %.3f max %.3f) qps %9.0f  [%s]" % (label, sum(ms) / len(ms), min(ms), max(ms), a.nq / (sum(ms) / len(ms) / 1e3), smi), flush=True)
+        return best
     for _ in range(a.reps):
         r = s.search(approx, w.queries, VSF.DOT_PRODUCT, 10, 100, reranker=rr)
         best = r if best is None or r.device_ms < best.device_ms else best
