@@ -1024,7 +1024,8 @@ cudaError_t launch_search(const GraphDesc &g, const DataDesc &approx, const Data
         // on for the latency-bound walks (PQ / BQ: c3 12.0 -> 11.5 ms); off where HBM is already saturated and a wasted adjacency
         // line costs more than an early one saves (fp32 / NVQ: c2 13.8 vs 14.0 ms). JV_EARLY_PREFETCH=0|1 overrides.
         const char *ep = getenv("JV_EARLY_PREFETCH");
-        P.early_pf = ep ? atoi(ep) : ((approx.kind == KIND_PQ || approx.kind == KIND_BQ) ? 1 : 0);
+        // (a batch that does not fill the GPU is latency bound whatever the scorer: on as well)
+        P.early_pf = ep ? atoi(ep) : ((approx.kind == KIND_PQ || approx.kind == KIND_BQ || nq <= plan.ctas) ? 1 : 0);
     }
     if (plan.blob_in_global) {
         size_t off = ((plan.vis_slots_log ? 256 : (size_t)plan.ctas * plan.visited_cap * sizeof(int32_t)) + 255) & ~(size_t)255;
