@@ -92,7 +92,14 @@ __device__ __forceinline__ bool visited_insert_smem(unsigned short *t, unsigned 
     unsigned short *base = t + ((size_t)(x >> 15) << rlog);
     unsigned h = (tag * 0x9E3779B1u) >> (32 - rlog);
     for (unsigned probes = 0; probes <= rmask; ++probes) {
+#ifdef JV_VIS_CAS_GENERIC
         const unsigned short old = atomicCAS(&base[h], (unsigned short)0, val);
+#else
+        // explicit .shared state space: a 16-bit CAS is an LDS + 32-bit ATOMS.CAS loop on the containing word; through a generic
+        // pointer (atomicCAS on unsigned short *) the compiler emits the slower generic ATOM.E.CAS
+        unsigned short old;
+        asm volatile("atom.shared.cas.b16 %0, [%1], %2, %3;" : "=h"(old) : "r"(smem_u32(base + h)), "h"((unsigned short)0), "h"(val) : "memory");
+#endif
         if (old == 0) return true;
         if (old == val) return false;
         h = (h + 1) & rmask;
@@ -786,13 +793,13 @@ static size_t search_smem_bytes(const DataDesc &approx, const DataDesc *rerank, 
 #define JV_ROW_PREFETCH_DEFAULT 1
 #endif
 #ifndef JV_SEARCH_MINB_ROWS
-#define JV_SEARCH_MINB_ROWS 8
+#define JV_SEARCH_MINB_ROWS 9
 #endif
 #ifndef JV_SEARCH_MINB_ROWS_WIDE
 #define JV_SEARCH_MINB_ROWS_WIDE 8
 #endif
 constexpr int MINB_DEFAULT = JV_SEARCH_MINB, MINB_PQ_LITE = JV_SEARCH_MINB_PQ, MINB_PQ_WIDE = JV_SEARCH_MINB_PQ_WIDE;
-constexpr int MINB_ROWS = JV_SEARCH_MINB_ROWS, MINB_ROWS_WIDE = JV_SEARCH_MINB_ROWS_WIDE;  // fp32 / NVQ walks (64 registers at 128 threads: 8 CTAs per SM; measured 9 x 56 registers: 14.24 ms, 8 x 64: 13.84 ms on c2)
+constexpr int MINB_ROWS = JV_SEARCH_MINB_ROWS, MINB_ROWS_WIDE = JV_SEARCH_MINB_ROWS_WIDE;  // fp32 / NVQ walks (56 registers at 128 threads, 9 CTAs per SM. c2, burst: 9 x 56 registers 14.24 ms, 8 x 64 registers 13.84 ms; sustained under the 1000 W cap — what bench.py times — 14.2 ms vs 14.8 ms: 9 x 56 ships)
 
 template <int KIND, int METRIC, int MINB, bool VSM>
 static cudaError_t occupancy_of(size_t smem, int *blocks_per_sm)
