@@ -153,3 +153,68 @@ def search(graph_levels, entry_node, score_fn, topK, rerankK, list_cap, rerank_f
                 heap_down(rh, len(rh) - 1, 1)
         keys = sorted(rh[1:], reverse=True)
     return [key_node(k) for k in keys], [key_score(k) for k in keys], visited, nrr
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# The visited set of the walk in shared memory (search.cu visited_insert_smem + the sizing rule of plan_search): 16-bit slots,
+# region = high bits of a bijective hash of the id, tag = its low 15 bits, probes never leave their region.
+# ------------------------------------------------------------------------------------------------------------------------
+VIS_MUL = 0x9E3779B1
+
+
+def visited_smem_plan(n, visited_cap, slots_env=None):
+    """(slots_log, region_log, id_mask) as plan_search chooses them, or None when the walk keeps the global table"""
+    bits = 15
+    while (1 << bits) < n:
+        bits += 1
+    slots = slots_env if slots_env else visited_cap // 2
+    slog = 0
+    while (1 << slog) < slots:
+        slog += 1
+    while not slots_env and slog - (bits - 15) < 7 and slog < 14:
+        slog += 1
+    rlog = slog - (bits - 15)
+    if slog < 10 or slog > 14 or rlog < 5:
+        return None
+    return slog, rlog, (1 << bits) - 1
+
+
+class VisitedSmem:
+    def __init__(self, slog, rlog, idmask):
+        self.t = np.zeros(1 << slog, np.uint16)
+        self.rlog, self.idmask = rlog, idmask
+        self.failed = False
+
+    def insert(self, v):
+        """True = new (visited.add() returned true), False = seen before (or the region is full: self.failed)"""
+        x = (int(v) * VIS_MUL) & 0xffffffff & self.idmask
+        tag = x & 0x7fff
+        val = tag | 0x8000
+        rmask = (1 << self.rlog) - 1
+        base = (x >> 15) << self.rlog
+        h = ((tag * VIS_MUL) & 0xffffffff) >> (32 - self.rlog)
+        for _ in range(rmask + 1):
+            old = int(self.t[base + h])
+            if old == 0:
+                self.t[base + h] = val
+                return True
+            if old == val:
+                return False
+            h = (h + 1) & rmask
+        self.failed = True
+        return False
+
+
+def pq_group_sum8(parts):
+    """group_sum<8> of common.cuh on one candidate's 8 lane sums: xor butterfly 4, 2, 1 in float32; returns lane 0's value"""
+    v = [np.float32(p) for p in parts]
+    for o in (4, 2, 1):
+        v = [np.float32(v[i] + v[i ^ o]) for i in range(8)]
+    return v
+
+
+def pq_fold8(parts):
+    """pq_fold8 of scorers.cuh: the same tree written out for one thread"""
+    p = [np.float32(x) for x in parts]
+    f = np.float32
+    return f(f(f(p[0] + p[4]) + f(p[2] + p[6])) + f(f(p[1] + p[5]) + f(p[3] + p[7])))

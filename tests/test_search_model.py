@@ -107,3 +107,45 @@ def test_list_model_equals_two_heap_reference(oracle, world, hier, kind):
                 oracle.jvo_scorer_free(rr)
     if kind == "bq":
         assert total_retries > 0, "tie tails were expected to overflow the tight list at least once"
+
+
+def test_visited_set_in_shared_memory_model_is_an_exact_set():
+    # the shared-memory visited set (search.cu visited_insert_smem) must behave exactly like a set of ids: the id -> (region, tag)
+    # map is a bijection, so two different ids never look alike; checked at the sizes plan_search picks for 30k, 1M, 2^21 and 10M
+    # nodes, with id streams that collide in their low bits, their high bits, and at random
+    rng = np.random.default_rng(5)
+    for n, cap in ((30_000, 8192), (1_000_000, 16384), (1 << 21, 8192), (10_000_000, 16384)):
+        plan = sm.visited_smem_plan(n, cap)
+        assert plan is not None, n
+        slog, rlog, idmask = plan
+        # bijection of id -> x on [0, 2^bits): multiplication by an odd constant modulo a power of two
+        probe = np.unique(np.concatenate([rng.integers(0, n, 200_000), np.arange(min(n, 70_000)), n - 1 - np.arange(min(n, 70_000))]))
+        x = (probe.astype(np.uint64) * np.uint64(sm.VIS_MUL)) & np.uint64(idmask)
+        assert len(np.unique(x)) == len(probe)
+        limit = 3 * (1 << slog) // 4
+        streams = [rng.integers(0, n, 3000),
+                   (rng.integers(0, 8, 3000) << 15) % n,                                  # ids that differ only above bit 15
+                   (7 + (np.arange(3000, dtype=np.int64) << 12)) % n,                       # same low 12 bits
+                   np.repeat(rng.integers(0, n, 500), 6)]                                  # every id six times
+        for ids in streams:
+            vs, seen = sm.VisitedSmem(slog, rlog, idmask), set()
+            for v in ids[:limit]:
+                new = vs.insert(v)
+                if vs.failed:
+                    break  # a full region: the kernel re-runs the query on the global table, never answers from this one
+                assert new == (int(v) not in seen), (n, int(v))
+                seen.add(int(v))
+    # beyond 2^24 nodes (regions would fall under 32 slots) and for beams whose table would not fit 32 KB the global table stays
+    assert sm.visited_smem_plan(1 << 26, 16384) is None
+    assert sm.visited_smem_plan(1_000_000, 1 << 17) is None
+
+
+def test_pq_partial_sums_fold_like_the_butterfly():
+    # score_pq_partial / pq_fold8 (one warp per partial sum, one thread folds) must give the bits of the 8-lane xor butterfly
+    rng = np.random.default_rng(6)
+    for _ in range(2000):
+        parts = (rng.standard_normal(8) * 10.0 ** rng.integers(-3, 4)).astype(np.float32)
+        lanes = sm.pq_group_sum8(parts)
+        want = lanes[0]
+        assert all(np.float32(v).view(np.int32) == np.float32(want).view(np.int32) for v in lanes)  # every lane ends with the same bits
+        assert sm.pq_fold8(parts).view(np.int32) == np.float32(want).view(np.int32)
