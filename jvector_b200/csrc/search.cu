@@ -2,19 +2,19 @@
 // (base:graph/GraphSearcher.java:263-282 internalSearch, :334-353 initializeInternal, :355-370 stopSearch,
 //  :406-457 searchOneLayer, :471-507 reranking; neighbour loop base:graph/OnHeapGraphIndex.java:475-483).
 //
-// State per query, all in shared memory except the visited set:
-//   * ONE list sorted by the reference's 64-bit key holding the best `rerankK` nodes SEEN so far, each with an
-//     "expanded" flag. The reference keeps a max-heap of unexpanded candidates plus a bounded min-heap of the best
-//     rerankK expanded ones and stops when |results| >= rerankK and best candidate < worst result; that is exactly
-//     "the first unexpanded entry of the merged sorted list lies at position >= rerankK" (a node outside the best
-//     rerankK seen can never be expanded before the stop condition fires, and the list only tightens). Exact up to
-//     score ties at the list boundary (the reference expands an equal-score candidate once more).
-//   * upper levels run with window K = 1 over the same list; moving down a level clears the expanded flags, which is
-//     setEntryPointsFromPreviousLayer (results + evicted + remaining candidates all become candidates again).
-//   * visited = open-addressing hash set in a per-CTA slice of global scratch (L2 resident), never cleared between
-//     levels (GraphSearcher keeps `visited` across levels).
-// Every hop is: read one adjacency row -> filter through visited -> score the survivors with the row scorers of
-// scorers.cuh (one lane group per candidate) -> parallel rank-merge into the list.
+// State per query, all in shared memory (the kernel's own header comment, further down, has the exactness argument):
+//   * ONE list sorted by the reference's 64-bit key holding the nodes SEEN so far that can still matter, each with an
+//     "expanded" and an "accepted" flag; its unexpanded entries are the reference's candidate max-heap in pop order;
+//   * a shadow copy of the reference's bounded result heap (same array, same sift procedures): stopSearch's strict <, the
+//     "tie with the worst result is expanded but not added" rule and NodeQueue.rerank's array order come from it;
+//   * upper levels run with a 1-entry result heap over the same list; moving down a level clears the expanded flags
+//     (setEntryPointsFromPreviousLayer);
+//   * visited = an exact set of node ids, never cleared between levels (GraphSearcher keeps `visited` across levels):
+//     16-bit region-tagged slots in shared memory (visited_insert_smem), or — for graphs / beams the shared-memory table
+//     does not take, and for the re-run of a query that outgrew it — an open-addressing table of 32-bit ids in a per-CTA slice
+//     of global scratch (visited_insert).
+// Every hop is: read one adjacency row (FusedPQ: one record) -> filter through visited, requesting every new row from DRAM
+// with one bulk L2 prefetch -> score the survivors with the row scorers of scorers.cuh -> parallel rank-merge into the list.
 #include <limits.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -179,7 +179,7 @@ __device__ __forceinline__ void heap_down(long long *h, int size, int pos)
 #endif
 // CTA width per walking scorer. fp32 / NVQ rows are scored a warp per row and, with every new row already on its way to L2
 // (bulk prefetch), the walk gains from MORE queries in flight rather than more warps per query: 128 threads, 10 CTAs per SM
-// (c2: 14.7 -> 14.2 ms). PQ / BQ score 8 lanes per candidate and want a hop's ~28 candidates in one pass: 256 threads.
+// (c2: 14.7 -> 14.2 ms). PQ / BQ score a hop's ~28 candidates in one pass over 8 warps (PQ: one warp per partial sum): 256 threads.
 #ifndef JV_SEARCH_THREADS_ROWS
 #define JV_SEARCH_THREADS_ROWS 128
 #endif
@@ -215,6 +215,8 @@ constexpr uint8_t F_ACCEPTED = 2;  // acceptOrds.get(node) && score >= threshold
 //   (setEntryPointsFromPreviousLayer re-queues results + evicted only, GraphSearcher.java:316-323).
 // MINB: resident CTAs per SM the register allocation is capped for. PQ is compiled twice: 6 (40 registers; the L2-LUT mode, where
 // nothing else limits residency) and 4 (64 registers; the modes whose shared-memory LUT part allows at most 4-5 CTAs anyway).
+// VSM: the visited set lives in shared memory (a template parameter, not a run-time flag: the two forms must not cost each other
+// registers — the fp32 walk lost 15 % when they shared one instantiation).
 template <int KIND, int METRIC, int MINB, bool VSM>
 __global__ void __launch_bounds__(SearchThreads<KIND>::value, MINB) graph_search_kernel(SearchParams P)
 {
