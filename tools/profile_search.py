@@ -30,6 +30,10 @@ ap.add_argument("--workloads", default="", help="comma list of c2,c3 for --envs"
 ap.add_argument("--sustain", type=float, default=0.0, help="seconds of back-to-back launches before the timed reps (power-capped steady state, like bench.py); reports the MEAN of the reps")
 ap.add_argument("--ncu", action="store_true", help="bracket the timed launches with cudaProfilerStart/Stop (ncu --profile-from-start off)")
 a = ap.parse_args()
+if a.ncu:
+    # under a profiler the kernel must not wait for copies of another stream (the host-pointer search overlaps its H2D copy with the
+    # kernel behind an arrival watermark; ncu synchronises before a profiled launch, so this is belt and braces)
+    os.environ["JV_SEARCH_OVERLAP"] = "0"
 
 args = argparse.Namespace(impl="b200", n=a.n, dim=768, nq=a.nq, dist="latent", topk=10, gt_queries=500)
 cx = bench.Ctx(args)
