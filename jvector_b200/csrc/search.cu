@@ -265,7 +265,12 @@ __global__ void __launch_bounds__(SearchThreads<KIND>::value, MINB) graph_search
             if (P.arrived && w < P.nq) {
                 // the batch is still being copied in (api.cu jv_graph_search_batch_ex): wait until the watermark has passed this query
                 const int need = P.query_index ? P.query_index[w] : w;
-                while (*reinterpret_cast<const volatile int *>(P.arrived) <= need) __nanosleep(200);
+                // (bounded: ~10 s of waiting for a copy that takes milliseconds means the copy stream died — trap, never hang the GPU)
+                unsigned spins = 0;
+                while (*reinterpret_cast<const volatile int *>(P.arrived) <= need) {
+                    __nanosleep(200);
+                    if (++spins > 50000000u) __trap();
+                }
             }
             s_q = w;
         }
