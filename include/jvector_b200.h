@@ -240,7 +240,10 @@ typedef struct {
 
 /* GraphSearcher.search for nq queries at once: traversal scored by `approx`, optional exact rerank by `reranker`
  * (NULL = none, then rerankK survivors are cut to topK by approximate score as GraphSearcher.java:478-486).
- * nodes_out/scores_out [nq][topK], best first, padded with -1 / 0. */
+ * nodes_out/scores_out [nq][topK], best first, padded with -1 / 0.
+ * Host buffers: a batch of >= 1 MB of queries is copied in chunks on a second stream while the search kernel already runs (each
+ * query is read only after its chunk has arrived), so with pinned (jv_host_register / cudaHostRegister) buffers the H2D copy is
+ * hidden behind the first wave of queries; pageable buffers work and simply copy first. device_ms then includes that overlap. */
 JV_API int jv_graph_search_batch(jv_graph g, jv_dataset approx, jv_dataset reranker, int metric,
                                  const float *queries, int nq, int topK, int rerankK,
                                  int32_t *nodes_out, float *scores_out, jv_search_stats *stats);
